@@ -1,0 +1,207 @@
+/*
+ * b200vlm — C ABI of the B200-native generate path (libb200vlm.so).
+ *
+ * The reference (Blaizzy/mlx-vlm) has NO FFI: its hot path is Python calling the
+ * third-party `mlx` array library.  This header is the boundary a maintainer
+ * would bind instead of `mlx`: every entry point names the reference call site
+ * (file:line under /root/reference/mlx_vlm) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all data pointers are DEVICE pointers unless
+ *     the name ends in `_host`.  Activations / weights are bf16 (uint16 storage),
+ *     indices are int32, pixel values float32.
+ *   - every call enqueues on the caller-supplied `stream` (a cudaStream_t cast to
+ *     void*; NULL = legacy default stream) and returns without synchronising
+ *     unless stated otherwise.
+ *   - return value: B200_OK or an error code; b200_last_error() returns a
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - an engine is not thread-safe (mirrors the reference's single GPU thread,
+ *     server/generation.py:1044-1051); the caller owns every buffer it passes in
+ *     (weights, workspace, KV pool stay referenced until engine destroy).
+ */
+#ifndef B200VLM_H
+#define B200VLM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID 1     /* bad argument / unsupported shape            */
+#define B200_ERR_CUDA 2        /* a CUDA runtime / driver call failed         */
+#define B200_ERR_UNSUPPORTED 3 /* device is not sm_100                        */
+#define B200_ERR_STATE 4       /* engine used before weights / cache bound    */
+
+#define B200_ABI_VERSION 1
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* Fails with B200_ERR_UNSUPPORTED unless `device` is compute capability 10.x. */
+int b200_device_check(int device, int* sm_count);
+
+/* ------------------------------------------------------------------------- */
+/* Op level (each is one kernel launch; used directly by the kernel tests)    */
+/* ------------------------------------------------------------------------- */
+
+/* qwen2_vl.py:44-45  pixel_values.astype(weight dtype) */
+int b200_cast_f32_bf16(const float* src, void* dst, long n, void* stream);
+
+/* epilogues of b200_gemm_bf16_tn */
+#define B200_EPI_NONE 0
+#define B200_EPI_GELU_FAST 1  /* nn.GELU(approx="fast")  vision.py:167          */
+#define B200_EPI_GELU_EXACT 2 /* nn.GELU()               vision.py:112          */
+
+/* nn.Linear / nn.Conv3d(kernel==stride) / Embedding.as_linear:
+ *   C[M,N] = epi( bf16( A[M,K] . W[N,K]^T + bias[N] ) )  then, if residual,
+ *   C = bf16(residual + C).   A row pitch lda, C/residual row pitch ldc/ldr
+ *   (elements).  tcgen05 tensor cores, TMA-fed, fp32 accumulate in TMEM.
+ *   Replaces every nn.Linear in models/qwen2_vl/{vision,language}.py and
+ *   PatchEmbed.proj (vision.py:83-102).  K*2 bytes and lda*2 bytes must be
+ *   multiples of 16. */
+int b200_gemm_bf16_tn(const void* A, long lda, const void* W, const void* bias,
+                      const void* residual, long ldr, void* C, long ldc,
+                      int M, int N, int K, int epilogue, void* stream);
+
+/* mx.fast.layer_norm (vision.py:180-181,108) / mx.fast.rms_norm (language.py:128-131) */
+int b200_layer_norm(const void* x, const void* w, const void* b, void* y,
+                    int rows, int dim, float eps, void* stream);
+int b200_rms_norm(const void* x, const void* w, void* y, int rows, int dim,
+                  float eps, void* stream);
+
+/* apply_rotary_pos_emb_vision (vision.py:35-50) in place on the q and k thirds of
+ * qkv (n_tok, 3, n_heads, head_dim).  pos_hw (n_tok,2) int32 = rot_pos_emb ids
+ * (vision.py:219-249); inv_freq (head_dim/4) fp32. */
+int b200_vision_rope(void* qkv, const int* pos_hw, const float* inv_freq,
+                     int n_tok, int n_heads, int head_dim, void* stream);
+
+/* apply_multimodal_rotary_pos_emb(style="chunked") (rope_utils.py:1456-1504,
+ * 1227-1241) on q (in place) and k, then KVCache.update_and_fetch's append
+ * (cache.py:345-367): k (rotated) and v rows go to kcache/vcache
+ * [(n_kv, cap, head_dim)] at token index ctx0 + t.
+ * qkv: (T, (n_heads + 2 n_kv) * head_dim); pos3: (3, T) int32;
+ * inv_freq (head_dim/2) fp32; axis_sel (head_dim/2) int32 in {0,1,2}. */
+int b200_mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq,
+                        const int* axis_sel, void* kcache, void* vcache,
+                        int T, int ctx0, int cap, int n_heads, int n_kv,
+                        int head_dim, void* stream);
+
+/* mx.fast.scaled_dot_product_attention as executed on the mlx CPU device
+ * (fallback graph; base.py:366-373, vision.py:154): q*scale, scores, softmax and
+ * output each rounded to bf16.  Strides in elements.  causal!=0: bottom-right
+ * aligned (key j visible to query i iff j <= S - Lq + i).  scale is rounded to
+ * bf16 inside. */
+int b200_attention(const void* q, long q_tok_stride, long q_head_stride,
+                   const void* k, long k_tok_stride, long k_head_stride,
+                   const void* v, long v_tok_stride, long v_head_stride,
+                   void* out, long out_tok_stride,
+                   int n_heads, int n_kv, int head_dim, int Lq, int S,
+                   int causal, float scale, void* stream);
+
+/* swiglu (activations.py:8-10): out[r,i] = silu(gu[r,i]) * gu[r,I+i] */
+int b200_swiglu(const void* gate_up, void* out, int rows, int inter, void* stream);
+
+/* embed_tokens + merge_input_ids_with_image_features (qwen2_vl.py:48,78-148) for
+ * B rows of T ids: out[b,t] = feats[start_b + cumsum(mask_b)[t]-1] where
+ * ids==image_token (or ==video_token when no image token is present anywhere),
+ * else table[ids[b,t]].  src_index_out (B*T int32, may be NULL) receives the
+ * feature row used (or -1).  Count validation is done by the host caller. */
+int b200_embed_merge(const int* ids, int B, int T, const void* table, int hidden,
+                     const void* feats, int n_feats, int image_token, int video_token,
+                     void* out, int* src_index_out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Engine level (Qwen2-VL): whole-tower / whole-step calls                     */
+/* ------------------------------------------------------------------------- */
+typedef struct b200_engine b200_engine;
+
+typedef struct {
+  /* text (language.py TextConfig) */
+  int hidden, n_layers, inter, n_heads, n_kv_heads, head_dim, vocab;
+  float rms_eps, rope_theta;
+  int mrope_section[3];
+  int tie_embeddings;
+  /* vision (config.py:9-23) */
+  int v_depth, v_embed, v_heads, v_mlp, v_patch_dim, v_merge, v_out;
+  float v_ln_eps;
+} b200_qwen2vl_config;
+
+int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine** out);
+int b200_engine_destroy(b200_engine* e);
+
+/* Weight registration by name (packed names):
+ *   v.patch_embed.w | v.blk.<i>.{ln1.w,ln1.b,ln2.w,ln2.b,qkv.w,qkv.b,proj.w,proj.b,
+ *   fc1.w,fc1.b,fc2.w,fc2.b} | v.merger.{ln.w,ln.b,fc1.w,fc1.b,fc2.w,fc2.b} |
+ *   lm.embed | lm.head (untied only) | lm.norm | lm.<i>.{ln1,ln2,wqkv,bqkv,wo,wgu,wd} */
+int b200_engine_set_weight(b200_engine* e, const char* name, const void* ptr, long n_elems);
+/* scratch for activations; must be >= b200_engine_workspace_bytes(max tokens) */
+long b200_engine_workspace_bytes(const b200_engine* e, int max_tokens, int max_patches);
+int b200_engine_set_workspace(b200_engine* e, void* ptr, long bytes);
+/* KV pool laid out (n_layers, 2, batch, n_kv, cap, head_dim) bf16 — per layer the
+ * reference KVCache layout (B, n_kv_heads, S, head_dim), cache.py:345-367. */
+int b200_engine_bind_kv(b200_engine* e, void* pool, int batch, int cap);
+/* rotary inverse-frequency tables, HOST fp32: lm (head_dim/2) =
+ * compute_inv_freq (rope_utils.py:1042-1044), vision (v_head_dim/4) =
+ * VisionRotaryEmbedding (vision.py:53-65).  Either may be NULL (keep default).
+ * The Python host passes the values it computed with the reference's formula so
+ * that host and device use bit-identical tables. */
+int b200_engine_set_rope_tables(b200_engine* e, const float* lm_inv_freq_host,
+                                const float* v_inv_freq_host);
+
+/* VisionModel.__call__ (vision.py:257-290): pixel_values (n_patches, v_patch_dim)
+ * f32, grid_thw_host (n_images,3) -> feats (n_patches / merge^2, v_out) bf16. */
+int b200_engine_vision(b200_engine* e, const float* pixel_values,
+                       const int* grid_thw_host, int n_images, void* feats_out,
+                       void* stream);
+
+/* LanguageModel.__call__ for L>1 (language.py:404-518; Qwen2Model :170-200):
+ * embeds (T, hidden) bf16, pos3 (3,T) int32 device, cache row `row` holds ctx0
+ * tokens already.  Appends T tokens of K/V.  If all_logits_out != NULL it
+ * receives (T, vocab) bf16 logits of every row (the reference computes them,
+ * ar.py:358); the last row always goes through the fused head+sampler:
+ * logits / logprobs (ar.py:368) / greedy token (sample_utils.py:63-64) land in
+ * the engine's step buffers and the decode state is armed with
+ * position = ctx0 + T + rope_delta. */
+int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3,
+                        int T, int ctx0, int rope_delta, void* all_logits_out,
+                        void* stream);
+
+/* generate_step's decode loop body (ar.py:496-515, _step :334-389) for greedy
+ * sampling, n_steps times: embed(last token) -> 28 x decoder layer (L=1) -> norm
+ * -> tied head -> logprobs -> argmax.  Launch-only; tokens accumulate in the
+ * device token log.  force_token_host (may be NULL): teacher-forced input ids
+ * for each step (testing). */
+int b200_engine_decode(b200_engine* e, int n_steps, const int* force_tokens_host,
+                       void* stream);
+/* arm the decode state explicitly (used when the caller sampled the token itself) */
+int b200_engine_set_next(b200_engine* e, int token, int ctx, int position, void* stream);
+
+/* device pointers of the step buffers (valid until the next step is launched) */
+const void* b200_engine_logits(const b200_engine* e);    /* (vocab) bf16 */
+const void* b200_engine_logprobs(const b200_engine* e);  /* (vocab) bf16 */
+const int* b200_engine_token_log(const b200_engine* e);  /* int32 ring of generated ids */
+int b200_engine_token_log_capacity(const b200_engine* e);
+/* number of tokens written so far (host mirror; launches counted, not completed) */
+long b200_engine_tokens_launched(const b200_engine* e);
+/* kernels launched by this engine since creation (bench `gpu_launches`) */
+long b200_engine_launch_count(const b200_engine* e);
+/* 0: decode via plain launches, 1: CUDA-graph replay (default) */
+int b200_engine_set_graph(b200_engine* e, int enabled);
+/* CTAs per kv head in the decode attention cluster (1, 2, 4 or 8; default 8) */
+int b200_engine_set_attn_cluster(b200_engine* e, int cluster);
+
+/* stream-ordered helpers so the Python host needs no torch op on the hot path:
+ * copy n generated ids [start, start+n) of the token log to HOST (pinned) memory;
+ * copy the current logits/logprobs vector into a caller buffer (device). */
+int b200_engine_fetch_tokens(b200_engine* e, long start, int n, int* host_out, void* stream);
+int b200_memcpy_d2d(void* dst, const void* src, long bytes, void* stream);
+int b200_memcpy_h2d(void* dst, const void* src_host, long bytes, void* stream);
+
+/* timing helper for bench.py: average device duration (ms) of the decode-step
+ * graph over the last b200_engine_decode call, measured with CUDA events on the
+ * launching stream. */
+float b200_engine_last_decode_ms(const b200_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VLM_H */

@@ -1,0 +1,69 @@
+// Shared declarations of the decode-step kernels (decode.cu) and the engine.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct DecodeDims {
+  int hidden, inter, n_heads, n_kv, hd, vocab, cap;
+  float eps;
+  float scale_bf;  // head_dim^-0.5 rounded to bf16 (mlx fallback: array(scale, q.dtype))
+};
+
+struct LayerW {
+  const bf16 *ln1, *ln2;   // RMSNorm weights
+  const bf16 *wqkv, *bqkv; // [(n_heads+2n_kv)*hd, hidden], bias
+  const bf16* wo;          // [hidden, hidden]
+  const bf16* wgu;         // [2*inter, hidden]  (gate rows then up rows)
+  const bf16* wd;          // [hidden, inter]
+};
+
+// device-resident decode state: lets a captured CUDA graph replay unchanged
+struct DecState {
+  unsigned long long best_key;  // packed (orderable logprob, ~index) of the running argmax
+  unsigned int blocks_done;
+  int tok;        // token fed to the next step
+  int ctx;        // tokens in the cache == write index of the next step
+  int pos;        // rope position of the next step (ctx + rope_delta)
+  int n_out;      // tokens written to the token log
+  int use_force;  // teacher forcing (tests)
+};
+
+void decode_set_sm_count(int n);
+int head_grid();
+size_t attn_smem_bytes(const DecodeDims& d, int chunk_cap);
+int launch_qkv(const DecodeDims& d, const LayerW& lw, const bf16* h, bf16* qbuf, bf16* kc,
+               bf16* vc, const DecState* st, const float* inv_freq, cudaStream_t s);
+int launch_attn(const DecodeDims& d, const bf16* qbuf, const bf16* kc, const bf16* vc, bf16* out,
+                const DecState* st, int cluster, cudaStream_t s);
+int launch_res(const bf16* W, const bf16* x, bf16* h, int N, int K, cudaStream_t s);
+int launch_gateup(const DecodeDims& d, const LayerW& lw, const bf16* h, bf16* act, cudaStream_t s);
+int launch_head(const DecodeDims& d, const bf16* norm_w, const bf16* E, const bf16* h,
+                bf16* logits, float2* partials, cudaStream_t s);
+int launch_sample(const DecodeDims& d, const bf16* logits, const float2* partials, bf16* logprobs,
+                  const bf16* E, bf16* h, DecState* st, int* token_log, int log_cap,
+                  const int* force_tokens, int advance, cudaStream_t s);
+int launch_set_state(DecState* st, int tok, int ctx, int pos, int use_force, int set_tok,
+                     const bf16* E, bf16* h, int hidden, cudaStream_t s);
+
+// row ops / gemm / attention (other translation units)
+int cast_f32_bf16(const float* src, void* dst, long n, cudaStream_t st);
+int layer_norm(const void* x, const void* w, const void* b, void* y, int rows, int dim, float eps,
+               cudaStream_t st);
+int rms_norm(const void* x, const void* w, void* y, int rows, int dim, float eps, cudaStream_t st);
+int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
+                int hd, cudaStream_t st);
+int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
+                   void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
+                   cudaStream_t st);
+int swiglu(const void* gu, void* out, int rows, int inter, cudaStream_t st);
+int embed_merge(const int* ids, int B, int T, const void* table, int hidden, const void* feats,
+                int n_feats, int image_token, int video_token, void* out, int* src_out,
+                cudaStream_t st);
+int gemm_bf16_tn(const void* A, long lda, const void* W, const void* bias, const void* residual,
+                 long ldr, void* C, long ldc, int M, int N, int K, int epilogue, cudaStream_t st);
+int attention(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
+              const void* v, long v_ts, long v_hs, void* out, long o_ts, int n_heads, int n_kv,
+              int hd, int Lq, int S, int causal, float scale, cudaStream_t st);
+
+}  // namespace b200

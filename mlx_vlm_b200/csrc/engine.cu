@@ -1,0 +1,626 @@
+// Engine: whole-tower / whole-step entry points of the C ABI (include/b200vlm.h).
+// Owns the weight table, the decode state, the step buffers and the captured
+// CUDA graph of one decode step.  The caller (Python, via ctypes) owns weights,
+// workspace and the KV pool (torch-allocated device memory).
+#include <stdarg.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return B200_ERR_CUDA;
+}
+
+struct VBlk {
+  const bf16 *ln1w, *ln1b, *ln2w, *ln2b, *qkvw, *qkvb, *projw, *projb, *fc1w, *fc1b, *fc2w, *fc2b;
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_engine {
+  b200_qwen2vl_config cfg;
+  int device = 0, sm_count = 148;
+  std::unordered_map<std::string, const bf16*> w;
+  std::unordered_map<std::string, long> wn;
+  bool resolved = false;
+  // resolved weights
+  const bf16* v_patch = nullptr;
+  std::vector<VBlk> vblk;
+  const bf16 *m_lnw = nullptr, *m_lnb = nullptr, *m_fc1w = nullptr, *m_fc1b = nullptr,
+             *m_fc2w = nullptr, *m_fc2b = nullptr;
+  const bf16 *embed = nullptr, *head = nullptr, *norm = nullptr;
+  std::vector<LayerW> layers;
+  // workspace (caller-owned)
+  uint8_t* ws = nullptr;
+  long ws_bytes = 0;
+  // kv pool (caller-owned)
+  bf16* kv = nullptr;
+  int kv_batch = 0, kv_cap = 0;
+  // engine-owned small device buffers
+  DecState* st = nullptr;
+  bf16 *h = nullptr, *qbuf = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr,
+       *logprobs = nullptr;
+  float2* partials = nullptr;
+  int *token_log = nullptr, *force = nullptr;
+  float *lm_inv_freq = nullptr, *v_inv_freq = nullptr;
+  int* axis_sel = nullptr;
+  int* pos_hw = nullptr;
+  long pos_hw_cap = 0;
+  int log_cap = 1 << 16;
+  // host mirrors of the decode state
+  int ctx_host = 0, pos_host = 0;
+  long tokens_launched = 0, launches = 0;
+  // graph
+  bool use_graph = true;
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int last_steps = 0;
+  bool timing_valid = false;
+  int attn_cluster = 8;
+
+  DecodeDims dims() const {
+    DecodeDims d;
+    d.hidden = cfg.hidden; d.inter = cfg.inter; d.n_heads = cfg.n_heads; d.n_kv = cfg.n_kv_heads;
+    d.hd = cfg.head_dim; d.vocab = cfg.vocab; d.cap = kv_cap; d.eps = cfg.rms_eps;
+    d.scale_bf = __bfloat162float(__float2bfloat16_rn(1.0f / sqrtf((float)cfg.head_dim)));
+    return d;
+  }
+  bf16* kptr(int layer, int row) const {
+    return kv + (((long)layer * 2 + 0) * kv_batch + row) * cfg.n_kv_heads * (long)kv_cap * cfg.head_dim;
+  }
+  bf16* vptr(int layer, int row) const {
+    return kv + (((long)layer * 2 + 1) * kv_batch + row) * cfg.n_kv_heads * (long)kv_cap * cfg.head_dim;
+  }
+};
+
+static const bf16* need(b200_engine* e, const std::string& name, long n_expected, bool* ok) {
+  auto it = e->w.find(name);
+  if (it == e->w.end()) {
+    set_error("engine: weight '%s' not set", name.c_str());
+    *ok = false;
+    return nullptr;
+  }
+  if (n_expected > 0 && e->wn[name] != n_expected) {
+    set_error("engine: weight '%s' has %ld elements, expected %ld", name.c_str(), e->wn[name],
+              n_expected);
+    *ok = false;
+    return nullptr;
+  }
+  return it->second;
+}
+
+static int resolve(b200_engine* e) {
+  if (e->resolved) return B200_OK;
+  const auto& c = e->cfg;
+  bool ok = true;
+  const long E = c.v_embed, Em = c.v_mlp, mg = (long)c.v_merge * c.v_merge * E;
+  e->v_patch = need(e, "v.patch_embed.w", E * c.v_patch_dim, &ok);
+  e->vblk.resize(c.v_depth);
+  for (int i = 0; i < c.v_depth && ok; ++i) {
+    const std::string p = "v.blk." + std::to_string(i) + ".";
+    VBlk& b = e->vblk[i];
+    b.ln1w = need(e, p + "ln1.w", E, &ok); b.ln1b = need(e, p + "ln1.b", E, &ok);
+    b.ln2w = need(e, p + "ln2.w", E, &ok); b.ln2b = need(e, p + "ln2.b", E, &ok);
+    b.qkvw = need(e, p + "qkv.w", 3 * E * E, &ok); b.qkvb = need(e, p + "qkv.b", 3 * E, &ok);
+    b.projw = need(e, p + "proj.w", E * E, &ok); b.projb = need(e, p + "proj.b", E, &ok);
+    b.fc1w = need(e, p + "fc1.w", Em * E, &ok); b.fc1b = need(e, p + "fc1.b", Em, &ok);
+    b.fc2w = need(e, p + "fc2.w", E * Em, &ok); b.fc2b = need(e, p + "fc2.b", E, &ok);
+  }
+  if (ok) {
+    e->m_lnw = need(e, "v.merger.ln.w", E, &ok); e->m_lnb = need(e, "v.merger.ln.b", E, &ok);
+    e->m_fc1w = need(e, "v.merger.fc1.w", mg * mg, &ok); e->m_fc1b = need(e, "v.merger.fc1.b", mg, &ok);
+    e->m_fc2w = need(e, "v.merger.fc2.w", (long)c.v_out * mg, &ok);
+    e->m_fc2b = need(e, "v.merger.fc2.b", c.v_out, &ok);
+  }
+  const long H = c.hidden, I = c.inter, QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  if (ok) {
+    e->embed = need(e, "lm.embed", (long)c.vocab * H, &ok);
+    e->norm = need(e, "lm.norm", H, &ok);
+    e->head = c.tie_embeddings ? e->embed : need(e, "lm.head", (long)c.vocab * H, &ok);
+  }
+  e->layers.resize(c.n_layers);
+  for (int i = 0; i < c.n_layers && ok; ++i) {
+    const std::string p = "lm." + std::to_string(i) + ".";
+    LayerW& l = e->layers[i];
+    l.ln1 = need(e, p + "ln1", H, &ok); l.ln2 = need(e, p + "ln2", H, &ok);
+    l.wqkv = need(e, p + "wqkv", QKV * H, &ok); l.bqkv = need(e, p + "bqkv", QKV, &ok);
+    l.wo = need(e, p + "wo", H * (long)c.n_heads * c.head_dim, &ok);
+    l.wgu = need(e, p + "wgu", 2 * I * H, &ok); l.wd = need(e, p + "wd", H * I, &ok);
+  }
+  if (!ok) return B200_ERR_STATE;
+  e->resolved = true;
+  return B200_OK;
+}
+
+static void invalidate_graph(b200_engine* e) {
+  if (e->gexec) {
+    cudaGraphExecDestroy(e->gexec);
+    e->gexec = nullptr;
+  }
+}
+
+// one decode step as plain launches on stream s (also what gets captured)
+static int enqueue_step(b200_engine* e, cudaStream_t s) {
+  const DecodeDims d = e->dims();
+  const auto& c = e->cfg;
+  int rc;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const LayerW& lw = e->layers[l];
+    bf16* kc = e->kptr(l, 0);
+    bf16* vc = e->vptr(l, 0);
+    if ((rc = launch_qkv(d, lw, e->h, e->qbuf, kc, vc, e->st, e->lm_inv_freq, s))) return rc;
+    if ((rc = launch_attn(d, e->qbuf, kc, vc, e->attn, e->st, e->attn_cluster, s))) return rc;
+    if ((rc = launch_res(lw.wo, e->attn, e->h, c.hidden, c.n_heads * c.head_dim, s))) return rc;
+    if ((rc = launch_gateup(d, lw, e->h, e->act, s))) return rc;
+    if ((rc = launch_res(lw.wd, e->act, e->h, c.hidden, c.inter, s))) return rc;
+  }
+  if ((rc = launch_head(d, e->norm, e->head, e->h, e->logits, e->partials, s))) return rc;
+  if ((rc = launch_sample(d, e->logits, e->partials, e->logprobs, e->embed, e->h, e->st,
+                          e->token_log, e->log_cap, e->force, 1, s)))
+    return rc;
+  return B200_OK;
+}
+
+static int kernels_per_step(const b200_engine* e) { return e->cfg.n_layers * 5 + 2; }
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err; }
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+int b200_device_check(int device, int* sm_count) {
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+              prop.minor);
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  return B200_OK;
+}
+
+int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine** out) {
+  B200_REQUIRE(cfg && out, "engine_create: null argument");
+  B200_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0 && cfg->vocab % 8 == 0 &&
+                   cfg->head_dim % 8 == 0 && cfg->n_heads % cfg->n_kv_heads == 0,
+               "engine_create: dims must be multiples of 8 (hidden=%d inter=%d vocab=%d)",
+               cfg->hidden, cfg->inter, cfg->vocab);
+  int sm = 0;
+  int rc = b200_device_check(device, &sm);
+  if (rc) return rc;
+  B200_CUDA(cudaSetDevice(device));
+  b200_engine* e = new b200_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->sm_count = sm;
+  decode_set_sm_count(sm);
+  const auto& c = e->cfg;
+  B200_CUDA(cudaMalloc(&e->st, sizeof(DecState)));
+  B200_CUDA(cudaMemset(e->st, 0, sizeof(DecState)));
+  B200_CUDA(cudaMalloc(&e->h, (size_t)c.hidden * 2));
+  B200_CUDA(cudaMalloc(&e->qbuf, (size_t)c.n_heads * c.head_dim * 2));
+  B200_CUDA(cudaMalloc(&e->attn, (size_t)c.n_heads * c.head_dim * 2));
+  B200_CUDA(cudaMalloc(&e->act, (size_t)c.inter * 2));
+  B200_CUDA(cudaMalloc(&e->logits, (size_t)c.vocab * 2));
+  B200_CUDA(cudaMalloc(&e->logprobs, (size_t)c.vocab * 2));
+  B200_CUDA(cudaMalloc(&e->partials, (size_t)sm * 8 * sizeof(float2)));
+  B200_CUDA(cudaMalloc(&e->token_log, (size_t)e->log_cap * 4));
+  B200_CUDA(cudaMalloc(&e->force, (size_t)e->log_cap * 4));
+  B200_CUDA(cudaMemset(e->token_log, 0, (size_t)e->log_cap * 4));
+  B200_CUDA(cudaMemset(e->force, 0, (size_t)e->log_cap * 4));
+  B200_CUDA(cudaMalloc(&e->lm_inv_freq, (size_t)(c.head_dim / 2) * 4));
+  B200_CUDA(cudaMalloc(&e->axis_sel, (size_t)(c.head_dim / 2) * 4));
+  const int vhd = c.v_embed / c.v_heads;
+  B200_CUDA(cudaMalloc(&e->v_inv_freq, (size_t)(vhd / 4 > 0 ? vhd / 4 : 1) * 4));
+  // default rope tables (the Python host overrides them with its own fp32 values so
+  // that they are bit-identical to what it hands to the oracle / reference formula)
+  std::vector<float> f(c.head_dim / 2);
+  for (int i = 0; i < c.head_dim / 2; ++i)
+    f[i] = 1.0f / powf(c.rope_theta, (float)(2 * i) / (float)c.head_dim);
+  B200_CUDA(cudaMemcpy(e->lm_inv_freq, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<int> sel(c.head_dim / 2, 0);
+  {  // _chunked_position_selector, rope_utils.py:519-526
+    int off = c.mrope_section[0];
+    for (int dim = 1; dim < 3; ++dim) {
+      for (int i = off; i < off + c.mrope_section[dim] && i < c.head_dim / 2; ++i) sel[i] = dim;
+      off += c.mrope_section[dim];
+    }
+  }
+  B200_CUDA(cudaMemcpy(e->axis_sel, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<float> vf(vhd / 4 > 0 ? vhd / 4 : 1);
+  for (int i = 0; i < (int)vf.size(); ++i)
+    vf[i] = 1.0f / powf(10000.0f, (float)(2 * i) / (float)(vhd / 2));
+  B200_CUDA(cudaMemcpy(e->v_inv_freq, vf.data(), vf.size() * 4, cudaMemcpyHostToDevice));
+  B200_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreate(&e->ev0));
+  B200_CUDA(cudaEventCreate(&e->ev1));
+  *out = e;
+  return B200_OK;
+}
+
+int b200_engine_destroy(b200_engine* e) {
+  if (!e) return B200_OK;
+  cudaSetDevice(e->device);
+  invalidate_graph(e);
+  cudaFree(e->st); cudaFree(e->h); cudaFree(e->qbuf); cudaFree(e->attn); cudaFree(e->act);
+  cudaFree(e->logits); cudaFree(e->logprobs); cudaFree(e->partials); cudaFree(e->token_log);
+  cudaFree(e->force); cudaFree(e->lm_inv_freq); cudaFree(e->axis_sel); cudaFree(e->v_inv_freq);
+  if (e->pos_hw) cudaFree(e->pos_hw);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+  return B200_OK;
+}
+
+int b200_engine_set_weight(b200_engine* e, const char* name, const void* ptr, long n_elems) {
+  B200_REQUIRE(e && name && ptr, "set_weight: null argument");
+  B200_REQUIRE(((uintptr_t)ptr & 15) == 0, "set_weight: '%s' must be 16-byte aligned", name);
+  e->w[name] = (const bf16*)ptr;
+  e->wn[name] = n_elems;
+  e->resolved = false;
+  invalidate_graph(e);
+  return B200_OK;
+}
+
+int b200_engine_set_rope_tables(b200_engine* e, const float* lm_inv_freq_host,
+                                const float* v_inv_freq_host) {
+  B200_REQUIRE(e, "set_rope_tables: null engine");
+  const auto& c = e->cfg;
+  if (lm_inv_freq_host)
+    B200_CUDA(cudaMemcpy(e->lm_inv_freq, lm_inv_freq_host, (size_t)(c.head_dim / 2) * 4,
+                         cudaMemcpyHostToDevice));
+  if (v_inv_freq_host) {
+    const int vhd = c.v_embed / c.v_heads;
+    B200_CUDA(cudaMemcpy(e->v_inv_freq, v_inv_freq_host, (size_t)(vhd / 4) * 4,
+                         cudaMemcpyHostToDevice));
+  }
+  return B200_OK;
+}
+
+static long align256(long x) { return (x + 255) & ~255L; }
+
+long b200_engine_workspace_bytes(const b200_engine* e, int max_tokens, int max_patches) {
+  const auto& c = e->cfg;
+  const long T = max_tokens, N = max_patches;
+  const long QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  long lm = align256(T * c.hidden * 2) * 2 + align256(T * QKV * 2) +
+            align256(T * (long)c.n_heads * c.head_dim * 2) + align256(T * 2L * c.inter * 2) +
+            align256(T * (long)c.inter * 2) + align256(3L * T * 4);
+  long v = align256(N * (long)c.v_patch_dim * 2) + align256(N * (long)c.v_embed * 2) * 2 +
+           align256(N * 3L * c.v_embed * 2) + align256(N * (long)c.v_mlp * 2) +
+           align256(N * (long)c.v_embed * 2);
+  return (lm > v ? lm : v) + 4096;
+}
+
+int b200_engine_set_workspace(b200_engine* e, void* ptr, long bytes) {
+  B200_REQUIRE(e && ptr && bytes > 0 && ((uintptr_t)ptr & 255) == 0,
+               "set_workspace: need a 256-byte aligned buffer");
+  e->ws = (uint8_t*)ptr;
+  e->ws_bytes = bytes;
+  return B200_OK;
+}
+
+int b200_engine_bind_kv(b200_engine* e, void* pool, int batch, int cap) {
+  B200_REQUIRE(e && pool && batch >= 1 && cap >= 1 && ((uintptr_t)pool & 15) == 0,
+               "bind_kv: bad arguments");
+  if (pool != e->kv || batch != e->kv_batch || cap != e->kv_cap) invalidate_graph(e);
+  e->kv = (bf16*)pool;
+  e->kv_batch = batch;
+  e->kv_cap = cap;
+  return B200_OK;
+}
+
+// rot_pos_emb ids (vision.py:219-249), host side, merge-group-major order
+static void build_pos_hw(const int* grid, int n_img, int ms, std::vector<int>* out) {
+  out->clear();
+  for (int i = 0; i < n_img; ++i) {
+    const int t = grid[i * 3], h = grid[i * 3 + 1], w = grid[i * 3 + 2];
+    for (int tt = 0; tt < t; ++tt)
+      for (int bh = 0; bh < h / ms; ++bh)
+        for (int bw = 0; bw < w / ms; ++bw)
+          for (int ih = 0; ih < ms; ++ih)
+            for (int iw = 0; iw < ms; ++iw) {
+              out->push_back(bh * ms + ih);
+              out->push_back(bw * ms + iw);
+            }
+  }
+}
+
+int b200_engine_vision(b200_engine* e, const float* pixel_values, const int* grid_thw_host,
+                       int n_images, void* feats_out, void* stream) {
+  B200_REQUIRE(e && pixel_values && grid_thw_host && n_images > 0 && feats_out,
+               "engine_vision: null argument");
+  int rc = resolve(e);
+  if (rc) return rc;
+  B200_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const auto& c = e->cfg;
+  long N = 0;
+  for (int i = 0; i < n_images; ++i) {
+    const int t = grid_thw_host[i * 3], h = grid_thw_host[i * 3 + 1], w = grid_thw_host[i * 3 + 2];
+    B200_REQUIRE(t > 0 && h > 0 && w > 0 && h % c.v_merge == 0 && w % c.v_merge == 0,
+                 "engine_vision: bad grid (%d,%d,%d)", t, h, w);
+    N += (long)t * h * w;
+  }
+  B200_REQUIRE(e->ws && b200_engine_workspace_bytes(e, 1, (int)N) <= e->ws_bytes,
+               "engine_vision: workspace too small for %ld patches", N);
+  const long E = c.v_embed, Em = c.v_mlp;
+  const int nh = c.v_heads, hd = c.v_embed / c.v_heads;
+  uint8_t* p = e->ws;
+  bf16* x = (bf16*)p; p += align256(N * (long)c.v_patch_dim * 2);
+  bf16* h = (bf16*)p; p += align256(N * E * 2);
+  bf16* y = (bf16*)p; p += align256(N * E * 2);
+  bf16* qkv = (bf16*)p; p += align256(N * 3 * E * 2);
+  bf16* mlp = (bf16*)p; p += align256(N * Em * 2);
+  bf16* att = (bf16*)p; p += align256(N * E * 2);
+  // position ids -> device
+  std::vector<int> pos;
+  build_pos_hw(grid_thw_host, n_images, c.v_merge, &pos);
+  if ((long)pos.size() > e->pos_hw_cap) {
+    if (e->pos_hw) B200_CUDA(cudaFree(e->pos_hw));
+    B200_CUDA(cudaMalloc(&e->pos_hw, pos.size() * 4));
+    e->pos_hw_cap = (long)pos.size();
+  }
+  B200_CUDA(cudaMemcpyAsync(e->pos_hw, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaStreamSynchronize(s));  // `pos` is a stack-lifetime pageable buffer
+
+  if ((rc = cast_f32_bf16(pixel_values, x, N * c.v_patch_dim, s))) return rc;
+  if ((rc = gemm_bf16_tn(x, c.v_patch_dim, e->v_patch, nullptr, nullptr, 0, h, E, (int)N, (int)E,
+                         c.v_patch_dim, B200_EPI_NONE, s)))
+    return rc;
+  e->launches += 2;
+  const float scale = 1.0f / sqrtf((float)hd);
+  for (int i = 0; i < c.v_depth; ++i) {
+    const VBlk& b = e->vblk[i];
+    if ((rc = layer_norm(h, b.ln1w, b.ln1b, y, (int)N, (int)E, c.v_ln_eps, s))) return rc;
+    if ((rc = gemm_bf16_tn(y, E, b.qkvw, b.qkvb, nullptr, 0, qkv, 3 * E, (int)N, (int)(3 * E),
+                           (int)E, B200_EPI_NONE, s)))
+      return rc;
+    if ((rc = vision_rope(qkv, e->pos_hw, e->v_inv_freq, (int)N, nh, hd, s))) return rc;
+    long off = 0;
+    for (int im = 0; im < n_images; ++im) {
+      const int t = grid_thw_host[im * 3];
+      const int seg = grid_thw_host[im * 3 + 1] * grid_thw_host[im * 3 + 2];
+      for (int tt = 0; tt < t; ++tt) {  // one attention segment per frame (vision.py:270-281)
+        const bf16* qb = qkv + off * 3 * E;
+        if ((rc = attention(qb, 3 * E, hd, qb + E, 3 * E, hd, qb + 2 * E, 3 * E, hd,
+                            att + off * E, E, nh, nh, hd, seg, seg, 0, scale, s)))
+          return rc;
+        off += seg;
+        e->launches += 1;
+      }
+    }
+    if ((rc = gemm_bf16_tn(att, E, b.projw, b.projb, h, E, h, E, (int)N, (int)E, (int)E,
+                           B200_EPI_NONE, s)))
+      return rc;
+    if ((rc = layer_norm(h, b.ln2w, b.ln2b, y, (int)N, (int)E, c.v_ln_eps, s))) return rc;
+    if ((rc = gemm_bf16_tn(y, E, b.fc1w, b.fc1b, nullptr, 0, mlp, Em, (int)N, (int)Em, (int)E,
+                           B200_EPI_GELU_FAST, s)))
+      return rc;
+    if ((rc = gemm_bf16_tn(mlp, Em, b.fc2w, b.fc2b, h, E, h, E, (int)N, (int)E, (int)Em,
+                           B200_EPI_NONE, s)))
+      return rc;
+    e->launches += 7;
+  }
+  // PatchMerger (vision.py:105-120)
+  const long mg = (long)c.v_merge * c.v_merge * E;
+  const long Nm = N / ((long)c.v_merge * c.v_merge);
+  if ((rc = layer_norm(h, e->m_lnw, e->m_lnb, y, (int)N, (int)E, 1e-6f, s))) return rc;
+  if ((rc = gemm_bf16_tn(y, mg, e->m_fc1w, e->m_fc1b, nullptr, 0, mlp, mg, (int)Nm, (int)mg,
+                         (int)mg, B200_EPI_GELU_EXACT, s)))
+    return rc;
+  if ((rc = gemm_bf16_tn(mlp, mg, e->m_fc2w, e->m_fc2b, nullptr, 0, feats_out, c.v_out, (int)Nm,
+                         c.v_out, (int)mg, B200_EPI_NONE, s)))
+    return rc;
+  e->launches += 3;
+  return B200_OK;
+}
+
+int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3, int T, int ctx0,
+                        int rope_delta, void* all_logits_out, void* stream) {
+  B200_REQUIRE(e && embeds && pos3 && T > 0 && ctx0 >= 0, "engine_prefill: bad arguments");
+  int rc = resolve(e);
+  if (rc) return rc;
+  B200_REQUIRE(e->kv, "engine_prefill: KV pool not bound");
+  B200_REQUIRE(ctx0 + T <= e->kv_cap, "engine_prefill: ctx0+T=%d exceeds cache capacity %d",
+               ctx0 + T, e->kv_cap);
+  B200_REQUIRE(e->ws && b200_engine_workspace_bytes(e, T, 1) <= e->ws_bytes,
+               "engine_prefill: workspace too small for %d tokens", T);
+  B200_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const auto& c = e->cfg;
+  const long H = c.hidden, I = c.inter, QH = (long)c.n_heads * c.head_dim;
+  const long QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  uint8_t* p = e->ws;
+  bf16* h = (bf16*)p; p += align256((long)T * H * 2);
+  bf16* xn = (bf16*)p; p += align256((long)T * H * 2);
+  bf16* qkv = (bf16*)p; p += align256((long)T * QKV * 2);
+  bf16* att = (bf16*)p; p += align256((long)T * QH * 2);
+  bf16* gu = (bf16*)p; p += align256((long)T * 2 * I * 2);
+  bf16* act = (bf16*)p; p += align256((long)T * I * 2);
+  B200_CUDA(cudaMemcpyAsync(h, embeds, (size_t)T * H * 2, cudaMemcpyDeviceToDevice, s));
+  const float scale = 1.0f / sqrtf((float)c.head_dim);
+  const int S = ctx0 + T;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const LayerW& lw = e->layers[l];
+    bf16* kc = e->kptr(l, 0);
+    bf16* vc = e->vptr(l, 0);
+    if ((rc = rms_norm(h, lw.ln1, xn, T, (int)H, c.rms_eps, s))) return rc;
+    if ((rc = gemm_bf16_tn(xn, H, lw.wqkv, lw.bqkv, nullptr, 0, qkv, QKV, T, (int)QKV, (int)H,
+                           B200_EPI_NONE, s)))
+      return rc;
+    if ((rc = mrope_kv_write(qkv, pos3, e->lm_inv_freq, e->axis_sel, kc, vc, T, ctx0, e->kv_cap,
+                             c.n_heads, c.n_kv_heads, c.head_dim, s)))
+      return rc;
+    if ((rc = attention(qkv, QKV, c.head_dim, kc, c.head_dim, (long)e->kv_cap * c.head_dim, vc,
+                        c.head_dim, (long)e->kv_cap * c.head_dim, att, QH, c.n_heads,
+                        c.n_kv_heads, c.head_dim, T, S, 1, scale, s)))
+      return rc;
+    if ((rc = gemm_bf16_tn(att, QH, lw.wo, nullptr, h, H, h, H, T, (int)H, (int)QH, B200_EPI_NONE,
+                           s)))
+      return rc;
+    if ((rc = rms_norm(h, lw.ln2, xn, T, (int)H, c.rms_eps, s))) return rc;
+    if ((rc = gemm_bf16_tn(xn, H, lw.wgu, nullptr, nullptr, 0, gu, 2 * I, T, (int)(2 * I), (int)H,
+                           B200_EPI_NONE, s)))
+      return rc;
+    if ((rc = swiglu(gu, act, T, (int)I, s))) return rc;
+    if ((rc = gemm_bf16_tn(act, I, lw.wd, nullptr, h, H, h, H, T, (int)H, (int)I, B200_EPI_NONE,
+                           s)))
+      return rc;
+    e->launches += 9;
+  }
+  if (all_logits_out) {  // the reference computes the head on every row (ar.py:358)
+    if ((rc = rms_norm(h, e->norm, xn, T, (int)H, c.rms_eps, s))) return rc;
+    if ((rc = gemm_bf16_tn(xn, H, e->head, nullptr, nullptr, 0, all_logits_out, c.vocab, T,
+                           c.vocab, (int)H, B200_EPI_NONE, s)))
+      return rc;
+    e->launches += 2;
+  }
+  // last row through the fused head + sampler; arms the decode state
+  const DecodeDims d = e->dims();
+  e->ctx_host = ctx0 + T;
+  e->pos_host = ctx0 + T + rope_delta;
+  if ((rc = launch_set_state(e->st, 0, e->ctx_host, e->pos_host, 0, 0, e->embed, e->h, c.hidden, s)))
+    return rc;
+  if ((rc = launch_head(d, e->norm, e->head, h + (long)(T - 1) * H, e->logits, e->partials, s)))
+    return rc;
+  if ((rc = launch_sample(d, e->logits, e->partials, e->logprobs, e->embed, e->h, e->st,
+                          e->token_log, e->log_cap, e->force, 0, s)))
+    return rc;
+  e->launches += 3;
+  e->tokens_launched += 1;
+  return B200_OK;
+}
+
+int b200_engine_set_next(b200_engine* e, int token, int ctx, int position, void* stream) {
+  B200_REQUIRE(e && token >= 0 && token < e->cfg.vocab && ctx >= 0, "set_next: bad arguments");
+  int rc = resolve(e);
+  if (rc) return rc;
+  e->ctx_host = ctx;
+  e->pos_host = position;
+  e->launches += 1;
+  return launch_set_state(e->st, token, ctx, position, 0, 1, e->embed, e->h, e->cfg.hidden,
+                          (cudaStream_t)stream);
+}
+
+int b200_engine_decode(b200_engine* e, int n_steps, const int* force_tokens_host, void* stream) {
+  B200_REQUIRE(e && n_steps > 0, "engine_decode: bad arguments");
+  int rc = resolve(e);
+  if (rc) return rc;
+  B200_REQUIRE(e->kv, "engine_decode: KV pool not bound");
+  B200_REQUIRE(e->ctx_host + n_steps <= e->kv_cap,
+               "engine_decode: %d cached + %d steps exceeds cache capacity %d", e->ctx_host,
+               n_steps, e->kv_cap);
+  B200_REQUIRE(n_steps < e->log_cap, "engine_decode: too many steps per call");
+  B200_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (force_tokens_host) {
+    // forced feed for the token sampled at log index n is force[n % cap]
+    for (int i = 0; i < n_steps; ++i) {
+      const long idx = (e->tokens_launched + i) % e->log_cap;
+      B200_CUDA(cudaMemcpyAsync(e->force + idx, force_tokens_host + i, 4, cudaMemcpyHostToDevice, s));
+    }
+  }
+  if ((rc = launch_set_state(e->st, 0, e->ctx_host, e->pos_host, force_tokens_host ? 1 : 0, 0,
+                             e->embed, e->h, e->cfg.hidden, s)))
+    return rc;
+  if (e->use_graph && !e->gexec) {
+    // capture one step on the engine's own stream (capture does not execute)
+    cudaGraph_t graph = nullptr;
+    B200_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_step(e, e->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture", __FILE__, __LINE__);
+    ce = cudaGraphInstantiate(&e->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate", __FILE__, __LINE__);
+  }
+  B200_CUDA(cudaEventRecord(e->ev0, s));
+  for (int i = 0; i < n_steps; ++i) {
+    if (e->use_graph) {
+      B200_CUDA(cudaGraphLaunch(e->gexec, s));
+    } else {
+      if ((rc = enqueue_step(e, s))) return rc;
+    }
+  }
+  B200_CUDA(cudaEventRecord(e->ev1, s));
+  e->last_steps = n_steps;
+  e->timing_valid = true;
+  e->ctx_host += n_steps;
+  e->pos_host += n_steps;
+  e->tokens_launched += n_steps;
+  e->launches += (long)n_steps * kernels_per_step(e) + 1;
+  return B200_OK;
+}
+
+const void* b200_engine_logits(const b200_engine* e) { return e ? e->logits : nullptr; }
+const void* b200_engine_logprobs(const b200_engine* e) { return e ? e->logprobs : nullptr; }
+const int* b200_engine_token_log(const b200_engine* e) { return e ? e->token_log : nullptr; }
+int b200_engine_token_log_capacity(const b200_engine* e) { return e ? e->log_cap : 0; }
+long b200_engine_tokens_launched(const b200_engine* e) { return e ? e->tokens_launched : 0; }
+long b200_engine_launch_count(const b200_engine* e) { return e ? e->launches : 0; }
+int b200_engine_set_graph(b200_engine* e, int enabled) {
+  B200_REQUIRE(e, "set_graph: null engine");
+  e->use_graph = enabled != 0;
+  return B200_OK;
+}
+int b200_engine_set_attn_cluster(b200_engine* e, int cluster) {
+  B200_REQUIRE(e && (cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8),
+               "set_attn_cluster: cluster must be 1, 2, 4 or 8");
+  e->attn_cluster = cluster;
+  invalidate_graph(e);
+  return B200_OK;
+}
+int b200_engine_fetch_tokens(b200_engine* e, long start, int n, int* host_out, void* stream) {
+  B200_REQUIRE(e && host_out && n > 0 && start >= 0 && n <= e->log_cap, "fetch_tokens: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long a = start % e->log_cap;
+  const long first = (a + n <= e->log_cap) ? n : e->log_cap - a;
+  B200_CUDA(cudaMemcpyAsync(host_out, e->token_log + a, (size_t)first * 4, cudaMemcpyDeviceToHost, s));
+  if (first < n)
+    B200_CUDA(cudaMemcpyAsync(host_out + first, e->token_log, (size_t)(n - first) * 4,
+                              cudaMemcpyDeviceToHost, s));
+  return B200_OK;
+}
+int b200_memcpy_d2d(void* dst, const void* src, long bytes, void* stream) {
+  B200_REQUIRE(dst && src && bytes >= 0, "memcpy_d2d: bad arguments");
+  B200_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B200_OK;
+}
+int b200_memcpy_h2d(void* dst, const void* src_host, long bytes, void* stream) {
+  B200_REQUIRE(dst && src_host && bytes >= 0, "memcpy_h2d: bad arguments");
+  B200_CUDA(cudaMemcpyAsync(dst, src_host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return B200_OK;
+}
+float b200_engine_last_decode_ms(const b200_engine* e) {
+  if (!e || !e->timing_valid || e->last_steps <= 0) return -1.0f;
+  if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.0f;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.0f;
+  return ms / (float)e->last_steps;
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// Row-wise memory-bound kernels of the prefill / vision path: dtype cast, LayerNorm,
+// RMSNorm, vision 2-D rotary, M-RoPE + KV append, SwiGLU, embed + image-feature
+// merge.  All are HBM-bound: 16-byte vector accesses, one warp per row where a
+// reduction is needed.  Rounding points follow oracle/mlx_semantics.py.
+#include "common.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long stride = (long)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint2 o;
+    o.x = pack2(v.x, v.y);
+    o.y = pack2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  }
+  if (i < n && i + 3 >= n) {
+    for (long j = i; j < n; ++j) dst[j] = f2bf(src[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// mx.fast.layer_norm CPU fallback: fp32 stats, cast, *w (round), +b (round).
+// One warp per row; dim % 8 == 0.
+__global__ void layer_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                  const bf16* __restrict__ b, bf16* __restrict__ y, int rows,
+                                  int dim, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const bf16* xr = x + (long)warp * dim;
+  bf16* yr = y + (long)warp * dim;
+  const int nvec = dim >> 3;
+  float s = 0.f;
+  for (int c = lane; c < nvec; c += 32) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  const float mu = warp_sum(s) / (float)dim;
+  float v = 0.f;
+  for (int c = lane; c < nvec; c += 32) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = f[j] - mu;
+      v += d * d;
+    }
+  }
+  const float var = warp_sum(v) / (float)dim;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  for (int c = lane; c < nvec; c += 32) {
+    float f[8], wf[8], bfv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+    if (w) unpack8(*reinterpret_cast<const uint4*>(w + c * 8), wf);
+    if (b) unpack8(*reinterpret_cast<const uint4*>(b + c * 8), bfv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = rbf((f[j] - mu) * rstd);
+      if (w) t = rbf(t * wf[j]);
+      if (b) t = rbf(t + bfv[j]);
+      o[j] = t;
+    }
+    uint4 ov;
+    ov.x = pack2(o[0], o[1]);
+    ov.y = pack2(o[2], o[3]);
+    ov.z = pack2(o[4], o[5]);
+    ov.w = pack2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(yr + c * 8) = ov;
+  }
+}
+
+// mx.fast.rms_norm CPU fallback: bf16(x * rsqrt(mean(x^2)+eps)) then * w (round).
+__global__ void rms_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                bf16* __restrict__ y, int rows, int dim, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const bf16* xr = x + (long)warp * dim;
+  bf16* yr = y + (long)warp * dim;
+  const int nvec = dim >> 3;
+  float s = 0.f;
+  for (int c = lane; c < nvec; c += 32) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j] * f[j];
+  }
+  const float rs = 1.0f / sqrtf(warp_sum(s) / (float)dim + eps);
+  for (int c = lane; c < nvec; c += 32) {
+    float f[8], wf[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), f);
+    unpack8(*reinterpret_cast<const uint4*>(w + c * 8), wf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = rbf(rbf(f[j] * rs) * wf[j]);
+    uint4 ov;
+    ov.x = pack2(o[0], o[1]);
+    ov.y = pack2(o[2], o[3]);
+    ov.z = pack2(o[4], o[5]);
+    ov.w = pack2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(yr + c * 8) = ov;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// apply_rotary_pos_emb_vision (vision.py:35-50): fp32 cos/sin, ONE rounding.
+// freqs for dim j of head_dim: half = hd/2; jj = j % half; jj < half/2 uses the
+// h position with inv_freq[jj], else the w position with inv_freq[jj - half/2].
+// One thread per (token, which in {q,k}, head, pair j<half).
+__global__ void vision_rope_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos_hw,
+                                   const float* __restrict__ inv_freq, int n_tok, int n_heads,
+                                   int hd) {
+  const int half = hd >> 1, quarter = hd >> 2;
+  const long total = (long)n_tok * 2 * n_heads * half;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % half);
+    long r = idx / half;
+    const int h = (int)(r % n_heads);
+    r /= n_heads;
+    const int which = (int)(r % 2);
+    const int t = (int)(r / 2);
+    const int axis = (j < quarter) ? 0 : 1;
+    const float ang = (float)pos_hw[t * 2 + axis] * inv_freq[j - axis * quarter];
+    const float c = cosf(ang), s = sinf(ang);
+    bf16* base = qkv + ((long)t * 3 + which) * n_heads * hd + (long)h * hd;
+    const float x1 = bf2f(base[j]), x2 = bf2f(base[j + half]);
+    // out[j] = x1*cos + (-x2)*sin ; out[j+half] = x2*cos + x1*sin   (fp32, one cast)
+    // separate fp32 mul / add like the reference's three array ops (no FMA contraction)
+    base[j] = f2bf(__fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, s)));
+    base[j + half] = f2bf(__fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, s)));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// M-RoPE (rope_utils.py:1227-1241 cos/sin cast to bf16; :1301-1334 three roundings)
+// + KV append.  One thread per (t, head-slot, pair j < hd/2); head-slot covers
+// n_heads q heads, n_kv k heads, n_kv v heads (v: plain copy).
+__global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos3,
+                                      const float* __restrict__ inv_freq,
+                                      const int* __restrict__ axis_sel, bf16* __restrict__ kc,
+                                      bf16* __restrict__ vc, int T, int ctx0, int cap, int n_heads,
+                                      int n_kv, int hd) {
+  const int half = hd >> 1;
+  const int slots = n_heads + 2 * n_kv;
+  const long total = (long)T * slots * half;
+  const long row_elems = (long)slots * hd;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % half);
+    long r = idx / half;
+    const int slot = (int)(r % slots);
+    const int t = (int)(r / slots);
+    bf16* base = qkv + (long)t * row_elems + (long)slot * hd;
+    const float x1 = bf2f(base[j]), x2 = bf2f(base[j + half]);
+    if (slot >= n_heads + n_kv) {  // V: copy into the cache
+      const int kvh = slot - n_heads - n_kv;
+      bf16* dst = vc + ((long)kvh * cap + ctx0 + t) * hd;
+      dst[j] = base[j];
+      dst[j + half] = base[j + half];
+      continue;
+    }
+    const float ang = (float)pos3[axis_sel[j] * T + t] * inv_freq[j];
+    const float c = rbf(cosf(ang)), s = rbf(sinf(ang));
+    const float o1 = rbf(rbf(x1 * c) + rbf((-x2) * s));
+    const float o2 = rbf(rbf(x2 * c) + rbf(x1 * s));
+    if (slot < n_heads) {
+      base[j] = f2bf(o1);
+      base[j + half] = f2bf(o2);
+    } else {
+      const int kvh = slot - n_heads;
+      bf16* dst = kc + ((long)kvh * cap + ctx0 + t) * hd;
+      dst[j] = f2bf(o1);
+      dst[j + half] = f2bf(o2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void swiglu_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, int rows,
+                              int inter) {
+  const int nvec = inter >> 3;
+  const long total = (long)rows * nvec;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % nvec);
+    const long r = idx / nvec;
+    float g[8], u[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * inter + c * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * inter + inter + c * 8), u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = swiglu_bf(g[j], u[j]);
+    uint4 ov;
+    ov.x = pack2(o[0], o[1]);
+    ov.y = pack2(o[2], o[3]);
+    ov.z = pack2(o[4], o[5]);
+    ov.w = pack2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(out + r * inter + c * 8) = ov;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// embed + merge (qwen2_vl.py:48,78-148).  One CTA per batch row computes the
+// inclusive prefix count of image positions with a block scan, then all threads
+// copy rows (16-byte vectors).  feature_start of row b = number of image
+// positions in rows < b (counted redundantly by each CTA; B and T are small).
+__global__ void embed_merge_kernel(const int* __restrict__ ids, int B, int T,
+                                   const bf16* __restrict__ table, int hidden,
+                                   const bf16* __restrict__ feats, int n_feats, int image_token,
+                                   int video_token, bf16* __restrict__ out,
+                                   int* __restrict__ src_out) {
+  extern __shared__ int sh[];  // [T] src index per position
+  __shared__ int s_any_image, s_start;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_any_image = 0;
+    s_start = 0;
+  }
+  __syncthreads();
+  // any image token anywhere? (reference: mx.sum(image_positions) == 0 -> video ids)
+  int local = 0;
+  for (int i = threadIdx.x; i < B * T; i += blockDim.x) local |= (ids[i] == image_token);
+  if (local) atomicOr(&s_any_image, 1);
+  __syncthreads();
+  const int tok = s_any_image ? image_token : video_token;
+  // features consumed by earlier rows
+  int cnt = 0;
+  for (int i = threadIdx.x; i < b * T; i += blockDim.x) cnt += (ids[i] == tok);
+  if (cnt) atomicAdd(&s_start, cnt);
+  __syncthreads();
+  // serial-in-chunks scan of this row (T is at most a few thousand)
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < T; ++t) {
+      const bool m = ids[b * T + t] == tok;
+      run += m;
+      sh[t] = m ? (s_start + run - 1) : -1;
+    }
+  }
+  __syncthreads();
+  const int nvec = hidden >> 3;
+  for (long idx = threadIdx.x; idx < (long)T * nvec; idx += blockDim.x) {
+    const int t = (int)(idx / nvec), c = (int)(idx % nvec);
+    const int src = sh[t];
+    const bf16* row;
+    if (src >= 0) {
+      row = feats + (long)min(src, max(n_feats - 1, 0)) * hidden;
+    } else {
+      row = table + (long)ids[b * T + t] * hidden;
+    }
+    *reinterpret_cast<uint4*>(out + ((long)b * T + t) * hidden + c * 8) =
+        *reinterpret_cast<const uint4*>(row + c * 8);
+  }
+  if (src_out)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) src_out[b * T + t] = sh[t];
+}
+
+// ---------------------------------------------------------------------------
+static inline int grid_for(long work, int block) {
+  long g = (work + block - 1) / block;
+  if (g > 148L * 16) g = 148L * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int cast_f32_bf16(const float* src, void* dst, long n, cudaStream_t st) {
+  B200_REQUIRE(n >= 0, "cast: n<0");
+  if (n == 0) return B200_OK;
+  B200_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "cast: misaligned");
+  cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(src, (bf16*)dst, n);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int layer_norm(const void* x, const void* w, const void* b, void* y, int rows, int dim, float eps,
+               cudaStream_t st) {
+  B200_REQUIRE(rows > 0 && dim > 0 && (dim % 8) == 0, "layer_norm: rows=%d dim=%d", rows, dim);
+  layer_norm_kernel<<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)b,
+                                                  (bf16*)y, rows, dim, eps);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int rms_norm(const void* x, const void* w, void* y, int rows, int dim, float eps,
+             cudaStream_t st) {
+  B200_REQUIRE(rows > 0 && dim > 0 && (dim % 8) == 0 && w, "rms_norm: rows=%d dim=%d", rows, dim);
+  rms_norm_kernel<<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rows,
+                                                dim, eps);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
+                int hd, cudaStream_t st) {
+  B200_REQUIRE(n_tok > 0 && n_heads > 0 && (hd % 4) == 0, "vision_rope: bad shape");
+  const long total = (long)n_tok * 2 * n_heads * (hd / 2);
+  vision_rope_kernel<<<grid_for(total, 256), 256, 0, st>>>((bf16*)qkv, pos_hw, inv_freq, n_tok,
+                                                          n_heads, hd);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
+                   void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
+                   cudaStream_t st) {
+  B200_REQUIRE(T > 0 && ctx0 >= 0 && ctx0 + T <= cap, "mrope_kv_write: T=%d ctx0=%d cap=%d", T,
+               ctx0, cap);
+  const long total = (long)T * (n_heads + 2 * n_kv) * (hd / 2);
+  mrope_kv_write_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+      (bf16*)qkv, pos3, inv_freq, axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int swiglu(const void* gu, void* out, int rows, int inter, cudaStream_t st) {
+  B200_REQUIRE(rows > 0 && inter > 0 && (inter % 8) == 0, "swiglu: bad shape");
+  swiglu_kernel<<<grid_for((long)rows * (inter / 8), 256), 256, 0, st>>>((const bf16*)gu,
+                                                                        (bf16*)out, rows, inter);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int embed_merge(const int* ids, int B, int T, const void* table, int hidden, const void* feats,
+                int n_feats, int image_token, int video_token, void* out, int* src_out,
+                cudaStream_t st) {
+  B200_REQUIRE(B > 0 && T > 0 && (hidden % 8) == 0, "embed_merge: bad shape");
+  B200_REQUIRE((long)T * 4 <= 200 * 1024, "embed_merge: T=%d too long", T);
+  if ((size_t)T * 4 > 48 * 1024) {
+    B200_CUDA(cudaFuncSetAttribute(embed_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   T * 4));
+  }
+  embed_merge_kernel<<<B, 512, (size_t)T * 4, st>>>(ids, B, T, (const bf16*)table, hidden,
+                                                   (const bf16*)feats, n_feats, image_token,
+                                                   video_token, (bf16*)out, src_out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+extern "C" {
+int b200_cast_f32_bf16(const float* s, void* d, long n, void* st) {
+  return cast_f32_bf16(s, d, n, (cudaStream_t)st);
+}
+int b200_layer_norm(const void* x, const void* w, const void* b, void* y, int rows, int dim,
+                    float eps, void* st) {
+  return layer_norm(x, w, b, y, rows, dim, eps, (cudaStream_t)st);
+}
+int b200_rms_norm(const void* x, const void* w, void* y, int rows, int dim, float eps, void* st) {
+  return rms_norm(x, w, y, rows, dim, eps, (cudaStream_t)st);
+}
+int b200_vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
+                     int hd, void* st) {
+  return vision_rope(qkv, pos_hw, inv_freq, n_tok, n_heads, hd, (cudaStream_t)st);
+}
+int b200_mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
+                        void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv,
+                        int hd, void* st) {
+  return mrope_kv_write(qkv, pos3, inv_freq, axis_sel, kc, vc, T, ctx0, cap, n_heads, n_kv, hd,
+                        (cudaStream_t)st);
+}
+int b200_swiglu(const void* gu, void* out, int rows, int inter, void* st) {
+  return swiglu(gu, out, rows, inter, (cudaStream_t)st);
+}
+int b200_embed_merge(const int* ids, int B, int T, const void* table, int hidden,
+                     const void* feats, int n_feats, int image_token, int video_token, void* out,
+                     int* src_out, void* st) {
+  return embed_merge(ids, B, T, table, hidden, feats, n_feats, image_token, video_token, out,
+                     src_out, (cudaStream_t)st);
+}
+}

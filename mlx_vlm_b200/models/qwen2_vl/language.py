@@ -1,0 +1,231 @@
+"""Qwen2-VL language model — Python face of the reference's
+mlx_vlm/models/qwen2_vl/language.py (`LanguageModel` :203-530).
+
+Host-side integer logic (M-RoPE position ids, decode position bookkeeping) is
+restated here in numpy and is bit-exact with the reference (tests pin it on the
+reference's known-answer vectors).  The transformer arithmetic runs in
+libb200vlm.so: `b200_engine_prefill` for L > 1, the captured decode-step graph
+(`b200_engine_decode`) for L == 1.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from ..base import LanguageModelOutput
+from ..cache import KVCache, KVPool
+from .config import ModelConfig, TextConfig
+
+
+def _np(x, dtype=np.int64):
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy().astype(dtype)
+    return np.asarray(x, dtype=dtype)
+
+
+class LanguageModel:
+    # generate_step passes logits_to_keep=1 when this is set (ar.py:341-342), so the
+    # head runs on the last prompt row only; all rows are still available on request.
+    supports_logits_to_keep = True
+
+    def __init__(self, args: TextConfig, config: ModelConfig, engine_getter):
+        self.args = args
+        self.config = config
+        self.model_type = args.model_type
+        self._rope_deltas = None
+        self._position_ids = None
+        self._engine = engine_getter
+        self._pool: Optional[KVPool] = None
+
+    # ------------------------------------------------------------------ rope
+    def get_rope_index(self, input_ids, image_grid_thw=None, video_grid_thw=None,
+                       attention_mask=None):
+        """language.py:216-402.  Returns numpy int64 (position_ids, rope_deltas):
+        (3,B,T),(B,1) with vision grids, else the 2-D text branch."""
+        cfg = self.config
+        ids = _np(input_ids)
+        B, T = ids.shape
+        ms = cfg.vision_config.spatial_merge_size
+        img_id, vid_id = cfg.image_token_id, cfg.video_token_id
+        vs_id = cfg.vision_start_token_id
+        igrid, vgrid = _np(image_grid_thw), _np(video_grid_thw)
+        amask = _np(attention_mask)
+        if igrid is not None or vgrid is not None:
+            if amask is None:
+                amask = np.ones_like(ids)
+            pos = np.ones((3, B, T), dtype=np.int64)
+            deltas: List[int] = []
+            ii = vi = 0
+            for i in range(B):
+                row_mask = amask[i].tolist()
+                toks = [t for t, keep in zip(ids[i].tolist(), row_mask) if keep == 1]
+                follow = [toks[j + 1] for j, t in enumerate(toks[:-1]) if t == vs_id]
+                n_img = sum(t == img_id for t in follow)
+                n_vid = sum(t == vid_id for t in follow)
+                parts: List[np.ndarray] = []
+                st = 0
+                left_i, left_v = n_img, n_vid
+                for _ in range(n_img + n_vid):
+                    e_img = toks.index(img_id, st) if (img_id in toks and left_i > 0) else len(toks) + 1
+                    e_vid = toks.index(vid_id, st) if (vid_id in toks and left_v > 0) else len(toks) + 1
+                    if e_img < e_vid:
+                        t, h, w = (int(v) for v in igrid[ii])
+                        ii += 1
+                        left_i -= 1
+                        ed = e_img
+                    else:
+                        t, h, w = (int(v) for v in vgrid[vi])
+                        vi += 1
+                        left_v -= 1
+                        ed = e_vid
+                    gt, gh, gw = t, h // ms, w // ms
+                    n_text = ed - st
+                    base = int(parts[-1].max()) + 1 if parts else 0
+                    parts.append(np.tile(np.arange(n_text), (3, 1)) + base)
+                    grid = np.indices((gt, gh, gw)).reshape(3, -1)  # rows: t, h, w
+                    parts.append(grid + n_text + base)
+                    st = ed + gt * gh * gw
+                if st < len(toks):
+                    base = int(parts[-1].max()) + 1 if parts else 0
+                    parts.append(np.tile(np.arange(len(toks) - st), (3, 1)) + base)
+                if not parts:
+                    deltas.append(0)
+                    continue
+                compact = np.concatenate(parts, axis=1).reshape(3, -1)
+                keep_cols = [c for c, k in enumerate(row_mask) if k == 1]
+                pos[:, i, keep_cols] = compact[:, :len(keep_cols)]
+                deltas.append(int(compact.max()) + 1 - len(toks))
+            return pos, np.asarray(deltas, dtype=np.int64).reshape(-1, 1)
+        if amask is not None:
+            pos = np.cumsum(amask, axis=-1) - 1
+            pos = np.where(amask == 0, 1, pos)
+            return pos, pos.max(axis=-1, keepdims=True) + 1 - amask.shape[-1]
+        pos = np.tile(np.arange(T), (B, 1))
+        return pos, np.zeros((B, 1), dtype=np.int64)
+
+    # ----------------------------------------------------------------- cache
+    def make_cache(self):
+        """One device pool per request; per-layer KVCache views (models/cache.py)."""
+        eng = self._engine()
+        pool = KVPool(self.args.num_hidden_layers, self.args.num_key_value_heads, self.head_dim,
+                      eng.device, batch=1)
+        self._pool = pool
+        return [KVCache(pool, l) for l in range(self.args.num_hidden_layers)]
+
+    def _bind(self, cache, need_tokens: int) -> KVPool:
+        c0 = cache[0]
+        pool = getattr(c0, "_pool", None)
+        if pool is None:
+            raise ValueError("b200 LanguageModel needs caches from make_prompt_cache(language_model)")
+        eng = self._engine()
+        if pool.capacity < need_tokens:
+            eng.stream.synchronize()
+            with torch.cuda.stream(eng.stream):
+                pool.reserve(need_tokens, live_tokens=c0.offset)
+        eng.bind_pool(pool)
+        return pool
+
+    # ------------------------------------------------------------------ call
+    def __call__(self, inputs, inputs_embeds=None, mask=None, cache=None, **kwargs):
+        position_ids = kwargs.pop("position_ids", None)
+        pixel_values = kwargs.pop("pixel_values", None)
+        image_grid_thw = kwargs.pop("image_grid_thw", None)
+        video_grid_thw = kwargs.pop("video_grid_thw", None)
+        rope_deltas_kw = kwargs.pop("rope_deltas", None)
+        logits_to_keep = kwargs.pop("logits_to_keep", None)
+        reserve_tokens = kwargs.pop("reserve_tokens", 0)
+        eng = self._engine()
+        if pixel_values is not None:  # new image/video: reset (language.py:418-420)
+            self._rope_deltas = None
+            self._position_ids = None
+        if rope_deltas_kw is not None:
+            self._rope_deltas = _np(rope_deltas_kw)
+        if cache is None or cache[0] is None:
+            cache = self.make_cache()  # stateless call: throw-away cache
+        cache_offset = int(cache[0].offset)
+
+        ids_host = _np(inputs)
+        if ids_host.ndim == 1:
+            ids_host = ids_host[None]
+        B, L = ids_host.shape
+        if B != 1:
+            raise NotImplementedError("batched LanguageModel calls arrive with BatchKVCache (next round)")
+        position_ids = _np(position_ids)
+        if position_ids is not None and position_ids.shape[-1] > L:
+            position_ids = position_ids[..., cache_offset:cache_offset + L]
+        rope_mask = mask
+        if mask is not None and _np(mask).shape[-1] != L:
+            rope_mask = None
+        if position_ids is None and (rope_mask is None or _np(rope_mask).ndim == 2):
+            if cache_offset == 0 or self._rope_deltas is None:
+                if self._position_ids is not None:
+                    position_ids = self._position_ids[..., cache_offset:cache_offset + L]
+                else:
+                    position_ids, deltas = self.get_rope_index(ids_host, image_grid_thw,
+                                                               video_grid_thw, rope_mask)
+                    self._rope_deltas = deltas
+                    self._position_ids = position_ids
+            else:
+                src = _np(rope_deltas_kw) if rope_deltas_kw is not None else self._rope_deltas
+                delta = cache_offset + np.asarray(src).reshape(-1)[:B]
+                position_ids = np.arange(L)[None, :] + delta[:, None]  # (B, L)
+                position_ids = np.broadcast_to(position_ids[None], (3, B, L))
+        if position_ids.ndim == 2:  # text-only: the same scalar position on every axis
+            position_ids = np.broadcast_to(position_ids[None], (3,) + position_ids.shape)
+        delta0 = int(np.asarray(self._rope_deltas).reshape(-1)[0]) if self._rope_deltas is not None else 0
+
+        need = max(cache_offset + L, reserve_tokens)
+        self._bind(cache, need)
+        V = self.args.vocab_size
+        if L == 1 and inputs_embeds is None:
+            # ---- decode step through the captured graph ----
+            pos = int(position_ids[0, 0, 0])
+            eng.set_next(int(ids_host[0, 0]), cache_offset, pos)
+            eng.decode(1)
+            logits = eng.snapshot("logits").view(1, 1, V)
+        else:
+            if inputs_embeds is None:
+                from .qwen2_vl import embed_tokens
+                inputs_embeds = embed_tokens(eng, ids_host)
+            emb = inputs_embeds.reshape(-1, inputs_embeds.shape[-1])
+            assert emb.shape[0] == L and emb.dtype == torch.bfloat16 and emb.is_cuda
+            pos3 = torch.from_numpy(np.ascontiguousarray(position_ids[:, 0, :], dtype=np.int32))
+            with torch.cuda.stream(eng.stream):
+                pos3 = pos3.to(eng.device, non_blocking=False)
+            keep_all = logits_to_keep is None or logits_to_keep != 1
+            all_logits = eng.empty((L, V)) if keep_all else None
+            eng.prefill(emb.contiguous(), pos3, cache_offset, delta0, all_logits)
+            logits = (all_logits.view(1, L, V) if keep_all
+                      else eng.snapshot("logits").view(1, 1, V))
+        for c in cache:
+            c.offset += L
+        return LanguageModelOutput(logits=logits)
+
+    # -------------------------------------------------- fused greedy decoding
+    def fused_greedy_decode(self, n_steps: int, cache, reserve_tokens: int = 0):
+        """The operator hook of the reference (ar.py:1015-1042 probes
+        `language_model.fused_greedy_decode`): run `n_steps` greedy decode steps
+        entirely on the device (token feedback through device memory, no host
+        round trip).  Tokens land in the engine's token log."""
+        eng = self._engine()
+        off = int(cache[0].offset)
+        self._bind(cache, max(off + n_steps, reserve_tokens))
+        eng.decode(n_steps)
+        for c in cache:
+            c.offset += n_steps
+
+    @property
+    def layers(self):
+        return list(range(self.args.num_hidden_layers))
+
+    @property
+    def head_dim(self):
+        return self.args.hidden_size // self.args.num_attention_heads
+
+    @property
+    def n_kv_heads(self):
+        return self.args.num_key_value_heads

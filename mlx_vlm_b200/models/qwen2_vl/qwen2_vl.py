@@ -1,0 +1,264 @@
+"""Qwen2-VL `Model` — the per-model contract of the reference
+(mlx_vlm/models/qwen2_vl/qwen2_vl.py:13-190): `get_input_embeddings`,
+`merge_input_ids_with_image_features`, `vision_tower`, `language_model`, `layers`,
+`sanitize`; plus weight packing for the native engine.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from ... import _native as N
+from ...engine import Engine
+from ..base import InputEmbeddingsFeatures
+from .config import ModelConfig
+from .language import LanguageModel, _np
+from .vision import VisionModel
+
+
+def _ids_to_device(eng: Engine, ids_host: np.ndarray) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(ids_host, dtype=np.int32))
+    with torch.cuda.stream(eng.stream):
+        return t.to(eng.device)
+
+
+def embed_tokens(eng: Engine, ids_host: np.ndarray) -> torch.Tensor:
+    """nn.Embedding lookup (language.py:183) through the merge kernel with no features."""
+    ids_host = np.asarray(ids_host).reshape(1, -1) if np.asarray(ids_host).ndim == 1 else np.asarray(ids_host)
+    B, T = ids_host.shape
+    H = eng.cfg.hidden
+    out = eng.empty((B, T, H))
+    ids = _ids_to_device(eng, ids_host)
+    N.check(eng.lib.b200_embed_merge(ids.data_ptr(), B, T, eng.weights["lm.embed"].data_ptr(), H,
+                                     0, 0, -1, -1, out.data_ptr(), 0, eng.s), "embed")
+    return out
+
+
+class Model:
+    def __init__(self, config: ModelConfig, device=None):
+        self.config = config
+        self._device = torch.device(device) if device is not None else torch.device("cuda", 0)
+        self._eng: Optional[Engine] = None
+        self.vision_tower = VisionModel(config.vision_config, self._engine)
+        self.language_model = LanguageModel(config.text_config, config, self._engine)
+
+    # ------------------------------------------------------------- engine
+    def native_config(self) -> N.Qwen2VLConfig:
+        t, v = self.config.text_config, self.config.vision_config
+        c = N.Qwen2VLConfig()
+        c.hidden, c.n_layers, c.inter = t.hidden_size, t.num_hidden_layers, t.intermediate_size
+        c.n_heads, c.n_kv_heads = t.num_attention_heads, t.num_key_value_heads
+        c.head_dim = t.hidden_size // t.num_attention_heads
+        c.vocab = t.vocab_size
+        c.rms_eps, c.rope_theta = t.rms_norm_eps, t.rope_theta
+        sec = t.mrope_section
+        c.mrope_section[0], c.mrope_section[1], c.mrope_section[2] = sec[0], sec[1], sec[2]
+        c.tie_embeddings = int(t.tie_word_embeddings)
+        c.v_depth, c.v_embed, c.v_heads = v.depth, v.embed_dim, v.num_heads
+        c.v_mlp = int(v.embed_dim * v.mlp_ratio)
+        c.v_patch_dim = v.in_channels * v.temporal_patch_size * v.patch_size * v.patch_size
+        c.v_merge, c.v_out, c.v_ln_eps = v.spatial_merge_size, v.hidden_size, v.layer_norm_eps
+        return c
+
+    def _engine(self) -> Engine:
+        if self._eng is None:
+            self._eng = Engine(self.native_config(), self._device)
+        return self._eng
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine()
+
+    # ------------------------------------------------------------ weights
+    def sanitize(self, weights):
+        """qwen2_vl.py:179-190 key renames (HF -> reference names)."""
+        def transform_key(key):
+            if "vision_tower" not in key:
+                key = key.replace("visual", "vision_tower")
+            if "language_model" not in key:
+                if "model" in key:
+                    key = key.replace("model", "language_model.model")
+                elif "lm_head" in key:
+                    key = key.replace("lm_head", "language_model.lm_head")
+            return key
+        return {transform_key(k): v for k, v in weights.items()}
+
+    def load_weights(self, weights: Dict[str, torch.Tensor], strict: bool = True):
+        """Pack reference-named tensors into the engine layout (bf16, device):
+        q/k/v rows fused into wqkv, gate/up rows into wgu."""
+        eng = self._engine()
+        t, v = self.config.text_config, self.config.vision_config
+        dev = eng.device
+
+        def dv(x):
+            return x.to(device=dev, dtype=torch.bfloat16).contiguous()
+
+        def get(name):
+            if name not in weights:
+                raise KeyError(f"missing weight {name}")
+            return weights[name]
+
+        w = self.vision_tower.sanitize({k: x for k, x in weights.items() if "vision_tower" in k})
+        E = v.embed_dim
+        eng.set_weight("v.patch_embed.w", dv(w["vision_tower.patch_embed.proj.weight"].reshape(E, -1)))
+        for i in range(v.depth):
+            p, q = f"vision_tower.blocks.{i}.", f"v.blk.{i}."
+            for a, b in (("norm1.weight", "ln1.w"), ("norm1.bias", "ln1.b"), ("norm2.weight", "ln2.w"),
+                         ("norm2.bias", "ln2.b"), ("attn.qkv.weight", "qkv.w"), ("attn.qkv.bias", "qkv.b"),
+                         ("attn.proj.weight", "proj.w"), ("attn.proj.bias", "proj.b"),
+                         ("mlp.fc1.weight", "fc1.w"), ("mlp.fc1.bias", "fc1.b"),
+                         ("mlp.fc2.weight", "fc2.w"), ("mlp.fc2.bias", "fc2.b")):
+                eng.set_weight(q + b, dv(get(p + a)))
+        for a, b in (("ln_q.weight", "ln.w"), ("ln_q.bias", "ln.b"), ("mlp.0.weight", "fc1.w"),
+                     ("mlp.0.bias", "fc1.b"), ("mlp.2.weight", "fc2.w"), ("mlp.2.bias", "fc2.b")):
+            eng.set_weight("v.merger." + b, dv(get("vision_tower.merger." + a)))
+        eng.set_weight("lm.embed", dv(get("language_model.model.embed_tokens.weight")))
+        eng.set_weight("lm.norm", dv(get("language_model.model.norm.weight")))
+        if not t.tie_word_embeddings:
+            eng.set_weight("lm.head", dv(get("language_model.lm_head.weight")))
+        for i in range(t.num_hidden_layers):
+            p, q = f"language_model.model.layers.{i}.", f"lm.{i}."
+            eng.set_weight(q + "ln1", dv(get(p + "input_layernorm.weight")))
+            eng.set_weight(q + "ln2", dv(get(p + "post_attention_layernorm.weight")))
+            eng.set_weight(q + "wqkv", dv(torch.cat([get(p + f"self_attn.{n}_proj.weight").to(dev)
+                                                     for n in "qkv"], 0)))
+            eng.set_weight(q + "bqkv", dv(torch.cat([get(p + f"self_attn.{n}_proj.bias").to(dev)
+                                                     for n in "qkv"], 0)))
+            eng.set_weight(q + "wo", dv(get(p + "self_attn.o_proj.weight")))
+            eng.set_weight(q + "wgu", dv(torch.cat([get(p + "mlp.gate_proj.weight").to(dev),
+                                                    get(p + "mlp.up_proj.weight").to(dev)], 0)))
+            eng.set_weight(q + "wd", dv(get(p + "mlp.down_proj.weight")))
+        torch.cuda.synchronize(dev)
+
+    def init_random(self, seed: int = 0, std: float = 0.02):
+        """Seeded random-init at the configured shapes, generated on the device
+        (benchmark weights; SURVEY §8d: N(0, 0.02), norm weights 1, norm biases 0)."""
+        eng = self._engine()
+        t, v = self.config.text_config, self.config.vision_config
+        g = torch.Generator(device=eng.device).manual_seed(seed)
+
+        def rnd(*shape):
+            return (torch.randn(shape, generator=g, device=eng.device, dtype=torch.float32) * std
+                    ).to(torch.bfloat16)
+
+        def ones(n):
+            return torch.ones(n, device=eng.device, dtype=torch.bfloat16)
+
+        def zeros(n):
+            return torch.zeros(n, device=eng.device, dtype=torch.bfloat16)
+
+        c = self.native_config()
+        E, Em, mg = c.v_embed, c.v_mlp, c.v_merge ** 2 * c.v_embed
+        eng.set_weight("v.patch_embed.w", rnd(E, c.v_patch_dim))
+        for i in range(c.v_depth):
+            q = f"v.blk.{i}."
+            eng.set_weight(q + "ln1.w", ones(E)); eng.set_weight(q + "ln1.b", zeros(E))
+            eng.set_weight(q + "ln2.w", ones(E)); eng.set_weight(q + "ln2.b", zeros(E))
+            eng.set_weight(q + "qkv.w", rnd(3 * E, E)); eng.set_weight(q + "qkv.b", rnd(3 * E))
+            eng.set_weight(q + "proj.w", rnd(E, E)); eng.set_weight(q + "proj.b", rnd(E))
+            eng.set_weight(q + "fc1.w", rnd(Em, E)); eng.set_weight(q + "fc1.b", rnd(Em))
+            eng.set_weight(q + "fc2.w", rnd(E, Em)); eng.set_weight(q + "fc2.b", rnd(E))
+        eng.set_weight("v.merger.ln.w", ones(E)); eng.set_weight("v.merger.ln.b", zeros(E))
+        eng.set_weight("v.merger.fc1.w", rnd(mg, mg)); eng.set_weight("v.merger.fc1.b", rnd(mg))
+        eng.set_weight("v.merger.fc2.w", rnd(c.v_out, mg)); eng.set_weight("v.merger.fc2.b", rnd(c.v_out))
+        H, I = c.hidden, c.inter
+        QKV = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim
+        eng.set_weight("lm.embed", rnd(c.vocab, H))
+        eng.set_weight("lm.norm", ones(H))
+        if not c.tie_embeddings:
+            eng.set_weight("lm.head", rnd(c.vocab, H))
+        for i in range(c.n_layers):
+            q = f"lm.{i}."
+            eng.set_weight(q + "ln1", ones(H)); eng.set_weight(q + "ln2", ones(H))
+            eng.set_weight(q + "wqkv", rnd(QKV, H)); eng.set_weight(q + "bqkv", rnd(QKV))
+            eng.set_weight(q + "wo", rnd(H, c.n_heads * c.head_dim))
+            eng.set_weight(q + "wgu", rnd(2 * I, H)); eng.set_weight(q + "wd", rnd(H, I))
+        torch.cuda.synchronize(eng.device)
+        return self
+
+    # ------------------------------------------------------------- contract
+    def get_input_embeddings(self, input_ids=None, pixel_values=None, **kwargs):
+        """qwen2_vl.py:20-76."""
+        if pixel_values is None:
+            pixel_values = kwargs.get("pixel_values_videos", None)
+        image_grid_thw = kwargs.get("image_grid_thw", None)
+        video_grid_thw = kwargs.get("video_grid_thw", None)
+        mask = kwargs.get("mask", None)
+        grid_thw = image_grid_thw if image_grid_thw is not None else video_grid_thw
+        eng = self._engine()
+        ids_host = _np(input_ids)
+        if ids_host.ndim == 1:
+            ids_host = ids_host[None]
+        lm = self.language_model
+        if pixel_values is None:
+            position_ids, rope_deltas = lm.get_rope_index(ids_host, attention_mask=mask)
+            return InputEmbeddingsFeatures(inputs_embeds=embed_tokens(eng, ids_host),
+                                           position_ids=position_ids, rope_deltas=rope_deltas)
+        cached = kwargs.get("cached_image_features", None)
+        if cached is not None:
+            hidden_states = cached
+        else:
+            hidden_states = self.vision_tower(pixel_values, grid_thw, output_hidden_states=False)
+        final = self.merge_input_ids_with_image_features(
+            self.config.image_token_id, self.config.video_token_id, hidden_states, None, ids_host,
+            _engine=eng)
+        position_ids, rope_deltas = lm.get_rope_index(ids_host, image_grid_thw, video_grid_thw, mask)
+        return InputEmbeddingsFeatures(inputs_embeds=final, position_ids=position_ids,
+                                       rope_deltas=rope_deltas)
+
+    @staticmethod
+    def merge_input_ids_with_image_features(image_token_id, video_token_id, image_features,
+                                            inputs_embeds, input_ids, _engine: Engine = None):
+        """qwen2_vl.py:78-148.  Host: count validation (the reference's ValueError);
+        device: one gather kernel (prefix sum of the image mask -> feature row).
+        `inputs_embeds=None` fuses the embedding lookup into the same kernel."""
+        ids = _np(input_ids)
+        if ids.ndim == 1:
+            ids = ids[None]
+        B, T = ids.shape
+        mask = ids == image_token_id
+        if mask.sum() == 0:
+            mask = ids == video_token_id
+        n_feats = int(image_features.shape[0])
+        start = 0
+        for b in range(B):
+            n = int(mask[b].sum())
+            if n > 0 and n_feats - start < n:
+                raise ValueError(
+                    f"Number of image token positions ({n}) does not match "
+                    f"number of image features ({max(n_feats - start, 0)}) for batch {b}")
+            start += n
+        eng = _engine
+        if eng is None:
+            raise N.B200Error("merge_input_ids_with_image_features needs the model's engine "
+                              "(call it through Model.get_input_embeddings or pass _engine=)")
+        H = int(image_features.shape[-1])
+        out = eng.empty((B, T, H))
+        feats = image_features.contiguous()
+        if inputs_embeds is None:
+            ids_dev = _ids_to_device(eng, ids)
+            N.check(eng.lib.b200_embed_merge(
+                ids_dev.data_ptr(), B, T, eng.weights["lm.embed"].data_ptr(), H, feats.data_ptr(),
+                n_feats, int(image_token_id), int(video_token_id), out.data_ptr(), 0, eng.s),
+                "embed_merge")
+            return out
+        # pre-computed embeddings: use them as the lookup table (row index = b*T + t)
+        sent = B * T
+        ids2 = np.where(mask, sent, np.arange(B * T).reshape(B, T))
+        ids_dev = _ids_to_device(eng, ids2)
+        table = inputs_embeds.reshape(B * T, H).contiguous()
+        N.check(eng.lib.b200_embed_merge(ids_dev.data_ptr(), B, T, table.data_ptr(), H,
+                                         feats.data_ptr(), n_feats, sent, sent, out.data_ptr(), 0,
+                                         eng.s), "embed_merge")
+        return out
+
+    @property
+    def layers(self):
+        return self.language_model.layers
+
+    def __call__(self, input_ids, pixel_values=None, mask=None, cache=None, **kwargs):
+        feats = self.get_input_embeddings(input_ids, pixel_values, **kwargs)
+        kwargs = {"pixel_values": pixel_values, **kwargs}
+        return self.language_model(input_ids, feats.inputs_embeds, mask=mask, cache=cache, **kwargs)
