@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native generate path.
+
+Workload (BASELINE.json configs[1], "C2"): Qwen2-VL-2B bf16, 1 synthetic image
+336x336 (144 merged image tokens), 128 text-side prompt tokens (T = 272),
+512 generated tokens, batch 1, greedy, EOS ignored; seeded random-init weights
+(no checkpoints offline).  One "step" = one whole request: ViT -> merge ->
+prefill -> 512 decode steps.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference ...                      # CPU restatement of the
+        reference path (oracle port; mlx itself is not installable offline)
+
+Prints ONE JSON line (rank 0).  `value` = decode tokens/s with inputs resident in
+HBM (CUDA events, max over ranks); `e2e` = the same request through the public
+API `generate(model, processor, prompt, image)` with a HOST image (preprocessing,
+pinned H2D of pixel_values, per-token D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TEXT, N_OUT, IMG_HW = 128, 512, (336, 336)
+W_BYTES_2B = 3_087_428_608      # decode weight bytes / token (bf16, tied head)
+KV_BYTES_PER_POS = 28_672       # 2 (k,v) * 2 kv heads * 128 * 2 B * 28 layers
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _engine_weights_to_oracle(model, cfg_o):
+    """Unpack the engine's packed device weights into the oracle's name space (fp32 CPU)."""
+    import torch
+    w = model.engine.weights
+    t, v = cfg_o.text, cfg_o.vision
+    H, hd = t.hidden_size, t.hidden_size // t.num_attention_heads
+    kvd = t.num_key_value_heads * hd
+    out = {}
+
+    def f(x):
+        return x.detach().float().cpu()
+
+    out["vision_tower.patch_embed.proj.weight"] = f(w["v.patch_embed.w"])
+    pairs = (("norm1.weight", "ln1.w"), ("norm1.bias", "ln1.b"), ("norm2.weight", "ln2.w"),
+             ("norm2.bias", "ln2.b"), ("attn.qkv.weight", "qkv.w"), ("attn.qkv.bias", "qkv.b"),
+             ("attn.proj.weight", "proj.w"), ("attn.proj.bias", "proj.b"),
+             ("mlp.fc1.weight", "fc1.w"), ("mlp.fc1.bias", "fc1.b"),
+             ("mlp.fc2.weight", "fc2.w"), ("mlp.fc2.bias", "fc2.b"))
+    for i in range(v.depth):
+        for a, b in pairs:
+            out[f"vision_tower.blocks.{i}.{a}"] = f(w[f"v.blk.{i}.{b}"])
+    for a, b in (("ln_q.weight", "ln.w"), ("ln_q.bias", "ln.b"), ("mlp.0.weight", "fc1.w"),
+                 ("mlp.0.bias", "fc1.b"), ("mlp.2.weight", "fc2.w"), ("mlp.2.bias", "fc2.b")):
+        out["vision_tower.merger." + a] = f(w["v.merger." + b])
+    out["language_model.model.embed_tokens.weight"] = f(w["lm.embed"])
+    out["language_model.model.norm.weight"] = f(w["lm.norm"])
+    for i in range(t.num_hidden_layers):
+        p = f"language_model.model.layers.{i}."
+        wqkv, bqkv, wgu = f(w[f"lm.{i}.wqkv"]), f(w[f"lm.{i}.bqkv"]), f(w[f"lm.{i}.wgu"])
+        out[p + "input_layernorm.weight"] = f(w[f"lm.{i}.ln1"])
+        out[p + "post_attention_layernorm.weight"] = f(w[f"lm.{i}.ln2"])
+        out[p + "self_attn.q_proj.weight"], out[p + "self_attn.k_proj.weight"], \
+            out[p + "self_attn.v_proj.weight"] = wqkv[:H], wqkv[H:H + kvd], wqkv[H + kvd:]
+        out[p + "self_attn.q_proj.bias"], out[p + "self_attn.k_proj.bias"], \
+            out[p + "self_attn.v_proj.bias"] = bqkv[:H], bqkv[H:H + kvd], bqkv[H + kvd:]
+        out[p + "self_attn.o_proj.weight"] = f(w[f"lm.{i}.wo"])
+        out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = \
+            wgu[:t.intermediate_size], wgu[t.intermediate_size:]
+        out[p + "mlp.down_proj.weight"] = f(w[f"lm.{i}.wd"])
+    return out
+
+
+def cpu_reference_run(W, n_decode, threads=None):
+    """Time the oracle (CPU restatement of the reference's path) on the C2 prompt:
+    ViT + merge + prefill once, then `n_decode` decode steps.  Returns dict."""
+    import numpy as np
+    import torch
+    from oracle import qwen2vl as O
+    if threads:
+        torch.set_num_threads(threads)
+    c = O.qwen2_vl_2b()
+    req = O.synthetic_request(c, N_TEXT, image_hw=IMG_HW, seed=0)
+    ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
+    R = O.Rounder("bf16")
+    t0 = time.perf_counter()
+    embeds, feats, pos, deltas = O.get_input_embeddings(c, W, ids, pv, grid, R)
+    cache = [O.OracleKVCache() for _ in range(c.text.num_hidden_layers)]
+    hidden = O.lm_layers_forward(c, W, embeds, pos, cache, R)
+    logits = O.lm_head(c, W, hidden[:, -1, :], R)
+    t1 = time.perf_counter()
+    for _ in range(n_decode):
+        lp = O.logprobs_from_logits(R, logits)
+        y = O.S.argmax_lowest(lp)
+        e = W["language_model.model.embed_tokens.weight"][y][:, None, :]
+        p = O.decode_position_ids(cache[0].offset, deltas, 1)
+        hidden = O.lm_layers_forward(c, W, e, p, cache, R)
+        logits = O.lm_head(c, W, hidden[:, -1, :], R)
+    t2 = time.perf_counter()
+    return {"prefill_s": t1 - t0, "decode_s": t2 - t1, "n_decode": n_decode,
+            "decode_tps": n_decode / (t2 - t1), "img_tps": 144 / (t1 - t0),
+            "cores": torch.get_num_threads()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import numpy as np
+    import torch
+
+    config = {"workload": "C2: Qwen2-VL-2B bf16, 1x336x336 image (144 img tokens) + 128 text "
+                          "tokens in (T=272), 512 greedy tokens out, batch 1",
+              "global_batch": world, "parallelism": f"dp{world} (one replica per GPU, "
+              "no per-step collective)", "l2": "weights streamed per token (3.09 GB) exceed the "
+              "126 MB L2; no flush needed"}
+
+    # ------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import qwen2vl as O
+        c = O.qwen2_vl_2b()
+        W = O.init_weights(c, 0)
+        n_dec = 4
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_reference_run(W, n_dec)
+            if i >= args.warmup:
+                vals.append(r)
+        dec_s = sum(v["decode_s"] for v in vals)
+        tps = len(vals) * n_dec / dec_s
+        line = {"impl": "reference", "metric": "decode_tokens_per_sec", "value": tps,
+                "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup,
+                "ms_per_step": 1e3 * sum(v["decode_s"] + v["prefill_s"] for v in vals) / len(vals),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": config,
+                "prefill_img_tokens_per_sec": len(vals) * 144 / sum(v["prefill_s"] for v in vals),
+                "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": vals[0]["cores"],
+                                 "kind": "port",
+                                 "sample": f"per step: C2 prompt ViT+prefill once, {n_dec} decode "
+                                           "steps (oracle = CPU restatement of the reference's "
+                                           "MLX-CPU path; mlx is not installable offline)"},
+                "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------ B200 arm
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from mlx_vlm_b200 import generate as api_generate
+    from mlx_vlm_b200.generate import generate_step
+    from mlx_vlm_b200.models.cache import make_prompt_cache
+    from mlx_vlm_b200.utils import load_synthetic, prepare_inputs
+
+    model, processor = load_synthetic("qwen2-vl-2b", seed=0, device=dev, n_text_tokens=N_TEXT)
+    model.config.eos_token_id = []  # benchmark: EOS ignored (fixed 512 tokens out)
+    eng = model.engine
+    if args.no_graph:
+        eng.set_graph(False)
+    if args.no_pdl:
+        eng.set_pdl(False)
+    if world > 1:
+        # the single collective of the design: rank 0's weights broadcast over NVLink (NCCL)
+        for name in sorted(eng.weights):
+            dist.broadcast(eng.weights[name], src=0)
+        torch.cuda.synchronize()
+
+    rng = np.random.default_rng(0)
+    image = rng.integers(0, 256, size=(IMG_HW[0], IMG_HW[1], 3), dtype=np.uint8)
+    prompt = "Describe this image in detail."
+    inputs = prepare_inputs(processor, images=[image], prompts=prompt, device=dev, stream=eng.stream)
+    ids = inputs["input_ids"]
+    pvd = inputs["pixel_values"]
+    grid = inputs["image_grid_thw"]
+    eng.stream.synchronize()
+    T = int(ids.shape[1])
+    assert T == N_TEXT + 144, T
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def device_step():
+        """one request with inputs resident in HBM; returns (prefill_ms, decode_ms)."""
+        cache = make_prompt_cache(model.language_model)
+        ev[0].record(eng.stream)
+        emb = model.get_input_embeddings(ids, pvd, image_grid_thw=grid)
+        model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache,
+                             position_ids=emb.position_ids, rope_deltas=emb.rope_deltas,
+                             logits_to_keep=1, reserve_tokens=T + N_OUT + 1)
+        ev[1].record(eng.stream)
+        model.language_model.fused_greedy_decode(N_OUT, cache, reserve_tokens=T + N_OUT + 1)
+        ev[2].record(eng.stream)
+        eng.stream.synchronize()
+        return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    pre_ms, dec_ms = 0.0, 0.0
+    for _ in range(args.steps):
+        a, b = device_step()
+        pre_ms += a
+        dec_ms += b
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = eng.launch_count - l0
+    clocks = sampler.stop()
+
+    # ---- e2e through the public API with a host image --------------------------
+    def e2e_step():
+        t = time.perf_counter()
+        r = api_generate(model, processor, prompt, image=[image], max_tokens=N_OUT)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t, r
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    e2e_t, e2e_gen_tps, e2e_prompt_tps = 0.0, [], []
+    for _ in range(args.steps):
+        dt, r = e2e_step()
+        e2e_t += dt
+        e2e_gen_tps.append(r.generation_tps)
+        e2e_prompt_tps.append(r.prompt_tps)
+        assert r.generation_tokens == N_OUT
+    barrier()
+
+    stats = torch.tensor([dec_ms, pre_ms, wall, e2e_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    dec_ms, pre_ms, wall, e2e_t = stats.tolist()
+
+    if rank == 0:
+        K = args.steps
+        dec_tps = world * K * N_OUT / (dec_ms / 1e3)
+        img_tps = world * K * 144 / (pre_ms / 1e3)
+        peak, peak_src = _peaks()
+        mean_ctx = T + N_OUT / 2
+        bytes_per_step = W_BYTES_2B + KV_BYTES_PER_POS * mean_ctx
+        step_ms = dec_ms / (K * N_OUT)
+        achieved = bytes_per_step / (step_ms / 1e3) / 1e9
+        line = {
+            "metric": "decode_tokens_per_sec", "value": dec_tps, "unit": "tokens/s",
+            "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": (pre_ms + dec_ms) / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "prefill_img_tokens_per_sec": img_tps,
+            "prefill_ms": pre_ms / K, "decode_ms_per_token": step_ms,
+            "wall_s_timed_region": wall,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": world * K * N_OUT / e2e_t, "unit": "tokens/s",
+                    "definition": "512 generated tokens / wall time of generate(model, processor, "
+                                  "prompt, image=[HxWx3 uint8 host array]) incl. host "
+                                  "preprocessing, H2D, ViT, prefill, decode, per-token D2H",
+                    "generation_tps_api": statistics.mean(e2e_gen_tps),
+                    "prompt_tps_api": statistics.mean(e2e_prompt_tps),
+                    "h2d_bytes_per_step": int(576 * 1176 * 4 + T * 4 + 3 * T * 4),
+                    "d2h_bytes_per_step": int(N_OUT * 4)},
+            "roofline": {"kernel": "decode-step CUDA graph (28 x {k_qkv,k_attn,k_res,k_gateup,"
+                                   "k_res} + k_head + k_sample), one launch = one token",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_step, "traffic": None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            W = _engine_weights_to_oracle(model, __import__("oracle.qwen2vl", fromlist=["x"]).qwen2_vl_2b())
+            r = cpu_reference_run(W, 6)
+            line["cpu_baseline"] = {
+                "value": r["decode_tps"], "unit": "tokens/s", "cores": r["cores"], "kind": "port",
+                "prefill_img_tokens_per_sec": r["img_tps"],
+                "sample": "same weights/prompt as the GPU run: ViT+merge+prefill (T=272) once, "
+                          "6 decode steps, torch-CPU fp32 matmuls with bf16 rounding points "
+                          "(oracle port of the reference's MLX-CPU path)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,8 @@ long b200_engine_tokens_launched(const b200_engine* e);
 long b200_engine_launch_count(const b200_engine* e);
 /* 0: decode via plain launches, 1: CUDA-graph replay (default) */
 int b200_engine_set_graph(b200_engine* e, int enabled);
+/* programmatic dependent launch between the decode-step kernels (default on) */
+int b200_engine_set_pdl(b200_engine* e, int enabled);
 /* CTAs per kv head in the decode attention cluster (1, 2, 4 or 8; default 8) */
 int b200_engine_set_attn_cluster(b200_engine* e, int cluster);
 

@@ -30,6 +30,8 @@ struct DecState {
 };
 
 void decode_set_sm_count(int n);
+void decode_set_pdl(bool on);
+int decode_prepare(const DecodeDims& d, int cluster);
 int head_grid();
 size_t attn_smem_bytes(const DecodeDims& d, int chunk_cap);
 int launch_qkv(const DecodeDims& d, const LayerW& lw, const bf16* h, bf16* qbuf, bf16* kc,

@@ -74,6 +74,7 @@ struct b200_engine {
   int last_steps = 0;
   bool timing_valid = false;
   int attn_cluster = 8;
+  int prepared_cap = -1, prepared_cluster = -1;
 
   DecodeDims dims() const {
     DecodeDims d;
@@ -497,6 +498,11 @@ int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3, int
   }
   // last row through the fused head + sampler; arms the decode state
   const DecodeDims d = e->dims();
+  if (e->prepared_cap != e->kv_cap || e->prepared_cluster != e->attn_cluster) {
+    if ((rc = decode_prepare(d, e->attn_cluster))) return rc;
+    e->prepared_cap = e->kv_cap;
+    e->prepared_cluster = e->attn_cluster;
+  }
   e->ctx_host = ctx0 + T;
   e->pos_host = ctx0 + T + rope_delta;
   if ((rc = launch_set_state(e->st, 0, e->ctx_host, e->pos_host, 0, 0, e->embed, e->h, c.hidden, s)))
@@ -543,6 +549,11 @@ int b200_engine_decode(b200_engine* e, int n_steps, const int* force_tokens_host
   if ((rc = launch_set_state(e->st, 0, e->ctx_host, e->pos_host, force_tokens_host ? 1 : 0, 0,
                              e->embed, e->h, e->cfg.hidden, s)))
     return rc;
+  if (e->prepared_cap != e->kv_cap || e->prepared_cluster != e->attn_cluster) {
+    if ((rc = decode_prepare(e->dims(), e->attn_cluster))) return rc;
+    e->prepared_cap = e->kv_cap;
+    e->prepared_cluster = e->attn_cluster;
+  }
   if (e->use_graph && !e->gexec) {
     // capture one step on the engine's own stream (capture does not execute)
     cudaGraph_t graph = nullptr;
@@ -585,6 +596,12 @@ long b200_engine_launch_count(const b200_engine* e) { return e ? e->launches : 0
 int b200_engine_set_graph(b200_engine* e, int enabled) {
   B200_REQUIRE(e, "set_graph: null engine");
   e->use_graph = enabled != 0;
+  return B200_OK;
+}
+int b200_engine_set_pdl(b200_engine* e, int enabled) {
+  B200_REQUIRE(e, "set_pdl: null engine");
+  decode_set_pdl(enabled != 0);
+  invalidate_graph(e);
   return B200_OK;
 }
 int b200_engine_set_attn_cluster(b200_engine* e, int cluster) {

@@ -174,5 +174,8 @@ class Engine:
     def set_graph(self, enabled: bool):
         N.check(self.lib.b200_engine_set_graph(self.h, int(enabled)), "set_graph")
 
+    def set_pdl(self, enabled: bool):
+        N.check(self.lib.b200_engine_set_pdl(self.h, int(enabled)), "set_pdl")
+
     def set_attn_cluster(self, n: int):
         N.check(self.lib.b200_engine_set_attn_cluster(self.h, int(n)), "set_attn_cluster")
