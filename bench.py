@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--pdl", action="store_true")
+    ap.add_argument("--no-mega", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -238,6 +240,10 @@ def main():
         eng.set_graph(False)
     if args.no_pdl:
         eng.set_pdl(False)
+    if args.pdl:
+        eng.set_pdl(True)
+    if args.no_mega:
+        eng.set_mega(False)
     if world > 1:
         # the single collective of the design: rank 0's weights broadcast over NVLink (NCCL)
         for name in sorted(eng.weights):

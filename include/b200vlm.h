@@ -186,6 +186,15 @@ long b200_engine_tokens_launched(const b200_engine* e);
 long b200_engine_launch_count(const b200_engine* e);
 /* 0: decode via plain launches, 1: CUDA-graph replay (default) */
 int b200_engine_set_graph(b200_engine* e, int enabled);
+/* 1 (default): the decode step is ONE persistent kernel (k_mega: weight ring +
+ * software grid barrier); 0: one kernel per phase (28 x 5 + 2 launches). */
+int b200_engine_set_mega(b200_engine* e, int enabled);
+/* synchronous: reads the device-side error flag (0 = none; a bounded wait gave up) */
+int b200_engine_device_error(b200_engine* e, int* out);
+/* debugging aid (k_mega): first call enables per-barrier globaltimer stamps, later
+ * calls copy them out: out_host[2][1024][2] int64 = (arrive, release) per grid barrier
+ * for CTA 0 and the last CTA of the most recent step. */
+int b200_engine_mega_timeline(b200_engine* e, long long* out_host);
 /* programmatic dependent launch between the decode-step kernels (default on) */
 int b200_engine_set_pdl(b200_engine* e, int enabled);
 /* CTAs per kv head in the decode attention cluster (1, 2, 4 or 8; default 8) */

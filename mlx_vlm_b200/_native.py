@@ -68,6 +68,9 @@ SIGNATURES = {
     "b200_engine_set_graph": (_I, [_P, _I]),
     "b200_engine_set_attn_cluster": (_I, [_P, _I]),
     "b200_engine_set_pdl": (_I, [_P, _I]),
+    "b200_engine_set_mega": (_I, [_P, _I]),
+    "b200_engine_mega_timeline": (_I, [_P, _P]),
+    "b200_engine_device_error": (_I, [_P, C.POINTER(_I)]),
     "b200_engine_fetch_tokens": (_I, [_P, _L, _I, _P, _P]),
     "b200_memcpy_d2d": (_I, [_P, _P, _L, _P]),
     "b200_memcpy_h2d": (_I, [_P, _P, _L, _P]),

@@ -27,7 +27,45 @@ struct DecState {
   int pos;        // rope position of the next step (ctx + rope_delta)
   int n_out;      // tokens written to the token log
   int use_force;  // teacher forcing (tests)
+  int error;      // set by a bounded wait that gave up (1: grid barrier, 2: mbarrier)
+  unsigned long long bar_base;  // k_mega: value of the grid-barrier counter at step start
 };
+
+// ---- k_mega (decode_mega.cu): the whole step as one persistent kernel ----------
+constexpr int MEGA_MAX_LAYERS = 64;
+struct MegaPhase {
+  int K, N;    // reduction length, output rows
+  int R, S;    // row(-pair)s per tile, K slices per row (R*S == 8 consumer warps)
+  int tiles;
+};
+struct MegaP {
+  DecodeDims d;
+  int n_layers;
+  LayerW layers[MEGA_MAX_LAYERS];  // in kernel-parameter (constant) space
+  const bf16 *final_norm, *head, *embed;
+  bf16 *h, *qbuf, *attn, *act, *logits, *logprobs;
+  bf16* kv;              // layer 0 K plane of cache row 0
+  long kv_layer_stride;  // elements between layers
+  long kv_v_offset;      // elements from a layer's K plane to its V plane
+  float2* partials;
+  DecState* st;
+  int* token_log;
+  int log_cap;
+  const int* force;
+  const float* inv_freq;
+  MegaPhase ph[5];  // QKV, ORES, GATEUP, DRES, HEAD
+  int n_stages, stage_bytes;
+  int attn_ctas, hsplit;
+  unsigned long long* bar;  // monotonic grid-barrier counter
+  int advance;
+  int l2_prefetch;
+  float* att_part;  // [groups][8 units][4*hd] fp32 partial attention outputs
+  int* att_cnt;     // [groups][2] arrival counters (zero between phases)
+  float* att_stats; // [groups][8 units][4] (max, sum exp) pairs
+  long long* dbg;  // optional [2][1024][2] globaltimer stamps (arrive, release) per barrier
+};
+int mega_fill(MegaP& p, int sm_count);
+int mega_launch(const MegaP& p, int sm_count, cudaStream_t s);
 
 void decode_set_sm_count(int n);
 void decode_set_pdl(bool on);

@@ -1,0 +1,937 @@
+// k_mega: the WHOLE decode step (28 x {qkv, attention, o_proj, gate/up, down} + head
+// + sampler) as ONE persistent kernel, one CTA per SM.
+//
+// Why: the step is a chain of ~140 small dependent phases.  As separate kernels
+// each boundary costs several microseconds during which HBM idles (measured: the
+// 4.7 MB o_proj kernel takes 5.9 us, 0.7 us of it streaming).  Here
+//   * warp 8 of every CTA is a PRODUCER that walks the static tile schedule of the
+//     whole step and streams weight tiles (cp.async.bulk -> shared-memory ring,
+//     mbarrier complete_tx) without ever waiting for a phase boundary: the ring
+//     (up to 4 x 48 KB per SM, ~28 MB chip-wide) runs ahead across phases and layers;
+//   * warps 0..7 are CONSUMERS that execute the phases in order, separated by a
+//     software grid barrier (one atomic + acquire spin, ~1 us) instead of a kernel
+//     boundary; activations cross CTAs through L2 (ld.global.cg).
+// Rounding points follow oracle/qwen2vl.py::lm_layers_forward (same device
+// functions as the multi-kernel path in decode.cu).
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+// bounded wait: a scheduling bug must not hang the GPU (sets *err and falls through)
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity, int* err) {
+  uint32_t done;
+  const uint32_t addr = s_u32(bar);
+  unsigned spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 20)) {
+      *err = 2;
+      break;
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1], %2, [%3], %4;" ::"r"(s_u32(dst)),
+      "l"(src), "r"(bytes), "r"(s_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// activations written by other CTAs in an earlier phase: read through L2
+__device__ __forceinline__ uint4 ldcg16(const void* p) {
+  return __ldcg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ float ldcg_bf(const bf16* p) {
+  return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+enum { PH_QKV = 0, PH_ORES = 1, PH_GATEUP = 2, PH_DRES = 3, PH_HEAD = 4 };
+
+template <int MODE>
+struct PhTraits {
+  static constexpr bool PAIR = (MODE == PH_QKV || MODE == PH_GATEUP);
+  static constexpr bool NORM = (MODE == PH_QKV || MODE == PH_GATEUP || MODE == PH_HEAD);
+  static constexpr int NRW = PAIR ? 2 : 1;
+};
+
+}  // namespace
+
+constexpr int MEGA_THREADS = 288;
+constexpr int MEGA_STAGE = 48 * 1024;
+constexpr int MEGA_ATT_G = 4;
+
+struct MegaShared {
+  uint64_t full_bar[8], empty_bar[8];
+  float red[2][8][2];
+  float2 wstat[8];
+  float s_m[8][MEGA_ATT_G], s_l[8][MEGA_ATT_G];
+  unsigned long long bar_base;
+  float lse;
+  unsigned long long best;
+  int feed;
+  int err;
+};
+
+// ring position shared by producer and consumers (each keeps its own copy)
+struct Ring {
+  uint32_t seq;
+  int n_stages;
+  __device__ __forceinline__ int slot() const { return (int)(seq % (uint32_t)n_stages); }
+  __device__ __forceinline__ uint32_t parity() const { return (seq / (uint32_t)n_stages) & 1u; }
+};
+
+template <int MODE>
+__device__ __forceinline__ const bf16* mega_tile_src(const MegaPhase& g, const bf16* W,
+                                                     const bf16* W2, int hd, int t, int m) {
+  if (MODE == PH_QKV) {
+    const int half = hd >> 1;
+    const int per_slot = half / g.R;
+    const int slot = t / per_slot, jb = t % per_slot;
+    return W + ((long)slot * hd + (long)m * half + (long)jb * g.R) * g.K;
+  }
+  if (MODE == PH_GATEUP) return (m == 0 ? W : W2) + (long)t * g.R * g.K;
+  return W + (long)t * g.R * g.K;
+}
+
+// ---- producer: stream the tiles of one phase --------------------------------
+template <int MODE>
+__device__ __forceinline__ void produce_phase(const MegaPhase& g, const bf16* W, const bf16* W2,
+                                              int hd, uint8_t* ring, MegaShared* sh, Ring& rg,
+                                              uint64_t pol) {
+  using T = PhTraits<MODE>;
+  const int rows_unit = g.K * 2;
+  for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+    const int s = rg.slot();
+    mb_wait(&sh->empty_bar[s], rg.parity() ^ 1u, &sh->err);
+    int rows = g.R;
+    if (MODE != PH_QKV) rows = min(g.R, g.N - t * g.R);
+    const uint32_t bytes = (uint32_t)rows * rows_unit;
+    mb_expect_tx(&sh->full_bar[s], bytes * T::NRW);
+    uint8_t* dst = ring + (long)s * MEGA_STAGE;
+    bulk_g2s(dst, mega_tile_src<MODE>(g, W, W2, hd, t, 0), bytes, &sh->full_bar[s], pol);
+    if (T::PAIR)
+      bulk_g2s(dst + (long)g.R * rows_unit, mega_tile_src<MODE>(g, W, W2, hd, t, 1), bytes,
+               &sh->full_bar[s], pol);
+    ++rg.seq;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void l2_prefetch_phase(const MegaPhase& g, const bf16* W,
+                                                  const bf16* W2) {
+  const int rows_unit = g.K * 2;
+  for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+    const int rows = min(g.R, g.N - t * g.R);
+    const uint32_t bytes = (uint32_t)rows * rows_unit;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + (long)t * g.R * g.K),
+                 "r"(bytes)
+                 : "memory");
+    if (PhTraits<MODE>::PAIR)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W2 + (long)t * g.R * g.K),
+                   "r"(bytes)
+                   : "memory");
+  }
+}
+
+// ---- consumers: one GEMV phase ----------------------------------------------
+struct PhaseIO {
+  const bf16* x;     // activation vector (cross-CTA: read with ld.cg)
+  const bf16* lnw;   // RMSNorm weight
+  const bf16* bias;  // QKV
+  bf16* out;         // h / act / logits / qbuf
+  bf16 *kc, *vc;     // QKV
+  float2* partials;  // HEAD
+};
+
+template <int MODE, int CHX>
+__device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g, const PhaseIO& io,
+                                              uint8_t* ring, MegaShared* sh, Ring& rg, int ctx,
+                                              int pos) {
+  using T = PhTraits<MODE>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rloc = warp % g.R, sub = warp / g.R;
+  const int nvec = g.K >> 3;
+  const int cb = (int)((long)nvec * sub / g.S), ce = (int)((long)nvec * (sub + 1) / g.S);
+  const int rows_unit = g.K * 2;
+  // activation slice -> registers (packed bf16)
+  uint4 xv[CHX];
+#pragma unroll
+  for (int u = 0; u < CHX; ++u) {
+    const int c = cb + lane + 32 * u;
+    xv[u] = (c < ce) ? ldcg16(io.x + (long)c * 8) : make_uint4(0, 0, 0, 0);
+  }
+  if (T::NORM) {
+    uint4 lw4[CHX];
+#pragma unroll
+    for (int u = 0; u < CHX; ++u) {
+      const int c = cb + lane + 32 * u;
+      lw4[u] = (c < ce) ? __ldg(reinterpret_cast<const uint4*>(io.lnw + (long)c * 8))
+                        : make_uint4(0, 0, 0, 0);
+    }
+    float ss = 0.f;
+    if (g.S == 1) {
+#pragma unroll
+      for (int u = 0; u < CHX; ++u) {
+        float f[8];
+        unpack8(xv[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+      }
+    } else {
+      for (int c = lane; c < nvec; c += 32) {
+        float f[8];
+        unpack8(ldcg16(io.x + (long)c * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+      }
+    }
+    ss = warp_sum(ss);
+    const float rs = 1.0f / sqrtf(ss / (float)g.K + p.d.eps);
+#pragma unroll
+    for (int u = 0; u < CHX; ++u) {
+      float f[8], lf[8];
+      unpack8(xv[u], f);
+      unpack8(lw4[u], lf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = rbf(rbf(f[j] * rs) * lf[j]);
+      xv[u].x = pack2(f[0], f[1]);
+      xv[u].y = pack2(f[2], f[3]);
+      xv[u].z = pack2(f[4], f[5]);
+      xv[u].w = pack2(f[6], f[7]);
+    }
+  }
+  float run_m = -INFINITY, run_l = 0.f;
+  // epilogue operands fetched BEFORE the tiles are waited for (off the critical path)
+  float hpre = 0.f;  // ORES/DRES: lane i holds the residual value of this warp's i-th tile
+  if ((MODE == PH_ORES || MODE == PH_DRES) && sub == 0) {
+    const int t = blockIdx.x + lane * gridDim.x;
+    const int r = t * g.R + rloc;
+    if (t < g.tiles && r < g.N) hpre = ldcg_bf(io.out + r);
+  }
+  float pb1 = 0.f, pb2 = 0.f, pc = 1.f, psn = 0.f;  // QKV, first tile: bias + rotary factors
+  if (MODE == PH_QKV && (int)blockIdx.x < g.tiles) {
+    const int hd = p.d.hd, half = hd >> 1;
+    const int per_slot = half / g.R;
+    const int slot = blockIdx.x / per_slot, j = (blockIdx.x % per_slot) * g.R + rloc;
+    pb1 = bf2f(io.bias[slot * hd + j]);
+    pb2 = bf2f(io.bias[slot * hd + j + half]);
+    const float ang = (float)pos * p.inv_freq[j];
+    pc = rbf(cosf(ang));
+    psn = rbf(sinf(ang));
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < g.tiles; t += gridDim.x, ++it) {
+    const int s = rg.slot();
+    int rows = g.R;
+    if (MODE != PH_QKV) rows = min(g.R, g.N - t * g.R);
+    mb_wait(&sh->full_bar[s], rg.parity(), &sh->err);
+    ++rg.seq;
+    const uint8_t* base = ring + (long)s * MEGA_STAGE + (long)rloc * rows_unit;
+    float acc[T::NRW];
+    {
+      float a8[T::NRW][8];
+#pragma unroll
+      for (int m = 0; m < T::NRW; ++m)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[m][j] = 0.f;
+      if (rloc < rows) {
+#pragma unroll
+        for (int u0 = 0; u0 < CHX; u0 += 2) {
+          uint4 w4[T::NRW][2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = cb + lane + 32 * (u0 + q);
+#pragma unroll
+            for (int m = 0; m < T::NRW; ++m)
+              w4[m][q] = (u0 + q < CHX && c < ce)
+                             ? *reinterpret_cast<const uint4*>(base + (long)m * g.R * rows_unit +
+                                                               (long)c * 16)
+                             : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (u0 + q < CHX) {
+              float xf[8];
+              unpack8(xv[u0 + q], xf);
+#pragma unroll
+              for (int m = 0; m < T::NRW; ++m) {
+                float wf[8];
+                unpack8(w4[m][q], wf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a8[m][j] = fmaf(wf[j], xf[j], a8[m][j]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < T::NRW; ++m)
+        acc[m] = ((a8[m][0] + a8[m][1]) + (a8[m][2] + a8[m][3])) +
+                 ((a8[m][4] + a8[m][5]) + (a8[m][6] + a8[m][7]));
+    }
+#pragma unroll
+    for (int m = 0; m < T::NRW; ++m) acc[m] = warp_sum(acc[m]);
+    __syncwarp();
+    if (lane == 0) mb_arrive(&sh->empty_bar[s]);
+    if (g.S > 1) {
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < T::NRW; ++m) sh->red[it & 1][warp][m] = acc[m];
+      }
+      cbar();
+      if (sub == 0) {
+#pragma unroll
+        for (int m = 0; m < T::NRW; ++m) {
+          float a = 0.f;
+          for (int q = 0; q < g.S; ++q) a += sh->red[it & 1][rloc + q * g.R][m];
+          acc[m] = a;
+        }
+      }
+    }
+    float hv = 0.f;
+    if (MODE == PH_ORES || MODE == PH_DRES) hv = __shfl_sync(0xffffffffu, hpre, it & 31);
+    if (sub == 0 && lane == 0 && rloc < rows) {
+      if (MODE == PH_QKV) {
+        const int hd = p.d.hd, half = hd >> 1;
+        const int per_slot = half / g.R;
+        const int slot = t / per_slot, j = (t % per_slot) * g.R + rloc;
+        const int r1 = slot * hd + j, r2 = r1 + half;
+        const float y1 = rbf(acc[0] + (it == 0 ? pb1 : bf2f(io.bias[r1])));
+        const float y2 = rbf(acc[T::NRW - 1] + (it == 0 ? pb2 : bf2f(io.bias[r2])));
+        if (slot >= p.d.n_heads + p.d.n_kv) {
+          bf16* dst = io.vc + ((long)(slot - p.d.n_heads - p.d.n_kv) * p.d.cap + ctx) * hd;
+          dst[j] = f2bf(y1);
+          dst[j + half] = f2bf(y2);
+        } else {
+          float c = pc, sn = psn;
+          if (it != 0) {
+            const float ang = (float)pos * p.inv_freq[j];
+            c = rbf(cosf(ang));
+            sn = rbf(sinf(ang));
+          }
+          const float o1 = rbf(rbf(y1 * c) + rbf((-y2) * sn));
+          const float o2 = rbf(rbf(y2 * c) + rbf(y1 * sn));
+          bf16* dst = (slot < p.d.n_heads)
+                          ? io.out + (long)slot * hd
+                          : io.kc + ((long)(slot - p.d.n_heads) * p.d.cap + ctx) * hd;
+          dst[j] = f2bf(o1);
+          dst[j + half] = f2bf(o2);
+        }
+      } else if (MODE == PH_GATEUP) {
+        io.out[t * g.R + rloc] = f2bf(swiglu_bf(rbf(acc[0]), rbf(acc[T::NRW - 1])));
+      } else if (MODE == PH_ORES || MODE == PH_DRES) {
+        const int r = t * g.R + rloc;
+        if (it >= 32) hv = ldcg_bf(io.out + r);
+        io.out[r] = f2bf(rbf(hv + rbf(acc[0])));
+      } else {  // HEAD
+        const float a = rbf(acc[0]);
+        io.out[t * g.R + rloc] = f2bf(a);
+        const float mn = fmaxf(run_m, a);
+        run_l = run_l * expf(run_m - mn) + expf(a - mn);
+        run_m = mn;
+      }
+    }
+  }
+  if (MODE == PH_HEAD) {
+    if (lane == 0) sh->wstat[warp] = make_float2(run_m, run_l);
+    cbar();
+    if (threadIdx.x == 0) {
+      float M = -INFINITY;
+      for (int i = 0; i < 8; ++i) M = fmaxf(M, sh->wstat[i].x);
+      float L = 0.f;
+      for (int i = 0; i < 8; ++i)
+        if (sh->wstat[i].y > 0.f) L += sh->wstat[i].y * expf(sh->wstat[i].x - M);
+      io.partials[blockIdx.x] = make_float2(M, L);
+    }
+  }
+}
+
+// ---- consumers: attention ------------------------------------------------------
+// Under the weight stream every dependent global round trip costs ~1 us, so the phase
+// is built around the NUMBER of such trips.  CTA (grp, unit): grp = (kv head, q-head
+// group), unit = one of ATT_UN key ranges.
+//   1. scores of the OWN key range (coalesced: 8 lanes per key, 4 keys per warp
+//      instruction, all K loads of the range in flight at once), local (max, sum exp)
+//      per head -> global stats;
+//   2. group barrier among the ATT_UN CTAs of the group (atomic counter);
+//   3. global (M, L) from the ATT_UN stats, p = bf16(exp(s - M) / L), partial P.V
+//      (V rows were requested before the barrier);
+//   4. the last CTA of the group to finish sums the partial outputs in a fixed order.
+// Measured alternatives (tools/mega_timeline.py, ctx ~470): one CTA per (kv head,
+// group) 15.9 us; one CTA per q head 17.1 us; every unit recomputing all scores
+// 11.1 us; this 10.6 us.
+constexpr int ATT_UN = 8;
+
+template <int HD>
+__device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const bf16* vc,
+                                           float* scratch, MegaShared* sh, int nkeys) {
+  constexpr int EPL = HD / 32, SEG = HD / 8, AG = MEGA_ATT_G, NV = SEG / 8, UNR = 2;
+  const DecodeDims& d = p.d;
+  const int Gall = d.n_heads / d.n_kv;
+  const int G = Gall / p.hsplit;
+  const int ucap = (d.cap + ATT_UN - 1) / ATT_UN;
+  float* sc = scratch;                       // [AG][ucap]
+  float* red = sc + (long)AG * ucap;         // [8][AG*HD]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x / ATT_UN, unit = blockIdx.x % ATT_UN;
+  const int kvh = grp / p.hsplit;
+  const int h0 = kvh * Gall + (grp % p.hsplit) * G;
+  const bf16* kb = kc + (long)kvh * d.cap * HD;
+  const bf16* vb = vc + (long)kvh * d.cap * HD;
+  const int per = (nkeys + ATT_UN - 1) / ATT_UN;
+  const int u0 = min(nkeys, unit * per), u1 = min(nkeys, u0 + per);
+  const int seg = lane & 7, ksub = lane >> 3;
+  float qr[AG][SEG];
+#pragma unroll
+  for (int g = 0; g < AG; ++g) {
+    if (g < G) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float f[8];
+        unpack8(ldcg16(p.qbuf + (long)(h0 + g) * HD + seg * SEG + v * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qr[g][v * 8 + i] = rbf(f[i] * d.scale_bf);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < SEG; ++i) qr[g][i] = 0.f;
+    }
+  }
+  // ---- 1. scores of the own range ----
+  float lm[AG];
+#pragma unroll
+  for (int g = 0; g < AG; ++g) lm[g] = -INFINITY;
+  for (int j0 = u0 + warp * 4; j0 < u1; j0 += 32 * UNR) {
+    uint4 kv[UNR][NV];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const int j = j0 + 32 * q + ksub;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        kv[q][v] = (j < u1) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const int j = j0 + 32 * q + ksub;
+      float s[AG];
+#pragma unroll
+      for (int g = 0; g < AG; ++g) s[g] = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float kf[8];
+        unpack8(kv[q][v], kf);
+#pragma unroll
+        for (int g = 0; g < AG; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[g] = fmaf(qr[g][v * 8 + i], kf[i], s[g]);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+        for (int g = 0; g < AG; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+      if (j < u1 && seg == 0) {
+#pragma unroll
+        for (int g = 0; g < AG; ++g) {
+          const float r = rbf(s[g]);
+          sc[(long)g * ucap + (j - u0)] = r;
+          lm[g] = fmaxf(lm[g], r);
+        }
+      }
+    }
+  }
+  // V rows of this warp's first keys: requested now, consumed after the group barrier
+  constexpr int VPRE = 4;
+  float vpre[VPRE][EPL];
+#pragma unroll
+  for (int q = 0; q < VPRE; ++q) {
+    const int j = u0 + warp + 8 * q;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) vpre[q][e] = 0.f;
+    if (j < u1) {
+      const bf16* vr = vb + (long)j * HD + lane * EPL;
+      if (EPL == 4) {
+        float t4[4];
+        unpack4(__ldcg(reinterpret_cast<const uint2*>(vr)), t4);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) vpre[q][e] = t4[e];
+      } else {
+        const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(vr));
+        vpre[q][0] = __uint_as_float(w << 16);
+        vpre[q][EPL - 1] = __uint_as_float(w & 0xffff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < AG; ++g) {
+    lm[g] = warp_max(lm[g]);
+    if (lane == 0) sh->s_m[warp][g] = lm[g];
+  }
+  cbar();
+  float ml[AG], ls[AG];
+#pragma unroll
+  for (int g = 0; g < AG; ++g) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = fmaxf(m, sh->s_m[w][g]);
+    ml[g] = m;
+    ls[g] = 0.f;
+  }
+  for (int j = threadIdx.x; j < u1 - u0; j += 256) {
+#pragma unroll
+    for (int g = 0; g < AG; ++g) ls[g] += expf(sc[(long)g * ucap + j] - ml[g]);
+  }
+#pragma unroll
+  for (int g = 0; g < AG; ++g) {
+    ls[g] = warp_sum(ls[g]);
+    if (lane == 0) sh->s_l[warp][g] = ls[g];
+  }
+  cbar();
+  // ---- 2. publish the local statistics, group barrier ----
+  float2* gstats = reinterpret_cast<float2*>(p.att_stats) + (long)grp * ATT_UN * AG;
+  if (threadIdx.x < AG) {
+    float l = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) l += sh->s_l[w][threadIdx.x];
+    gstats[unit * AG + threadIdx.x] = make_float2(ml[threadIdx.x], (u1 > u0) ? l : 0.f);
+  }
+  cbar();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(&p.att_cnt[grp * 2]), "r"(1)
+                 : "memory");
+    unsigned spins = 0;
+    int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(&p.att_cnt[grp * 2])
+                   : "memory");
+      if (seen < ATT_UN && ++spins > (1u << 22)) {
+        sh->err = 3;
+        break;
+      }
+    } while (seen < ATT_UN);
+  }
+  cbar();
+  // ---- 3. global statistics, p, partial P.V over the own range ----
+  float M[AG], L[AG];
+#pragma unroll
+  for (int g = 0; g < AG; ++g) {
+    float2 stv[ATT_UN];
+#pragma unroll
+    for (int u = 0; u < ATT_UN; ++u) stv[u] = __ldcg(&gstats[u * AG + g]);
+    float m = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < ATT_UN; ++u) m = fmaxf(m, stv[u].x);
+    float l = 0.f;
+#pragma unroll
+    for (int u = 0; u < ATT_UN; ++u)
+      if (stv[u].y > 0.f) l += stv[u].y * expf(stv[u].x - m);
+    M[g] = m;
+    L[g] = l;
+  }
+  float acc[AG][EPL];
+#pragma unroll
+  for (int g = 0; g < AG; ++g)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[g][e] = 0.f;
+#pragma unroll
+  for (int q = 0; q < VPRE; ++q) {
+    const int j = u0 + warp + 8 * q;
+    if (j < u1) {
+#pragma unroll
+      for (int g = 0; g < AG; ++g) {
+        const float pj = rbf(expf(sc[(long)g * ucap + (j - u0)] - M[g]) / L[g]);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[g][e] = fmaf(pj, vpre[q][e], acc[g][e]);
+      }
+    }
+  }
+  for (int j0 = u0 + warp + 8 * VPRE; j0 < u1; j0 += 32) {  // 4 keys per trip, loads first
+    float vf[4][EPL];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + 8 * q;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) vf[q][e] = 0.f;
+      if (j < u1) {
+        const bf16* vr = vb + (long)j * HD + lane * EPL;
+        if (EPL == 4) {
+          float t4[4];
+          unpack4(__ldcg(reinterpret_cast<const uint2*>(vr)), t4);
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) vf[q][e] = t4[e];
+        } else {
+          const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(vr));
+          vf[q][0] = __uint_as_float(w << 16);
+          vf[q][EPL - 1] = __uint_as_float(w & 0xffff0000u);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + 8 * q;
+      if (j < u1) {
+#pragma unroll
+        for (int g = 0; g < AG; ++g) {
+          const float pj = rbf(expf(sc[(long)g * ucap + (j - u0)] - M[g]) / L[g]);
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) acc[g][e] = fmaf(pj, vf[q][e], acc[g][e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < AG; ++g)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) red[((long)warp * AG + g) * HD + lane * EPL + e] = acc[g][e];
+  cbar();
+  float* mypart = p.att_part + ((long)grp * ATT_UN + unit) * AG * HD;
+  for (int i = threadIdx.x; i < G * HD; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[(long)w * AG * HD + i];
+    mypart[i] = s;
+  }
+  cbar();
+  // ---- 4. last CTA of the group combines ----
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int old = atomicAdd(&p.att_cnt[grp * 2 + 1], 1);
+    sh->feed = (old == ATT_UN - 1);
+    __threadfence();
+  }
+  cbar();
+  if (sh->feed) {
+    const float* gp = p.att_part + (long)grp * ATT_UN * AG * HD;
+    for (int i = threadIdx.x; i < G * HD; i += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int u = 0; u < ATT_UN; ++u) s += __ldcg(gp + (long)u * AG * HD + i);
+      p.attn[(long)h0 * HD + i] = f2bf(s);
+    }
+    if (threadIdx.x == 0) {  // every CTA of the group is past both counters by now
+      p.att_cnt[grp * 2] = 0;
+      p.att_cnt[grp * 2 + 1] = 0;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t orderable_u(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// software grid barrier among the consumer threads of all CTAs
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void grid_barrier(const MegaP& p, MegaShared* sh, unsigned& idx) {
+  cbar();
+  if (threadIdx.x == 0) {
+    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+      p.dbg[((blockIdx.x ? 1 : 0) * 1024 + idx) * 2] = gtimer();
+    const unsigned long long target = sh->bar_base + (unsigned long long)(idx + 1) * gridDim.x;
+    // release: the CTA's writes (ordered before by bar.sync) become visible before the count
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p.bar), "l"(1ull) : "memory");
+    unsigned spins = 0;
+    while (ld_acquire_u64(p.bar) < target) {
+      if (++spins > (1u << 22)) {
+        sh->err = 1;
+        break;
+      }
+    }
+    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+      p.dbg[((blockIdx.x ? 1 : 0) * 1024 + idx) * 2 + 1] = gtimer();
+  }
+  ++idx;
+  cbar();
+}
+
+template <int CHH, int CHI>
+__global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ MegaShared sh;
+  uint8_t* ring = sm;
+  float* scratch = reinterpret_cast<float*>(sm + (long)p.n_stages * MEGA_STAGE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.st->error) return;  // a previous step gave up: do not spin again
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_stages; ++s) {
+      mb_init(&sh.full_bar[s], 1);
+      mb_init(&sh.empty_bar[s], 8);
+    }
+    sh.err = 0;
+    sh.bar_base = p.st->bar_base;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  Ring rg;
+  rg.seq = 0;
+  rg.n_stages = p.n_stages;
+  const DecodeDims& d = p.d;
+
+  if (warp == 8) {
+    // ===== producer: the whole step's weight stream, never blocked by a phase =====
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      for (int l = 0; l < p.n_layers; ++l) {
+        const LayerW& lw = p.layers[l];
+        // the qkv/attention/o_proj chain is latency-bound (~20 us with ~11 MB of weights):
+        // use it to pull this CTA's share of the layer's MLP weights (82 MB chip-wide,
+        // fits the 126 MB L2) into L2, so the ring later refills at L2 speed.
+        // (measured, round 1: no gain — gate/up is consumer-bound at 8 warps — and a
+        // straggler CTA in the down phase; kept behind a switch for round 2)
+        if (p.l2_prefetch) {
+          l2_prefetch_phase<PH_GATEUP>(p.ph[PH_GATEUP], lw.wgu, lw.wgu + (long)d.inter * d.hidden);
+          l2_prefetch_phase<PH_DRES>(p.ph[PH_DRES], lw.wd, nullptr);
+        }
+        produce_phase<PH_QKV>(p.ph[PH_QKV], lw.wqkv, nullptr, d.hd, ring, &sh, rg, pol);
+        produce_phase<PH_ORES>(p.ph[PH_ORES], lw.wo, nullptr, d.hd, ring, &sh, rg, pol);
+        produce_phase<PH_GATEUP>(p.ph[PH_GATEUP], lw.wgu, lw.wgu + (long)d.inter * d.hidden, d.hd,
+                                 ring, &sh, rg, pol);
+        produce_phase<PH_DRES>(p.ph[PH_DRES], lw.wd, nullptr, d.hd, ring, &sh, rg, pol);
+      }
+      produce_phase<PH_HEAD>(p.ph[PH_HEAD], p.head, nullptr, d.hd, ring, &sh, rg, pol);
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  unsigned bidx = 0;
+  const int ctx = p.st->ctx, pos = p.st->pos;
+  const long plane = (long)d.n_kv * d.cap * d.hd;  // one K (or V) plane of a layer, batch 1
+  for (int l = 0; l < p.n_layers; ++l) {
+    const LayerW& lw = p.layers[l];
+    bf16* kc = p.kv + (long)l * p.kv_layer_stride;
+    bf16* vc = kc + p.kv_v_offset;
+    (void)plane;
+    {
+      PhaseIO io = {p.h, lw.ln1, lw.bqkv, p.qbuf, kc, vc, nullptr};
+      consume_phase<PH_QKV, CHH>(p, p.ph[PH_QKV], io, ring, &sh, rg, ctx, pos);
+    }
+    grid_barrier(p, &sh, bidx);
+    if ((int)blockIdx.x < p.attn_ctas) {
+      if (d.hd == 128) attn_phase<128>(p, kc, vc, scratch, &sh, ctx + 1);
+      else attn_phase<64>(p, kc, vc, scratch, &sh, ctx + 1);
+    }
+    grid_barrier(p, &sh, bidx);
+    {
+      PhaseIO io = {p.attn, nullptr, nullptr, p.h, nullptr, nullptr, nullptr};
+      if (p.ph[PH_ORES].S == 1) consume_phase<PH_ORES, CHH>(p, p.ph[PH_ORES], io, ring, &sh, rg, 0, 0);
+      else consume_phase<PH_DRES, CHH>(p, p.ph[PH_ORES], io, ring, &sh, rg, 0, 0);
+    }
+    grid_barrier(p, &sh, bidx);
+    {
+      PhaseIO io = {p.h, lw.ln2, nullptr, p.act, nullptr, nullptr, nullptr};
+      consume_phase<PH_GATEUP, CHH>(p, p.ph[PH_GATEUP], io, ring, &sh, rg, 0, 0);
+    }
+    grid_barrier(p, &sh, bidx);
+    {
+      PhaseIO io = {p.act, nullptr, nullptr, p.h, nullptr, nullptr, nullptr};
+      consume_phase<PH_DRES, CHI>(p, p.ph[PH_DRES], io, ring, &sh, rg, 0, 0);
+    }
+    grid_barrier(p, &sh, bidx);
+  }
+  {
+    PhaseIO io = {p.h, p.final_norm, nullptr, p.logits, nullptr, nullptr, p.partials};
+    consume_phase<PH_HEAD, CHH>(p, p.ph[PH_HEAD], io, ring, &sh, rg, 0, 0);
+  }
+  grid_barrier(p, &sh, bidx);
+  // ---- sampler: logprobs = bf16(logits - bf16(lse)), argmax with lowest index ----
+  if (warp == 0) {
+    float M = -INFINITY;
+    for (int i = lane; i < (int)gridDim.x; i += 32) M = fmaxf(M, __ldcg(&p.partials[i]).x);
+    M = warp_max(M);
+    float L = 0.f;
+    for (int i = lane; i < (int)gridDim.x; i += 32) {
+      const float2 pr = __ldcg(&p.partials[i]);
+      if (pr.y > 0.f) L += pr.y * expf(pr.x - M);
+    }
+    L = warp_sum(L);
+    if (lane == 0) {
+      sh.lse = rbf(M + logf(L));
+      sh.best = 0ull;
+    }
+  }
+  cbar();
+  {
+    const float lse = sh.lse;
+    unsigned long long best = 0ull;
+    const int nvec = d.vocab >> 3;
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < nvec; c += gridDim.x * 256) {
+      float f[8], o[8];
+      unpack8(ldcg16(p.logits + (long)c * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = rbf(f[j] - lse);
+        const unsigned long long key =
+            ((unsigned long long)orderable_u(o[j]) << 32) | (0xFFFFFFFFu - (uint32_t)(c * 8 + j));
+        best = key > best ? key : best;
+      }
+      uint4 ov;
+      ov.x = pack2(o[0], o[1]);
+      ov.y = pack2(o[2], o[3]);
+      ov.z = pack2(o[4], o[5]);
+      ov.w = pack2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(p.logprobs + (long)c * 8) = ov;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) atomicMax(&sh.best, best);
+    cbar();
+    if (threadIdx.x == 0) atomicMax(&p.st->best_key, sh.best);
+  }
+  grid_barrier(p, &sh, bidx);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      const unsigned long long key = ld_acquire_u64(&p.st->best_key);
+      const int tok = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+      const int n = p.st->n_out;
+      p.token_log[n % p.log_cap] = tok;
+      int feed = tok;
+      if (p.st->use_force) feed = p.force[n % p.log_cap];
+      sh.feed = feed;
+      p.st->tok = feed;
+      p.st->n_out = n + 1;
+      p.st->ctx += p.advance;
+      p.st->pos += p.advance;
+      p.st->best_key = 0ull;
+      p.st->bar_base = sh.bar_base + (unsigned long long)bidx * gridDim.x;
+      if (sh.err) p.st->error = sh.err;
+    }
+    cbar();
+    const int feed = sh.feed;
+    const int nv = d.hidden >> 3;
+    for (int c = threadIdx.x; c < nv; c += 256)
+      *reinterpret_cast<uint4*>(p.h + c * 8) =
+          __ldg(reinterpret_cast<const uint4*>(p.embed + (long)feed * d.hidden + c * 8));
+  } else if (threadIdx.x == 0 && sh.err) {
+    p.st->error = sh.err;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------
+static int mega_geometry(MegaPhase& g, int K, int N, bool pair, int units) {
+  g.K = K;
+  g.N = N;
+  const long unit = (long)K * 2 * (pair ? 2 : 1);
+  int R = 8;
+  while (R > 1 && (R * unit > MEGA_STAGE || R > units)) R >>= 1;
+  B200_REQUIRE(R * unit <= MEGA_STAGE, "mega: K=%d does not fit a %d-byte ring stage", K, MEGA_STAGE);
+  g.R = R;
+  g.S = 8 / R;
+  return B200_OK;
+}
+
+static size_t mega_attn_scratch(const DecodeDims& d) {
+  return ((size_t)MEGA_ATT_G * cdiv(d.cap, ATT_UN) + (size_t)8 * MEGA_ATT_G * d.hd) * 4;
+}
+
+int mega_fill(MegaP& p, int sm_count) {
+  const DecodeDims& d = p.d;
+  int rc;
+  const int half = d.hd / 2;
+  if ((rc = mega_geometry(p.ph[PH_QKV], d.hidden, 0, true, half))) return rc;
+  B200_REQUIRE(half % p.ph[PH_QKV].R == 0, "mega: head_dim/2 %% tile rows != 0");
+  p.ph[PH_QKV].tiles = (d.n_heads + 2 * d.n_kv) * (half / p.ph[PH_QKV].R);
+  if ((rc = mega_geometry(p.ph[PH_ORES], d.n_heads * d.hd, d.hidden, false, d.hidden))) return rc;
+  p.ph[PH_ORES].tiles = cdiv(d.hidden, p.ph[PH_ORES].R);
+  if ((rc = mega_geometry(p.ph[PH_GATEUP], d.hidden, d.inter, true, d.inter))) return rc;
+  p.ph[PH_GATEUP].tiles = cdiv(d.inter, p.ph[PH_GATEUP].R);
+  if ((rc = mega_geometry(p.ph[PH_DRES], d.inter, d.hidden, false, d.hidden))) return rc;
+  p.ph[PH_DRES].tiles = cdiv(d.hidden, p.ph[PH_DRES].R);
+  if ((rc = mega_geometry(p.ph[PH_HEAD], d.hidden, d.vocab, false, d.vocab))) return rc;
+  p.ph[PH_HEAD].tiles = cdiv(d.vocab, p.ph[PH_HEAD].R);
+  const int G = d.n_heads / d.n_kv;
+  int hs = 1;
+  while (G / hs > MEGA_ATT_G || (G % hs) != 0) ++hs;
+  if (hs == 1 && G % 2 == 0 && G >= 4) hs = 2;
+  p.hsplit = hs;
+  p.attn_ctas = d.n_kv * hs * ATT_UN;
+  B200_REQUIRE(p.attn_ctas <= sm_count, "mega: %d attention CTAs > %d SMs", p.attn_ctas, sm_count);
+  B200_REQUIRE(d.hd == 64 || d.hd == 128, "mega: head_dim %d (64|128)", d.hd);
+  const size_t scratch = mega_attn_scratch(d);
+  const long budget = 227 * 1024 - 1024 - (long)scratch;
+  int ns = (int)(budget / MEGA_STAGE);
+  B200_REQUIRE(ns >= 2, "mega: cache capacity %d leaves no room for the weight ring", d.cap);
+  p.n_stages = ns > 8 ? 8 : ns;
+  p.stage_bytes = MEGA_STAGE;
+  return B200_OK;
+}
+
+static int mega_chx(const MegaPhase& g) { return cdiv(cdiv(g.K >> 3, g.S), 32); }
+
+template <int CHH, int CHI>
+static int mega_launch_t(const MegaP& p, int grid, size_t smem, cudaStream_t s) {
+  static bool set = false;
+  if (!set) {
+    B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024 - 1024));
+    B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    set = true;
+  }
+  k_mega<CHH, CHI><<<grid, MEGA_THREADS, smem, s>>>(p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int mega_launch(const MegaP& p, int sm_count, cudaStream_t s) {
+  const size_t smem = (size_t)p.n_stages * MEGA_STAGE + mega_attn_scratch(p.d);
+  int chh = mega_chx(p.ph[PH_QKV]);
+  chh = max(chh, mega_chx(p.ph[PH_ORES]));
+  chh = max(chh, mega_chx(p.ph[PH_GATEUP]));
+  chh = max(chh, mega_chx(p.ph[PH_HEAD]));
+  const int chi = mega_chx(p.ph[PH_DRES]);
+  // every CTA must be resident at once (software grid barrier): one CTA per SM
+  const int grid = sm_count;
+  if (chh <= 2 && chi <= 2) return mega_launch_t<2, 2>(p, grid, smem, s);
+  if (chh <= 6 && chi <= 10) return mega_launch_t<6, 10>(p, grid, smem, s);
+  if (chh <= 10 && chi <= 10) return mega_launch_t<10, 10>(p, grid, smem, s);
+  set_error("mega: unsupported widths (hidden chunks %d, inter chunks %d per lane)", chh, chi);
+  return B200_ERR_INVALID;
+}
+
+}  // namespace b200

@@ -75,6 +75,15 @@ struct b200_engine {
   bool timing_valid = false;
   int attn_cluster = 8;
   int prepared_cap = -1, prepared_cluster = -1;
+  // megakernel
+  bool use_mega = true;
+  float* att_part = nullptr;
+  float* att_stats = nullptr;
+  int* att_cnt = nullptr;
+  unsigned long long* bar = nullptr;
+  bool mega_ready = false;
+  MegaP mp;
+  long long* dbg = nullptr;
 
   DecodeDims dims() const {
     DecodeDims d;
@@ -151,10 +160,46 @@ static int resolve(b200_engine* e) {
 }
 
 static void invalidate_graph(b200_engine* e) {
+  e->mega_ready = false;
   if (e->gexec) {
     cudaGraphExecDestroy(e->gexec);
     e->gexec = nullptr;
   }
+}
+
+static int mega_prepare(b200_engine* e) {
+  const auto& c = e->cfg;
+  B200_REQUIRE(c.n_layers <= MEGA_MAX_LAYERS, "mega: %d layers > %d", c.n_layers, MEGA_MAX_LAYERS);
+  if (!e->bar) {
+    B200_CUDA(cudaMalloc(&e->bar, sizeof(unsigned long long)));
+    B200_CUDA(cudaMemset(e->bar, 0, sizeof(unsigned long long)));
+    const size_t part = (size_t)64 * 8 * 4 * c.head_dim * sizeof(float);
+    B200_CUDA(cudaMalloc(&e->att_part, part));
+    B200_CUDA(cudaMalloc(&e->att_cnt, 128 * sizeof(int)));
+    B200_CUDA(cudaMemset(e->att_cnt, 0, 128 * sizeof(int)));
+    B200_CUDA(cudaMalloc(&e->att_stats, (size_t)64 * 8 * 4 * sizeof(float2)));
+  }
+  MegaP& p = e->mp;
+  memset(&p, 0, sizeof(p));
+  p.d = e->dims();
+  p.n_layers = c.n_layers;
+  for (int l = 0; l < c.n_layers; ++l) p.layers[l] = e->layers[l];
+  p.att_part = e->att_part;
+  p.att_cnt = e->att_cnt;
+  p.att_stats = e->att_stats;
+  p.final_norm = e->norm; p.head = e->head; p.embed = e->embed;
+  p.h = e->h; p.qbuf = e->qbuf; p.attn = e->attn; p.act = e->act;
+  p.logits = e->logits; p.logprobs = e->logprobs;
+  p.kv = e->kptr(0, 0);
+  p.kv_layer_stride = 2L * e->kv_batch * c.n_kv_heads * (long)e->kv_cap * c.head_dim;
+  p.kv_v_offset = (long)e->kv_batch * c.n_kv_heads * (long)e->kv_cap * c.head_dim;
+  p.partials = e->partials; p.st = e->st; p.token_log = e->token_log; p.log_cap = e->log_cap;
+  p.force = e->force; p.inv_freq = e->lm_inv_freq; p.bar = e->bar; p.advance = 1;
+  p.dbg = e->dbg;
+  int rc = mega_fill(p, e->sm_count);
+  if (rc) return rc;
+  e->mega_ready = true;
+  return B200_OK;
 }
 
 // one decode step as plain launches on stream s (also what gets captured)
@@ -162,6 +207,7 @@ static int enqueue_step(b200_engine* e, cudaStream_t s) {
   const DecodeDims d = e->dims();
   const auto& c = e->cfg;
   int rc;
+  if (e->use_mega) return mega_launch(e->mp, e->sm_count, s);
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerW& lw = e->layers[l];
     bf16* kc = e->kptr(l, 0);
@@ -179,7 +225,9 @@ static int enqueue_step(b200_engine* e, cudaStream_t s) {
   return B200_OK;
 }
 
-static int kernels_per_step(const b200_engine* e) { return e->cfg.n_layers * 5 + 2; }
+static int kernels_per_step(const b200_engine* e) {
+  return e->use_mega ? 1 : e->cfg.n_layers * 5 + 2;
+}
 
 extern "C" {
 
@@ -265,6 +313,11 @@ int b200_engine_destroy(b200_engine* e) {
   cudaFree(e->logits); cudaFree(e->logprobs); cudaFree(e->partials); cudaFree(e->token_log);
   cudaFree(e->force); cudaFree(e->lm_inv_freq); cudaFree(e->axis_sel); cudaFree(e->v_inv_freq);
   if (e->pos_hw) cudaFree(e->pos_hw);
+  if (e->att_part) cudaFree(e->att_part);
+  if (e->att_cnt) cudaFree(e->att_cnt);
+  if (e->att_stats) cudaFree(e->att_stats);
+  if (e->bar) cudaFree(e->bar);
+  if (e->dbg) cudaFree(e->dbg);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -554,6 +607,9 @@ int b200_engine_decode(b200_engine* e, int n_steps, const int* force_tokens_host
     e->prepared_cap = e->kv_cap;
     e->prepared_cluster = e->attn_cluster;
   }
+  if (e->use_mega && !e->mega_ready) {
+    if ((rc = mega_prepare(e))) return rc;
+  }
   if (e->use_graph && !e->gexec) {
     // capture one step on the engine's own stream (capture does not execute)
     cudaGraph_t graph = nullptr;
@@ -596,6 +652,33 @@ long b200_engine_launch_count(const b200_engine* e) { return e ? e->launches : 0
 int b200_engine_set_graph(b200_engine* e, int enabled) {
   B200_REQUIRE(e, "set_graph: null engine");
   e->use_graph = enabled != 0;
+  return B200_OK;
+}
+int b200_engine_set_mega(b200_engine* e, int enabled) {
+  B200_REQUIRE(e, "set_mega: null engine");
+  e->use_mega = enabled != 0;
+  invalidate_graph(e);
+  return B200_OK;
+}
+int b200_engine_device_error(b200_engine* e, int* out) {
+  B200_REQUIRE(e && out, "device_error: null argument");
+  DecState st;
+  B200_CUDA(cudaMemcpy(&st, e->st, sizeof(st), cudaMemcpyDeviceToHost));
+  *out = st.error;
+  return B200_OK;
+}
+/* debugging aid: per-barrier globaltimer stamps of CTA 0 and the last CTA for the most
+ * recent step; out_host must hold 2*1024*2 int64.  Enables stamping on first call. */
+int b200_engine_mega_timeline(b200_engine* e, long long* out_host) {
+  B200_REQUIRE(e, "mega_timeline: null engine");
+  const size_t n = (size_t)2 * 1024 * 2 * sizeof(long long);
+  if (!e->dbg) {
+    B200_CUDA(cudaMalloc(&e->dbg, n));
+    B200_CUDA(cudaMemset(e->dbg, 0, n));
+    invalidate_graph(e);
+    return B200_OK;
+  }
+  if (out_host) B200_CUDA(cudaMemcpy(out_host, e->dbg, n, cudaMemcpyDeviceToHost));
   return B200_OK;
 }
 int b200_engine_set_pdl(b200_engine* e, int enabled) {

@@ -174,6 +174,14 @@ class Engine:
     def set_graph(self, enabled: bool):
         N.check(self.lib.b200_engine_set_graph(self.h, int(enabled)), "set_graph")
 
+    def set_mega(self, enabled: bool):
+        N.check(self.lib.b200_engine_set_mega(self.h, int(enabled)), "set_mega")
+
+    def device_error(self) -> int:
+        v = C.c_int(0)
+        N.check(self.lib.b200_engine_device_error(self.h, C.byref(v)), "device_error")
+        return int(v.value)
+
     def set_pdl(self, enabled: bool):
         N.check(self.lib.b200_engine_set_pdl(self.h, int(enabled)), "set_pdl")
 

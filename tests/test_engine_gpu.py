@@ -185,6 +185,30 @@ def test_generate_path_parity(kind, n_text, hw, n_dec):
         if tok != toks[n]:
             break  # a (near-)tie: histories legitimately diverge from here
     print(f"{kind}: tokens {got} oracle {toks}")
+    assert eng.device_error() == 0
+
+
+def test_multi_kernel_decode_equals_megakernel():
+    """The per-phase kernels (decode.cu) and the persistent megakernel
+    (decode_mega.cu) share device code and tile geometry: same tokens, same logits."""
+    from mlx_vlm_b200.generate import generate_step
+    c, W, model, req = _build("wide2", 16, (56, 56))
+    ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
+    pvd = torch.from_numpy(pv).cuda()
+    eng = model.engine
+    runs = []
+    for mega in (True, False):
+        eng.set_mega(mega)
+        toks, lps = [], []
+        for tok, lp in generate_step(ids, model, pvd, None, max_tokens=6, image_grid_thw=grid):
+            toks.append(tok)
+            lps.append(lp.float().cpu())
+        assert eng.device_error() == 0
+        runs.append((toks, lps))
+    eng.set_mega(True)
+    assert runs[0][0] == runs[1][0]
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert rl2(a, b) <= 1e-3
 
 
 def test_text_only_and_cache_reuse():

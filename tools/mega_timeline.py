@@ -1,0 +1,41 @@
+"""Per-phase timeline of one decode step of the persistent megakernel (globaltimer
+stamps at every grid barrier).  Prints mean compute / barrier-wait per phase kind."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from mlx_vlm_b200 import _native as N
+from mlx_vlm_b200.models.cache import make_prompt_cache
+from mlx_vlm_b200.utils import load_synthetic, prepare_inputs
+model, proc = load_synthetic("qwen2-vl-2b", seed=0, device="cuda:0", n_text_tokens=128)
+eng = model.engine
+eng.set_graph(False)
+N.check(eng.lib.b200_engine_mega_timeline(eng.h, 0))
+img = np.random.default_rng(0).integers(0, 256, size=(336, 336, 3), dtype=np.uint8)
+inp = prepare_inputs(proc, images=[img], prompts="x", device=eng.device, stream=eng.stream)
+ids, pvd, grid = inp["input_ids"], inp["pixel_values"], inp["image_grid_thw"]
+T = ids.shape[1]
+cache = make_prompt_cache(model.language_model)
+emb = model.get_input_embeddings(ids, pvd, image_grid_thw=grid)
+model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache, position_ids=emb.position_ids,
+                     rope_deltas=emb.rope_deltas, logits_to_keep=1, reserve_tokens=T + 600)
+model.language_model.fused_greedy_decode(200, cache, reserve_tokens=T + 600)
+eng.stream.synchronize()
+buf = np.zeros((2, 1024, 2), dtype=np.int64)
+N.check(eng.lib.b200_engine_mega_timeline(eng.h, buf.ctypes.data))
+L = 28
+names = ["qkv", "attn", "ores", "gateup", "dres"]
+for cta in (0, 1):
+    a = buf[cta]
+    nb = 5 * L + 2
+    arrive, release = a[:nb, 0], a[:nb, 1]
+    t0 = release[0]
+    comp = np.empty(nb); comp[0] = np.nan
+    comp[1:] = arrive[1:] - release[:-1]
+    wait = release - arrive
+    print(f"--- CTA {'0' if cta == 0 else 'last'}: step span {(release[nb-1]-arrive[0])/1e3:.1f} us (first arrive -> last release)")
+    for k, nm in enumerate(names):
+        idx = np.arange(L) * 5 + k
+        c = comp[idx[1:] if k == 0 else idx]
+        print(f"  {nm:7s} compute {np.nanmean(c)/1e3:7.2f} us  barrier wait {wait[idx].mean()/1e3:7.2f} us")
+    print(f"  head    compute {comp[5*L]/1e3:7.2f} us  wait {wait[5*L]/1e3:7.2f} us; sample compute {comp[5*L+1]/1e3:7.2f} wait {wait[5*L+1]/1e3:7.2f}")
+    print("  layer 5 raw (compute, wait) us:", [(round(comp[25+k]/1e3,2), round(wait[25+k]/1e3,2)) for k in range(5)])
