@@ -1,0 +1,229 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN FUNCTION SOURCE.
+
+`mlx` (the array library the reference runs on) is not installable offline, and
+importing the `mlx_vlm` package pulls in Metal-kernel modules.  The functions on
+the hot path that are pure array bookkeeping, however, only use a dozen array ops
+that have exact numpy equivalents.  This script therefore
+
+  1. parses the reference files under /root/reference with `ast`,
+  2. extracts the UNMODIFIED source of the functions / methods listed in TARGETS,
+  3. executes them against a minimal numpy-backed stand-in for `mlx.core`
+     (`mx.arange = np.arange`, ... — no arithmetic is re-implemented),
+  4. runs them on seeded inputs and writes inputs + outputs to
+     tests/golden/reference_golden.json.
+
+Run it in the build container only (it reads /root/reference; the GPU box does
+not have it):   python tests/golden/make_golden.py
+The CPU test-suite (tests/test_oracle_golden.py) checks the oracle AND the product's
+host code against the committed JSON.
+"""
+import ast
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference/mlx_vlm"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_golden.json")
+
+
+# ---------------------------------------------------------------- mx stand-in
+def make_mx():
+    mx = types.ModuleType("mx_numpy_standin")
+    for name in ("arange", "broadcast_to", "ones", "ones_like", "zeros", "zeros_like", "stack",
+                 "concatenate", "expand_dims", "where", "cumsum", "sum", "repeat", "tile",
+                 "transpose", "max", "outer", "cos", "sin", "take", "maximum", "minimum", "pad"):
+        setattr(mx, name, getattr(np, name))
+    mx.array = lambda x, dtype=None: np.array(x, dtype=dtype)
+    mx.int32, mx.int64, mx.float32, mx.bool_ = np.int32, np.int64, np.float32, np.bool_
+    mx.eval = lambda *a, **k: None
+    mx.contiguous = np.ascontiguousarray
+
+    def compile_(fn=None, **kw):
+        return fn if fn is not None else (lambda f: f)
+    mx.compile = compile_
+    return mx
+
+
+def extract(path, name, cls=None):
+    """Return the source text of function `name` (optionally a method of `cls`)."""
+    src = open(os.path.join(REF, path)).read()
+    tree = ast.parse(src)
+    body = tree.body
+    if cls is not None:
+        body = next(n for n in body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    node = next(n for n in body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name == name)
+    seg = ast.get_source_segment(src, node)
+    # strip decorators (mx.compile etc. are identity here); dedent methods
+    lines = src.splitlines()[node.lineno - 1:node.end_lineno]
+    import textwrap
+    return textwrap.dedent("\n".join(lines)), f"{path}:{node.lineno}-{node.end_lineno}"
+
+
+def load(ns, path, name, cls=None):
+    code, where = extract(path, name, cls)
+    exec(compile(code, f"<reference {where}>", "exec"), ns)
+    return ns[name], where
+
+
+def tolist(x):
+    return np.asarray(x).tolist()
+
+
+def main():
+    mx = make_mx()
+    from typing import Optional, Sequence
+    ns = {"mx": mx, "np": np, "Optional": Optional, "Sequence": Sequence}
+    provenance = {}
+    golden = {"_about": "outputs of the reference's own function source executed over a "
+                        "numpy stand-in for mlx.core (tests/golden/make_golden.py)",
+              "provenance": provenance}
+
+    # ---------------- get_rope_index (language.py:216-402)
+    get_rope_index, w = load(ns, "models/qwen2_vl/language.py", "get_rope_index", "LanguageModel")
+    provenance["get_rope_index"] = w
+    stub = types.SimpleNamespace(config=types.SimpleNamespace(
+        vision_config=types.SimpleNamespace(spatial_merge_size=2),
+        image_token_id=100, video_token_id=101, vision_start_token_id=99))
+    rng = np.random.default_rng(0)
+    cases = []
+
+    def run_rope(ids, igrid=None, vgrid=None, mask=None, tag=""):
+        a = mx.array(ids)
+        pos, delta = get_rope_index(stub, a,
+                                    None if igrid is None else mx.array(igrid),
+                                    None if vgrid is None else mx.array(vgrid),
+                                    None if mask is None else mx.array(mask))
+        cases.append({"tag": tag, "input_ids": tolist(ids), "image_grid_thw": igrid,
+                      "video_grid_thw": vgrid, "attention_mask": mask,
+                      "position_ids": tolist(pos), "rope_deltas": tolist(delta)})
+
+    two = [1, 2, 99, 100, 100, 100, 100, 5, 99, 100, 100, 100, 100, 7]
+    run_rope([two], [[1, 4, 4], [1, 4, 4]], tag="reference test: two images")
+    run_rope([[0, 0] + two], [[1, 4, 4], [1, 4, 4]], mask=[[0, 0] + [1] * len(two)],
+             tag="reference test: left padding")
+    run_rope([[0, 0, 0, 0], [10, 99, 100, 11]], [[1, 2, 2]], mask=[[0, 0, 0, 0], [1, 1, 1, 1]],
+             tag="reference test: fully masked row")
+    # one 336x336 image (grid 24x24 -> 144 tokens) inside a 32-token text prompt
+    ids = rng.integers(0, 90, size=8).tolist() + [99] + [100] * 144 + [98] + rng.integers(0, 90, size=22).tolist()
+    run_rope([ids], [[1, 24, 24]], tag="C1 layout: 336x336 image")
+    # video block (t=2) then an image, batch of 2 with different lengths (left padded)
+    r0 = [3, 99] + [101] * (2 * 2 * 3) + [4, 5, 99] + [100] * 4 + [6]
+    r1 = [7, 8, 9, 99] + [100] * 6 + [10]
+    L = max(len(r0), len(r1))
+    pad = lambda r: [0] * (L - len(r)) + r
+    m = lambda r: [0] * (L - len(r)) + [1] * len(r)
+    run_rope([pad(r0), pad(r1)], [[1, 4, 4], [1, 4, 6]], [[2, 4, 6]], mask=[m(r0), m(r1)],
+             tag="video + images, batch 2, left padded")
+    run_rope([rng.integers(0, 90, size=11).tolist()], tag="text only, no mask")
+    run_rope([[0, 0, 0, 5, 6, 7, 8], [1, 2, 3, 4, 5, 6, 7]],
+             mask=[[0, 0, 0, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1, 1]], tag="text only, with mask")
+    golden["get_rope_index"] = {"config": {"spatial_merge_size": 2, "image_token_id": 100,
+                                           "video_token_id": 101, "vision_start_token_id": 99},
+                                "cases": cases}
+
+    # ---------------- merge_input_ids_with_image_features (qwen2_vl.py:78-148)
+    merge, w = load(ns, "models/qwen2_vl/qwen2_vl.py", "merge_input_ids_with_image_features", "Model")
+    provenance["merge_input_ids_with_image_features"] = w
+    mcases = []
+
+    def run_merge(ids, n_feats, tag, image_id=100, video_id=101):
+        ids = np.asarray(ids)
+        B, T = ids.shape
+        H = 4
+        feats = (1000 + np.arange(n_feats * H, dtype=np.float32)).reshape(n_feats, H)
+        emb = -(np.arange(B * T * H, dtype=np.float32) + 1).reshape(B, T, H)
+        try:
+            out = merge(image_id, video_id, mx.array(feats), mx.array(emb), mx.array(ids))
+            out = tolist(out)
+            err = None
+        except ValueError as e:
+            out, err = None, str(e)
+        mcases.append({"tag": tag, "input_ids": ids.tolist(), "n_feats": n_feats, "hidden": H,
+                       "output": out, "error": err})
+
+    run_merge([[5, 100, 100, 100, 6, 7]], 3, "one image")
+    run_merge([[5, 100, 100, 6, 100, 100, 100, 7], [100, 1, 2, 3, 100, 100, 4, 8]], 8, "two rows, interleaved")
+    run_merge([[5, 101, 101, 6]], 2, "video fallback (no image token)")
+    run_merge([[5, 6, 7]], 2, "no vision tokens at all")
+    run_merge([[5, 100, 100, 100, 6]], 2, "too few features -> ValueError")
+    run_merge([[5, 100, 100, 6]], 5, "more features than positions (extra ignored)")
+    golden["merge_input_ids_with_image_features"] = mcases
+
+    # ---------------- vision rot_pos_emb ids + freqs (vision.py:53-65, 219-255)
+    ns["nn"] = types.SimpleNamespace(Module=object)
+    load(ns, "models/qwen2_vl/vision.py", "VisionRotaryEmbedding")
+    rot_pos_emb, w2 = load(ns, "models/qwen2_vl/vision.py", "rot_pos_emb", "VisionModel")
+    provenance["rot_pos_emb"] = w2
+    vstub = types.SimpleNamespace(spatial_merge_size=2, rotary_pos_emb=ns["VisionRotaryEmbedding"](40))
+    vcases = []
+    for grid in ([[1, 4, 6]], [[1, 24, 24]], [[2, 4, 4], [1, 6, 2]]):
+        fr = rot_pos_emb(vstub, mx.array(grid))
+        vcases.append({"grid_thw": grid, "freqs_shape": list(fr.shape),
+                       "freqs_sum": float(np.asarray(fr, dtype=np.float64).sum()),
+                       "freqs_head": tolist(np.asarray(fr)[:6, :]),
+                       "freqs_tail": tolist(np.asarray(fr)[-3:, :])})
+    golden["rot_pos_emb"] = vcases
+
+    # ---------------- apply_rotary_pos_emb_vision / rotate_half (vision.py:28-50), fp32
+    load(ns, "models/qwen2_vl/vision.py", "rotate_half")
+    arv, w = load(ns, "models/qwen2_vl/vision.py", "apply_rotary_pos_emb_vision")
+    provenance["apply_rotary_pos_emb_vision"] = w
+    x = rng.standard_normal((1, 5, 2, 8)).astype(np.float32)
+    fr = rng.standard_normal((5, 4)).astype(np.float32)
+    golden["apply_rotary_pos_emb_vision"] = {"x": tolist(x), "freqs": tolist(fr),
+                                             "out": tolist(arv(mx.array(x), mx.array(fr)))}
+
+    # ---------------- M-RoPE pieces (rope_utils.py:519-526, 1289-1334), fp32
+    sel, w = load(ns, "models/rope_utils.py", "_chunked_position_selector")
+    provenance["_chunked_position_selector"] = w
+    golden["chunked_position_selector"] = {"mrope_section": [16, 24, 24], "freq_dim": 64,
+                                           "selector": tolist(sel([16, 24, 24], 64)),
+                                           "small": tolist(sel([2, 3, 3], 8))}
+    load(ns, "models/rope_utils.py", "rotate_half")
+    are, w = load(ns, "models/rope_utils.py", "_apply_rotary_embedding")
+    provenance["_apply_rotary_embedding"] = w
+    q = rng.standard_normal((1, 2, 3, 8)).astype(np.float32)
+    k = rng.standard_normal((1, 1, 3, 8)).astype(np.float32)
+    ang = rng.standard_normal((1, 1, 3, 8)).astype(np.float32)
+    qe, ke = are(mx.array(q), mx.array(k), np.cos(ang), np.sin(ang), ns["rotate_half"])
+    golden["apply_rotary_embedding"] = {"q": tolist(q), "k": tolist(k), "angles": tolist(ang),
+                                        "q_out": tolist(qe), "k_out": tolist(ke)}
+
+    # ---------------- KVCache bookkeeping (cache.py:337-439) + create_causal_mask (:24-42)
+    ccm, w = load(ns, "models/cache.py", "create_causal_mask")
+    provenance["create_causal_mask"] = w
+    golden["create_causal_mask"] = [{"N": n, "offset": o, "mask": tolist(ccm(n, o).astype(np.int32))}
+                                    for n, o in ((1, 0), (4, 0), (3, 5))]
+    ns["_BaseCache"] = object
+    ns["BatchKVCache"] = None
+    ns["QuantizedKVCache"] = None
+    ns["create_attention_mask"] = lambda *a, **k: None
+    ns["tree_reduce"] = None
+    code, w = extract("models/cache.py", "KVCache")
+    exec(compile(code, "<ref KVCache>", "exec"), ns)
+    provenance["KVCache"] = w
+    c = ns["KVCache"]()
+    trace = []
+    for L in (5, 1, 1, 300, 1):
+        kk = rng.standard_normal((1, 2, L, 4)).astype(np.float32)
+        ks, vs = c.update_and_fetch(mx.array(kk), mx.array(kk + 1))
+        trace.append({"L": L, "offset": int(c.offset), "capacity": int(c.keys.shape[2]),
+                      "returned_len": int(ks.shape[2]),
+                      "last_key_sum": float(np.asarray(ks)[..., -1, :].sum())})
+    n = c.trim(7)
+    trace.append({"trim": 7, "trimmed": int(n), "offset": int(c.offset),
+                  "state_len": int(c.state[0].shape[2])})
+    golden["KVCache_trace"] = trace
+
+    with open(OUT, "w") as f:
+        json.dump(golden, f)
+    print(f"wrote {OUT} ({os.path.getsize(OUT)} bytes); functions: {sorted(provenance)}")
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit("reference tree not present: golden vectors can only be regenerated in the build container")
+    main()
