@@ -350,11 +350,15 @@ def main():
                     "prompt_tps_api": statistics.mean(e2e_prompt_tps),
                     "h2d_bytes_per_step": int(576 * 1176 * 4 + T * 4 + 3 * T * 4),
                     "d2h_bytes_per_step": int(N_OUT * 4)},
-            "roofline": {"kernel": "decode-step CUDA graph (28 x {k_qkv,k_attn,k_res,k_gateup,"
-                                   "k_res} + k_head + k_sample), one launch = one token",
+            "roofline": {"kernel": "k_mega (persistent decode-step kernel: 28 x {qkv, attention, "
+                                   "o_proj, gate/up, down} + head + sampler), one launch = one "
+                                   "token",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_step, "traffic": None},
+                         "algorithmic_bytes_per_launch": bytes_per_step,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_mega launch,
+                         # ncu --set full, profiles/r1_k_mega_ncu_full.txt (ctx ~275)
+                         "traffic": 3_095_564_000 + 4_551_936},
         }
         if not args.no_cpu_baseline and world == 1:
             W = _engine_weights_to_oracle(model, __import__("oracle.qwen2vl", fromlist=["x"]).qwen2_vl_2b())

@@ -1,0 +1,22 @@
+#!/bin/bash
+mkdir -p gpurun_out
+rm -f gpurun_out/summary.txt
+timeout -s KILL 1500 python -m pytest tests -q -m gpu -s > gpurun_out/t_gpu_all.log 2>&1
+echo "pytest gpu exit $?" >> gpurun_out/summary.txt
+timeout -s KILL 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/summary.txt
+timeout -s KILL 900 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err
+echo "bench exit $?" >> gpurun_out/summary.txt
+timeout -s KILL 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r1_reference.json 2>> gpurun_out/bench_r1.err
+echo "bench ref exit $?" >> gpurun_out/summary.txt
+timeout -s KILL 300 python tools/mega_timeline.py > gpurun_out/mega_timeline_r1.txt 2>&1
+timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:b200" -c 2000 --csv --log-file gpurun_out/launches_request_r1.csv python tools/profile_decode.py 3 > gpurun_out/prof.log 2>&1
+echo "ncu list exit $?" >> gpurun_out/summary.txt
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:k_mega" -s 2 -c 1 -o gpurun_out/prof_mega_r1 -f python tools/profile_decode.py 3 > gpurun_out/prof2.log 2>&1
+echo "ncu full exit $?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt
+grep -E "passed|failed" gpurun_out/t_gpu_all.log | tail -3
+tail -2 gpurun_out/smoke.log
+cat gpurun_out/bench_r1.json | cut -c1-1500
+cat gpurun_out/bench_r1_reference.json | cut -c1-600
+tail -5 gpurun_out/bench_r1.err
