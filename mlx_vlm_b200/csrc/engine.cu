@@ -671,7 +671,7 @@ int b200_engine_device_error(b200_engine* e, int* out) {
  * recent step; out_host must hold 2*1024*2 int64.  Enables stamping on first call. */
 int b200_engine_mega_timeline(b200_engine* e, long long* out_host) {
   B200_REQUIRE(e, "mega_timeline: null engine");
-  const size_t n = (size_t)2 * 1024 * 2 * sizeof(long long);
+  const size_t n = (size_t)(2 * 1024 * 2 + 256) * sizeof(long long);
   if (!e->dbg) {
     B200_CUDA(cudaMalloc(&e->dbg, n));
     B200_CUDA(cudaMemset(e->dbg, 0, n));

@@ -20,8 +20,9 @@ model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache, position
                      rope_deltas=emb.rope_deltas, logits_to_keep=1, reserve_tokens=T + 600)
 model.language_model.fused_greedy_decode(200, cache, reserve_tokens=T + 600)
 eng.stream.synchronize()
-buf = np.zeros((2, 1024, 2), dtype=np.int64)
-N.check(eng.lib.b200_engine_mega_timeline(eng.h, buf.ctypes.data))
+raw = np.zeros(2 * 1024 * 2 + 256, dtype=np.int64)
+buf = raw[:4096].reshape(2, 1024, 2)
+N.check(eng.lib.b200_engine_mega_timeline(eng.h, raw.ctypes.data))
 L = 28
 names = ["qkv", "attn", "ores", "gateup", "dres"]
 for cta in (0, 1):
@@ -39,3 +40,19 @@ for cta in (0, 1):
         print(f"  {nm:7s} compute {np.nanmean(c)/1e3:7.2f} us  barrier wait {wait[idx].mean()/1e3:7.2f} us")
     print(f"  head    compute {comp[5*L]/1e3:7.2f} us  wait {wait[5*L]/1e3:7.2f} us; sample compute {comp[5*L+1]/1e3:7.2f} wait {wait[5*L+1]/1e3:7.2f}")
     print("  layer 5 raw (compute, wait) us:", [(round(comp[25+k]/1e3,2), round(wait[25+k]/1e3,2)) for k in range(5)])
+
+for name, off in (("gateup CTA0", 4096), ("gateup CTA77", 4096 + 32), ("dres CTA0", 4096 + 64)):
+    t = raw[off:off + 30]
+    t = t[t > 0]
+    if len(t) > 2:
+        d = np.diff(t) / 1e3
+        print(f"{name}: prologue {d[0]:.2f} us; then (wait, compute) per tile:", [(round(d[i],2), round(d[i+1],2)) for i in range(1, len(d)-1, 2)])
+
+t = raw[4096 + 96:4096 + 126]; t = t[t > 0]
+c = raw[4096:4096 + 30]; c = c[c > 0]
+b = buf[0]
+print("layer-5 CTA0 absolute us (relative to QKV-barrier release of layer 5):")
+t0 = b[25, 1]
+print("  barrier releases qkv/attn/ores/gateup/dres:", [round((b[25 + k, 1] - t0) / 1e3, 2) for k in range(5)])
+print("  producer issue times of gate/up tiles:", [round((x - t0) / 1e3, 2) for x in t])
+print("  consumer gate/up stamps (start, prologue end, then wait-done/compute-done):", [round((x - t0) / 1e3, 2) for x in c])
