@@ -189,8 +189,9 @@ struct PhaseIO {
 
 template <int MODE, int CHX>
 __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g, const PhaseIO& io,
-                                              uint8_t* ring, MegaShared* sh, Ring& rg, int ctx,
-                                              int pos, long long* tdbg = nullptr) {
+                                              uint8_t* ring, uint8_t* xs_raw, MegaShared* sh,
+                                              Ring& rg, int ctx, int pos,
+                                              long long* tdbg = nullptr) {
   using T = PhTraits<MODE>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tn = 0;
@@ -199,52 +200,52 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
   const int nvec = g.K >> 3;
   const int cb = (int)((long)nvec * sub / g.S), ce = (int)((long)nvec * (sub + 1) / g.S);
   const int rows_unit = g.K * 2;
-  // activation slice -> registers (packed bf16)
+  // ---- prologue: the 256 consumer threads load / RMS-normalise the activation vector ONCE
+  // per CTA into shared memory (one global round trip, two block barriers); each warp then
+  // takes its register slice from there.  (Per-warp redundant normalisation cost 2.4 us of
+  // every NORM phase in the round-1 timeline; this costs 0.8-1.0 us.)
+  uint4* xs = reinterpret_cast<uint4*>(xs_raw);
+  {
+    float ss = 0.f;
+    for (int c = threadIdx.x; c < nvec; c += 256) {
+      const uint4 v = ldcg16(io.x + (long)c * 8);
+      xs[c] = v;
+      if (T::NORM) {
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+      }
+    }
+    if (T::NORM) {
+      ss = warp_sum(ss);
+      if (lane == 0) sh->s_l[warp][0] = ss;
+      cbar();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += sh->s_l[w][0];
+      const float rs = 1.0f / sqrtf(tot / (float)g.K + p.d.eps);
+      for (int c = threadIdx.x; c < nvec; c += 256) {
+        float f[8], lf[8];
+        unpack8(xs[c], f);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(io.lnw + (long)c * 8)), lf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = rbf(rbf(f[j] * rs) * lf[j]);
+        uint4 o;
+        o.x = pack2(f[0], f[1]);
+        o.y = pack2(f[2], f[3]);
+        o.z = pack2(f[4], f[5]);
+        o.w = pack2(f[6], f[7]);
+        xs[c] = o;
+      }
+    }
+    cbar();
+  }
   uint4 xv[CHX];
 #pragma unroll
   for (int u = 0; u < CHX; ++u) {
     const int c = cb + lane + 32 * u;
-    xv[u] = (c < ce) ? ldcg16(io.x + (long)c * 8) : make_uint4(0, 0, 0, 0);
-  }
-  if (T::NORM) {
-    uint4 lw4[CHX];
-#pragma unroll
-    for (int u = 0; u < CHX; ++u) {
-      const int c = cb + lane + 32 * u;
-      lw4[u] = (c < ce) ? __ldg(reinterpret_cast<const uint4*>(io.lnw + (long)c * 8))
-                        : make_uint4(0, 0, 0, 0);
-    }
-    float ss = 0.f;
-    if (g.S == 1) {
-#pragma unroll
-      for (int u = 0; u < CHX; ++u) {
-        float f[8];
-        unpack8(xv[u], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
-      }
-    } else {
-      for (int c = lane; c < nvec; c += 32) {
-        float f[8];
-        unpack8(ldcg16(io.x + (long)c * 8), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
-      }
-    }
-    ss = warp_sum(ss);
-    const float rs = 1.0f / sqrtf(ss / (float)g.K + p.d.eps);
-#pragma unroll
-    for (int u = 0; u < CHX; ++u) {
-      float f[8], lf[8];
-      unpack8(xv[u], f);
-      unpack8(lw4[u], lf);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = rbf(rbf(f[j] * rs) * lf[j]);
-      xv[u].x = pack2(f[0], f[1]);
-      xv[u].y = pack2(f[2], f[3]);
-      xv[u].z = pack2(f[4], f[5]);
-      xv[u].w = pack2(f[6], f[7]);
-    }
+    xv[u] = (c < ce) ? xs[c] : make_uint4(0, 0, 0, 0);
   }
   if (tdbg && threadIdx.x == 0) tdbg[tn++] = gtimer();
   float run_m = -INFINITY, run_l = 0.f;
@@ -714,7 +715,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ MegaShared sh;
   uint8_t* ring = sm;
-  float* scratch = reinterpret_cast<float*>(sm + (long)p.n_stages * MEGA_STAGE);
+  uint8_t* xs = sm + (long)p.n_stages * MEGA_STAGE;  // activation vector (GEMV phases) /
+  float* scratch = reinterpret_cast<float*>(xs);     // attention scratch (attention phase)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.st->error) return;  // a previous step gave up: do not spin again
   if (threadIdx.x == 0) {
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     (void)plane;
     {
       PhaseIO io = {p.h, lw.ln1, lw.bqkv, p.qbuf, kc, vc, nullptr};
-      consume_phase<PH_QKV, CHH>(p, p.ph[PH_QKV], io, ring, &sh, rg, ctx, pos);
+      consume_phase<PH_QKV, CHH>(p, p.ph[PH_QKV], io, ring, xs, &sh, rg, ctx, pos);
     }
     grid_barrier(p, &sh, bidx);
     if ((int)blockIdx.x < p.attn_ctas) {
@@ -781,27 +783,27 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     grid_barrier(p, &sh, bidx);
     {
       PhaseIO io = {p.attn, nullptr, nullptr, p.h, nullptr, nullptr, nullptr};
-      if (p.ph[PH_ORES].S == 1) consume_phase<PH_ORES, CHH>(p, p.ph[PH_ORES], io, ring, &sh, rg, 0, 0);
-      else consume_phase<PH_DRES, CHH>(p, p.ph[PH_ORES], io, ring, &sh, rg, 0, 0);
+      if (p.ph[PH_ORES].S == 1) consume_phase<PH_ORES, CHH>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
+      else consume_phase<PH_DRES, CHH>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
     }
     grid_barrier(p, &sh, bidx);
     {
       PhaseIO io = {p.h, lw.ln2, nullptr, p.act, nullptr, nullptr, nullptr};
       long long* td = (p.dbg && l == 5 && (blockIdx.x == 0 || blockIdx.x == 77))
                           ? p.dbg + 4096 + (blockIdx.x ? 32 : 0) : nullptr;
-      consume_phase<PH_GATEUP, CHH>(p, p.ph[PH_GATEUP], io, ring, &sh, rg, 0, 0, td);
+      consume_phase<PH_GATEUP, CHH>(p, p.ph[PH_GATEUP], io, ring, xs, &sh, rg, 0, 0, td);
     }
     grid_barrier(p, &sh, bidx);
     {
       PhaseIO io = {p.act, nullptr, nullptr, p.h, nullptr, nullptr, nullptr};
       long long* td = (p.dbg && l == 5 && blockIdx.x == 0) ? p.dbg + 4096 + 64 : nullptr;
-      consume_phase<PH_DRES, CHI>(p, p.ph[PH_DRES], io, ring, &sh, rg, 0, 0, td);
+      consume_phase<PH_DRES, CHI>(p, p.ph[PH_DRES], io, ring, xs, &sh, rg, 0, 0, td);
     }
     grid_barrier(p, &sh, bidx);
   }
   {
     PhaseIO io = {p.h, p.final_norm, nullptr, p.logits, nullptr, nullptr, p.partials};
-    consume_phase<PH_HEAD, CHH>(p, p.ph[PH_HEAD], io, ring, &sh, rg, 0, 0);
+    consume_phase<PH_HEAD, CHH>(p, p.ph[PH_HEAD], io, ring, xs, &sh, rg, 0, 0);
   }
   grid_barrier(p, &sh, bidx);
   // ---- sampler: logprobs = bf16(logits - bf16(lse)), argmax with lowest index ----
@@ -895,8 +897,11 @@ static int mega_geometry(MegaPhase& g, int K, int N, bool pair, int units) {
   return B200_OK;
 }
 
+// region after the ring: attention scratch, or the activation vector of a GEMV phase
 static size_t mega_attn_scratch(const DecodeDims& d) {
-  return ((size_t)MEGA_ATT_G * cdiv(d.cap, ATT_UN) + (size_t)8 * MEGA_ATT_G * d.hd) * 4;
+  const size_t att = ((size_t)MEGA_ATT_G * cdiv(d.cap, ATT_UN) + (size_t)8 * MEGA_ATT_G * d.hd) * 4;
+  const size_t xs = (size_t)max(max(d.inter, d.hidden), d.n_heads * d.hd) * 2;
+  return ((att > xs ? att : xs) + 127) & ~(size_t)127;
 }
 
 int mega_fill(MegaP& p, int sm_count) {
@@ -923,7 +928,7 @@ int mega_fill(MegaP& p, int sm_count) {
   B200_REQUIRE(p.attn_ctas <= sm_count, "mega: %d attention CTAs > %d SMs", p.attn_ctas, sm_count);
   B200_REQUIRE(d.hd == 64 || d.hd == 128, "mega: head_dim %d (64|128)", d.hd);
   const size_t scratch = mega_attn_scratch(d);
-  const long budget = 227 * 1024 - 1024 - (long)scratch;
+  const long budget = 227 * 1024 - 2048 - (long)scratch;
   int ns = (int)(budget / MEGA_STAGE);
   B200_REQUIRE(ns >= 2, "mega: cache capacity %d leaves no room for the weight ring", d.cap);
   p.n_stages = ns > 8 ? 8 : ns;
@@ -938,7 +943,7 @@ static int mega_launch_t(const MegaP& p, int grid, size_t smem, cudaStream_t s) 
   static bool set = false;
   if (!set) {
     B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024 - 1024));
+                                   227 * 1024 - 2048));
     B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
     set = true;

@@ -203,7 +203,8 @@ def test_multi_kernel_decode_equals_megakernel():
         for tok, lp in generate_step(ids, model, pvd, None, max_tokens=6, image_grid_thw=grid):
             toks.append(tok)
             lps.append(lp.float().cpu())
-        assert eng.device_error() == 0
+        err = eng.device_error()
+        assert err == 0, f"device error flag {err} (mega={mega})"
         runs.append((toks, lps))
     eng.set_mega(True)
     assert runs[0][0] == runs[1][0]
