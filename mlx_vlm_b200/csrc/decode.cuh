@@ -29,6 +29,7 @@ struct DecState {
   int use_force;  // teacher forcing (tests)
   int error;      // set by a bounded wait that gave up (1: grid barrier, 2: mbarrier)
   unsigned long long bar_base;  // k_mega: value of the grid-barrier counter at step start
+  unsigned long long att_base;  // k_mega: attention phases executed before this step
 };
 
 // ---- k_mega (decode_mega.cu): the whole step as one persistent kernel ----------
@@ -60,7 +61,7 @@ struct MegaP {
   int advance;
   int l2_prefetch;
   float* att_part;  // [groups][8 units][4*hd] fp32 partial attention outputs
-  int* att_cnt;     // [groups][2] arrival counters (zero between phases)
+  unsigned long long* att_cnt;  // [groups] monotonic arrival counters
   float* att_stats; // [groups][8 units][4] (max, sum exp) pairs
   long long* dbg;  // optional [2][1024][2] globaltimer stamps (arrive, release) per barrier
 };

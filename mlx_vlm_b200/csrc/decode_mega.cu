@@ -101,6 +101,7 @@ struct PhTraits {
 constexpr int MEGA_THREADS = 288;
 constexpr int MEGA_STAGE = 48 * 1024;
 constexpr int MEGA_ATT_G = 4;
+constexpr int ATT_UN = 8;  // key ranges per (kv head, q-head group) in the attention phase
 
 struct MegaShared {
   uint64_t full_bar[8], empty_bar[8];
@@ -108,6 +109,7 @@ struct MegaShared {
   float2 wstat[8];
   float s_m[8][MEGA_ATT_G], s_l[8][MEGA_ATT_G];
   unsigned long long bar_base;
+  unsigned long long att_base;
   float lse;
   unsigned long long best;
   int feed;
@@ -185,6 +187,7 @@ struct PhaseIO {
   bf16* out;         // h / act / logits / qbuf
   bf16 *kc, *vc;     // QKV
   float2* partials;  // HEAD
+  const float* xpart;  // ORES: partial attention outputs to be summed (instead of x)
 };
 
 template <int MODE, int CHX>
@@ -208,7 +211,32 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
   {
     float ss = 0.f;
     for (int c = threadIdx.x; c < nvec; c += 256) {
-      const uint4 v = ldcg16(io.x + (long)c * 8);
+      uint4 v;
+      if (MODE == PH_ORES && io.xpart) {
+        // x = bf16( sum over the ATT_UN key ranges of the partial attention outputs )
+        const DecodeDims& d = p.d;
+        const int d0 = c * 8, h = d0 / d.hd, Gall = d.n_heads / d.n_kv, G = Gall / p.hsplit;
+        const int grp = (h / Gall) * p.hsplit + (h % Gall) / G, gi = (h % Gall) % G;
+        const float* src = io.xpart + (long)grp * ATT_UN * MEGA_ATT_G * d.hd + (long)gi * d.hd + (d0 % d.hd);
+        float4 a[ATT_UN], b[ATT_UN];
+#pragma unroll
+        for (int u = 0; u < ATT_UN; ++u) {
+          a[u] = __ldcg(reinterpret_cast<const float4*>(src + (long)u * MEGA_ATT_G * d.hd));
+          b[u] = __ldcg(reinterpret_cast<const float4*>(src + (long)u * MEGA_ATT_G * d.hd + 4));
+        }
+        float4 sa = a[0], sb = b[0];
+#pragma unroll
+        for (int u = 1; u < ATT_UN; ++u) {
+          sa.x += a[u].x; sa.y += a[u].y; sa.z += a[u].z; sa.w += a[u].w;
+          sb.x += b[u].x; sb.y += b[u].y; sb.z += b[u].z; sb.w += b[u].w;
+        }
+        v.x = pack2(sa.x, sa.y);
+        v.y = pack2(sa.z, sa.w);
+        v.z = pack2(sb.x, sb.y);
+        v.w = pack2(sb.z, sb.w);
+      } else {
+        v = ldcg16(io.x + (long)c * 8);
+      }
       xs[c] = v;
       if (T::NORM) {
         float f[8];
@@ -256,16 +284,15 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
     const int r = t * g.R + rloc;
     if (t < g.tiles && r < g.N) hpre = ldcg_bf(io.out + r);
   }
-  float pb1 = 0.f, pb2 = 0.f, pc = 1.f, psn = 0.f;  // QKV, first tile: bias + rotary factors
+  float pb1 = 0.f, pb2 = 0.f, pc = 1.f;  // QKV, first tile: bias + inverse frequency
   if (MODE == PH_QKV && (int)blockIdx.x < g.tiles) {
     const int hd = p.d.hd, half = hd >> 1;
     const int per_slot = half / g.R;
     const int slot = blockIdx.x / per_slot, j = (blockIdx.x % per_slot) * g.R + rloc;
     pb1 = bf2f(io.bias[slot * hd + j]);
     pb2 = bf2f(io.bias[slot * hd + j + half]);
-    const float ang = (float)pos * p.inv_freq[j];
-    pc = rbf(cosf(ang));
-    psn = rbf(sinf(ang));
+    pc = p.inv_freq[j];  // raw inverse frequency; cos/sin are taken in the epilogue so that
+                         // this load does not stall the warp before its tile
   }
   float keep0 = 0.f, keep1 = 0.f;
   // epilogue of tiles [it0, it0+cnt): lane i owns tile it0+i (only the slice-0 warps hold sums)
@@ -287,12 +314,8 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
           dst[j] = f2bf(y1);
           dst[j + half] = f2bf(y2);
         } else {
-          float c = pc, sn = psn;
-          if (ti != 0) {
-            const float ang = (float)pos * p.inv_freq[j];
-            c = rbf(cosf(ang));
-            sn = rbf(sinf(ang));
-          }
+          const float ang = (float)pos * (ti == 0 ? pc : p.inv_freq[j]);
+          const float c = rbf(cosf(ang)), sn = rbf(sinf(ang));
           const float o1 = rbf(rbf(y1 * c) + rbf((-y2) * sn));
           const float o2 = rbf(rbf(y2 * c) + rbf(y1 * sn));
           bf16* dst = (slot < p.d.n_heads)
@@ -428,11 +451,13 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
 // Measured alternatives (tools/mega_timeline.py, ctx ~470): one CTA per (kv head,
 // group) 15.9 us; one CTA per q head 17.1 us; every unit recomputing all scores
 // 11.1 us; this 10.6 us.
-constexpr int ATT_UN = 8;
-
 template <int HD>
 __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const bf16* vc,
-                                           float* scratch, MegaShared* sh, int nkeys) {
+                                           float* scratch, MegaShared* sh, int nkeys, int layer,
+                                           long long* tdbg = nullptr) {
+  int tn = 0;
+#define ATT_STAMP() do { if (tdbg && threadIdx.x == 0 && tn < 30) tdbg[tn++] = gtimer(); } while (0)
+  ATT_STAMP();
   constexpr int EPL = HD / 32, SEG = HD / 8, AG = MEGA_ATT_G, NV = SEG / 8, UNR = 2;
   const DecodeDims& d = p.d;
   const int Gall = d.n_heads / d.n_kv;
@@ -465,6 +490,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
       for (int i = 0; i < SEG; ++i) qr[g][i] = 0.f;
     }
   }
+  ATT_STAMP();  // q loaded
   // ---- 1. scores of the own range ----
   float lm[AG];
 #pragma unroll
@@ -507,8 +533,9 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
       }
     }
   }
+  ATT_STAMP();  // scores done
   // V rows of this warp's first keys: requested now, consumed after the group barrier
-  constexpr int VPRE = 4;
+  constexpr int VPRE = 8;  // V rows requested before the group barrier (8 keys per warp)
   float vpre[VPRE][EPL];
 #pragma unroll
   for (int q = 0; q < VPRE; ++q) {
@@ -554,6 +581,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
     if (lane == 0) sh->s_l[warp][g] = ls[g];
   }
   cbar();
+  ATT_STAMP();  // local stats done
   // ---- 2. publish the local statistics, group barrier ----
   float2* gstats = reinterpret_cast<float2*>(p.att_stats) + (long)grp * ATT_UN * AG;
   if (threadIdx.x < AG) {
@@ -564,37 +592,50 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
   }
   cbar();
   if (threadIdx.x == 0) {
-    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(&p.att_cnt[grp * 2]), "r"(1)
+    const unsigned long long target = (sh->att_base + (unsigned long long)layer + 1ull) * ATT_UN;
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&p.att_cnt[grp]), "l"(1ull)
                  : "memory");
     unsigned spins = 0;
-    int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(&p.att_cnt[grp * 2])
-                   : "memory");
-      if (seen < ATT_UN && ++spins > (1u << 22)) {
+    while (ld_acquire_u64(&p.att_cnt[grp]) < target) {
+      if (++spins > (1u << 22)) {
         sh->err = 3;
         break;
       }
-    } while (seen < ATT_UN);
+    }
   }
   cbar();
-  // ---- 3. global statistics, p, partial P.V over the own range ----
+  ATT_STAMP();  // group barrier passed
+  // ---- 3. global statistics: ONE warp reads the ATT_UN x AG pairs (lane = u*AG + g) ----
+  if (warp == 0) {
+    static_assert(ATT_UN * MEGA_ATT_G == 32, "one lane per (unit, head)");
+    const float2 stv = __ldcg(&gstats[lane]);
+    // max / rescaled sum over the units of head g = lane % AG: butterfly over the unit bits
+    float m = stv.x;
+#pragma unroll
+    for (int o = AG; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = (stv.y > 0.f) ? stv.y * expf(stv.x - m) : 0.f;
+#pragma unroll
+    for (int o = AG; o < 32; o <<= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane < AG) {
+      sh->s_m[0][lane] = m;
+      sh->s_l[0][lane] = l;
+    }
+  }
+  cbar();
   float M[AG], L[AG];
 #pragma unroll
   for (int g = 0; g < AG; ++g) {
-    float2 stv[ATT_UN];
-#pragma unroll
-    for (int u = 0; u < ATT_UN; ++u) stv[u] = __ldcg(&gstats[u * AG + g]);
-    float m = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < ATT_UN; ++u) m = fmaxf(m, stv[u].x);
-    float l = 0.f;
-#pragma unroll
-    for (int u = 0; u < ATT_UN; ++u)
-      if (stv[u].y > 0.f) l += stv[u].y * expf(stv[u].x - m);
-    M[g] = m;
-    L[g] = l;
+    M[g] = sh->s_m[0][g];
+    L[g] = sh->s_l[0][g];
   }
+  // p = bf16(exp(s - M) / L) for the own keys, one key per thread, in place
+  for (int j = threadIdx.x; j < u1 - u0; j += 256) {
+#pragma unroll
+    for (int g = 0; g < AG; ++g)
+      sc[(long)g * ucap + j] = rbf(expf(sc[(long)g * ucap + j] - M[g]) / L[g]);
+  }
+  cbar();
+  ATT_STAMP();  // global stats read
   float acc[AG][EPL];
 #pragma unroll
   for (int g = 0; g < AG; ++g)
@@ -606,7 +647,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
     if (j < u1) {
 #pragma unroll
       for (int g = 0; g < AG; ++g) {
-        const float pj = rbf(expf(sc[(long)g * ucap + (j - u0)] - M[g]) / L[g]);
+        const float pj = sc[(long)g * ucap + (j - u0)];
 #pragma unroll
         for (int e = 0; e < EPL; ++e) acc[g][e] = fmaf(pj, vpre[q][e], acc[g][e]);
       }
@@ -639,7 +680,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
       if (j < u1) {
 #pragma unroll
         for (int g = 0; g < AG; ++g) {
-          const float pj = rbf(expf(sc[(long)g * ucap + (j - u0)] - M[g]) / L[g]);
+          const float pj = sc[(long)g * ucap + (j - u0)];
 #pragma unroll
           for (int e = 0; e < EPL; ++e) acc[g][e] = fmaf(pj, vf[q][e], acc[g][e]);
         }
@@ -650,6 +691,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
   for (int g = 0; g < AG; ++g)
 #pragma unroll
     for (int e = 0; e < EPL; ++e) red[((long)warp * AG + g) * HD + lane * EPL + e] = acc[g][e];
+  ATT_STAMP();  // PV done
   cbar();
   float* mypart = p.att_part + ((long)grp * ATT_UN + unit) * AG * HD;
   for (int i = threadIdx.x; i < G * HD; i += 256) {
@@ -659,27 +701,9 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
     mypart[i] = s;
   }
   cbar();
-  // ---- 4. last CTA of the group combines ----
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const int old = atomicAdd(&p.att_cnt[grp * 2 + 1], 1);
-    sh->feed = (old == ATT_UN - 1);
-    __threadfence();
-  }
-  cbar();
-  if (sh->feed) {
-    const float* gp = p.att_part + (long)grp * ATT_UN * AG * HD;
-    for (int i = threadIdx.x; i < G * HD; i += 256) {
-      float s = 0.f;
-#pragma unroll
-      for (int u = 0; u < ATT_UN; ++u) s += __ldcg(gp + (long)u * AG * HD + i);
-      p.attn[(long)h0 * HD + i] = f2bf(s);
-    }
-    if (threadIdx.x == 0) {  // every CTA of the group is past both counters by now
-      p.att_cnt[grp * 2] = 0;
-      p.att_cnt[grp * 2 + 1] = 0;
-    }
-  }
+  // (the ATT_UN partial outputs are summed, in a fixed order, by the o_proj prologue)
+  ATT_STAMP();  // end
+#undef ATT_STAMP
 }
 
 __device__ __forceinline__ uint32_t orderable_u(float f) {
@@ -726,6 +750,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     }
     sh.err = 0;
     sh.bar_base = p.st->bar_base;
+    sh.att_base = p.st->att_base;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -777,12 +802,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     }
     grid_barrier(p, &sh, bidx);
     if ((int)blockIdx.x < p.attn_ctas) {
-      if (d.hd == 128) attn_phase<128>(p, kc, vc, scratch, &sh, ctx + 1);
-      else attn_phase<64>(p, kc, vc, scratch, &sh, ctx + 1);
+      if (d.hd == 128) attn_phase<128>(p, kc, vc, scratch, &sh, ctx + 1, l,
+                                       (p.dbg && l == 5 && blockIdx.x < 2) ? p.dbg + 4096 + 128 + 32 * blockIdx.x : nullptr);
+      else attn_phase<64>(p, kc, vc, scratch, &sh, ctx + 1, l);
     }
     grid_barrier(p, &sh, bidx);
     {
-      PhaseIO io = {p.attn, nullptr, nullptr, p.h, nullptr, nullptr, nullptr};
+      PhaseIO io = {p.attn, nullptr, nullptr, p.h, nullptr, nullptr, nullptr, p.att_part};
       if (p.ph[PH_ORES].S == 1) consume_phase<PH_ORES, CHH>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
       else consume_phase<PH_DRES, CHH>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
     }
@@ -869,6 +895,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
       p.st->pos += p.advance;
       p.st->best_key = 0ull;
       p.st->bar_base = sh.bar_base + (unsigned long long)bidx * gridDim.x;
+      p.st->att_base = sh.att_base + (unsigned long long)p.n_layers;
       if (sh.err) p.st->error = sh.err;
     }
     cbar();

@@ -79,7 +79,7 @@ struct b200_engine {
   bool use_mega = true;
   float* att_part = nullptr;
   float* att_stats = nullptr;
-  int* att_cnt = nullptr;
+  unsigned long long* att_cnt = nullptr;
   unsigned long long* bar = nullptr;
   bool mega_ready = false;
   MegaP mp;
@@ -175,8 +175,8 @@ static int mega_prepare(b200_engine* e) {
     B200_CUDA(cudaMemset(e->bar, 0, sizeof(unsigned long long)));
     const size_t part = (size_t)64 * 8 * 4 * c.head_dim * sizeof(float);
     B200_CUDA(cudaMalloc(&e->att_part, part));
-    B200_CUDA(cudaMalloc(&e->att_cnt, 128 * sizeof(int)));
-    B200_CUDA(cudaMemset(e->att_cnt, 0, 128 * sizeof(int)));
+    B200_CUDA(cudaMalloc(&e->att_cnt, 64 * sizeof(unsigned long long)));
+    B200_CUDA(cudaMemset(e->att_cnt, 0, 64 * sizeof(unsigned long long)));
     B200_CUDA(cudaMalloc(&e->att_stats, (size_t)64 * 8 * 4 * sizeof(float2)));
   }
   MegaP& p = e->mp;

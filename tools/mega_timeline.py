@@ -56,3 +56,9 @@ t0 = b[25, 1]
 print("  barrier releases qkv/attn/ores/gateup/dres:", [round((b[25 + k, 1] - t0) / 1e3, 2) for k in range(5)])
 print("  producer issue times of gate/up tiles:", [round((x - t0) / 1e3, 2) for x in t])
 print("  consumer gate/up stamps (start, prologue end, then wait-done/compute-done):", [round((x - t0) / 1e3, 2) for x in c])
+
+names = ["start", "q loaded", "scores", "local stats", "group barrier", "stats read", "PV", "partial written", "counter", "end"]
+for cta in (0, 1):
+    t = raw[4096 + 128 + 32 * cta:4096 + 128 + 32 * cta + 12]; t = t[t > 0]
+    if len(t) > 2:
+        print(f"attention CTA{cta} (layer 5) step durations us:", list(zip(names[1:], [round(x / 1e3, 2) for x in np.diff(t)])))
