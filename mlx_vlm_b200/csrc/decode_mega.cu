@@ -73,6 +73,14 @@ __device__ __forceinline__ uint4 ldcg16(const void* p) {
 __device__ __forceinline__ float ldcg_bf(const bf16* p) {
   return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p)) << 16);
 }
+// packed fp32 FMA (Blackwell FFMA2): (d0,d1) += (a0,a1) * (b0,b1), two IEEE fp32 FMAs per issue
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%0,%1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0,%1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -118,10 +126,17 @@ struct MegaShared {
 
 // ring position shared by producer and consumers (each keeps its own copy)
 struct Ring {
-  uint32_t seq;
+  int cur;        // ring slot of the next tile
+  uint32_t ph;    // its phase parity
   int n_stages;
-  __device__ __forceinline__ int slot() const { return (int)(seq % (uint32_t)n_stages); }
-  __device__ __forceinline__ uint32_t parity() const { return (seq / (uint32_t)n_stages) & 1u; }
+  __device__ __forceinline__ int slot() const { return cur; }
+  __device__ __forceinline__ uint32_t parity() const { return ph; }
+  __device__ __forceinline__ void advance() {  // no integer division on the per-tile path
+    if (++cur == n_stages) {
+      cur = 0;
+      ph ^= 1u;
+    }
+  }
 };
 
 template <int MODE>
@@ -158,7 +173,7 @@ __device__ __forceinline__ void produce_phase(const MegaPhase& g, const bf16* W,
     if (T::PAIR)
       bulk_g2s(dst + (long)g.R * rows_unit, mega_tile_src<MODE>(g, W, W2, hd, t, 1), bytes,
                &sh->full_bar[s], pol);
-    ++rg.seq;
+    rg.advance();
   }
 }
 
@@ -353,7 +368,7 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
     if (MODE != PH_QKV) rows = min(g.R, g.N - t * g.R);
     mb_wait(&sh->full_bar[s], rg.parity(), &sh->err);
     if (tdbg && threadIdx.x == 0 && tn < 30) tdbg[tn++] = gtimer();
-    ++rg.seq;
+    rg.advance();
     const uint8_t* base = ring + (long)s * MEGA_STAGE + (long)rloc * rows_unit;
     float acc[T::NRW];
     {
@@ -384,7 +399,8 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
             float wf[8];
             unpack8(w4[m][u], wf);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a8[m][j] = fmaf(wf[j], xf[j], a8[m][j]);
+            for (int j = 0; j < 8; j += 2)
+              ffma2(a8[m][j], a8[m][j + 1], wf[j], wf[j + 1], xf[j], xf[j + 1]);
           }
         }
       }
@@ -474,35 +490,68 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
   const int per = (nkeys + ATT_UN - 1) / ATT_UN;
   const int u0 = min(nkeys, unit * per), u1 = min(nkeys, u0 + per);
   const int seg = lane & 7, ksub = lane >> 3;
-  float qr[AG][SEG];
+  // ---- all global requests of the phase are issued before the first use: q, the first
+  // 2 x 4 keys of this warp, and the V rows of its first VPRE keys (one round trip) ----
+  constexpr int VPRE = 8;
+  uint4 qraw[AG][NV];
 #pragma unroll
-  for (int g = 0; g < AG; ++g) {
-    if (g < G) {
+  for (int g = 0; g < AG; ++g)
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        float f[8];
-        unpack8(ldcg16(p.qbuf + (long)(h0 + g) * HD + seg * SEG + v * 8), f);
+    for (int v = 0; v < NV; ++v)
+      qraw[g][v] = (g < G) ? ldcg16(p.qbuf + (long)(h0 + g) * HD + seg * SEG + v * 8)
+                           : make_uint4(0, 0, 0, 0);
+  uint4 kvn[UNR][NV];
+  {
+    const int j0 = u0 + warp * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) qr[g][v * 8 + i] = rbf(f[i] * d.scale_bf);
-      }
-    } else {
+    for (int q = 0; q < UNR; ++q) {
+      const int j = j0 + 32 * q + ksub;
 #pragma unroll
-      for (int i = 0; i < SEG; ++i) qr[g][i] = 0.f;
+      for (int v = 0; v < NV; ++v)
+        kvn[q][v] = (j < u1) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8) : make_uint4(0, 0, 0, 0);
     }
   }
+  uint2 vraw[VPRE];
+#pragma unroll
+  for (int q = 0; q < VPRE; ++q) {
+    const int j = u0 + warp + 8 * q;
+    vraw[q] = make_uint2(0, 0);
+    if (j < u1) {
+      const bf16* vr = vb + (long)j * HD + lane * EPL;
+      if (EPL == 4) vraw[q] = __ldcg(reinterpret_cast<const uint2*>(vr));
+      else vraw[q].x = __ldcg(reinterpret_cast<const uint32_t*>(vr));
+    }
+  }
+  float qr[AG][SEG];
+#pragma unroll
+  for (int g = 0; g < AG; ++g)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float f[8];
+      unpack8(qraw[g][v], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qr[g][v * 8 + i] = rbf(f[i] * d.scale_bf);
+    }
   ATT_STAMP();  // q loaded
-  // ---- 1. scores of the own range ----
+  // ---- 1. scores of the own range (software-pipelined over trips of 2 x 4 keys) ----
   float lm[AG];
 #pragma unroll
   for (int g = 0; g < AG; ++g) lm[g] = -INFINITY;
   for (int j0 = u0 + warp * 4; j0 < u1; j0 += 32 * UNR) {
     uint4 kv[UNR][NV];
 #pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      const int j = j0 + 32 * q + ksub;
+    for (int q = 0; q < UNR; ++q)
 #pragma unroll
-      for (int v = 0; v < NV; ++v)
-        kv[q][v] = (j < u1) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8) : make_uint4(0, 0, 0, 0);
+      for (int v = 0; v < NV; ++v) kv[q][v] = kvn[q][v];
+    if (j0 + 32 * UNR < u1) {
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int j = j0 + 32 * UNR + 32 * q + ksub;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          kvn[q][v] = (j < u1) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8)
+                               : make_uint4(0, 0, 0, 0);
+      }
     }
 #pragma unroll
     for (int q = 0; q < UNR; ++q) {
@@ -534,26 +583,17 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
     }
   }
   ATT_STAMP();  // scores done
-  // V rows of this warp's first keys: requested now, consumed after the group barrier
-  constexpr int VPRE = 8;  // V rows requested before the group barrier (8 keys per warp)
   float vpre[VPRE][EPL];
 #pragma unroll
   for (int q = 0; q < VPRE; ++q) {
-    const int j = u0 + warp + 8 * q;
+    if (EPL == 4) {
+      float t4[4];
+      unpack4(vraw[q], t4);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) vpre[q][e] = 0.f;
-    if (j < u1) {
-      const bf16* vr = vb + (long)j * HD + lane * EPL;
-      if (EPL == 4) {
-        float t4[4];
-        unpack4(__ldcg(reinterpret_cast<const uint2*>(vr)), t4);
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) vpre[q][e] = t4[e];
-      } else {
-        const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(vr));
-        vpre[q][0] = __uint_as_float(w << 16);
-        vpre[q][EPL - 1] = __uint_as_float(w & 0xffff0000u);
-      }
+      for (int e = 0; e < EPL; ++e) vpre[q][e] = t4[e];
+    } else {
+      vpre[q][0] = __uint_as_float(vraw[q].x << 16);
+      vpre[q][EPL - 1] = __uint_as_float(vraw[q].x & 0xffff0000u);
     }
   }
 #pragma unroll
@@ -756,7 +796,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
   }
   __syncthreads();
   Ring rg;
-  rg.seq = 0;
+  rg.cur = 0;
+  rg.ph = 0;
   rg.n_stages = p.n_stages;
   const DecodeDims& d = p.d;
 
