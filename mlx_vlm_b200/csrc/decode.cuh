@@ -68,6 +68,35 @@ struct MegaP {
 int mega_fill(MegaP& p, int sm_count);
 int mega_launch(const MegaP& p, int sm_count, cudaStream_t s);
 
+// ---- k_mega_tc (decode_mega_tc.cu): the same step with tcgen05 GEMV phases ---------
+struct LayerWT {
+  const uint8_t *wqkv, *wo, *wgu, *wd;  // tile images (128 rows x 64 cols, 128B swizzle)
+};
+struct MegaTcPhase {
+  int K, N;    // reduction length, output rows (gate/up: intermediate channels)
+  int KB, RB;  // K blocks of 64, row blocks
+  int S;       // K splits (units = RB * S; split phases have at most one unit per CTA)
+  int units;
+};
+struct MegaTcP {
+  MegaP base;
+  LayerWT lt[MEGA_MAX_LAYERS];
+  const uint8_t* head_t;
+  float *qkv_part, *o_part, *d_part;  // [S][part_stride] fp32 split-K partial sums
+  long part_stride;
+  MegaTcPhase ph[5];
+  int sps;           // K blocks per ring stage
+  int x_kstride;     // bytes between K blocks of the activation operand (1024: 8 rows, 2048: 16)
+  int x_sbo;         // stride between its 8-row groups (0: rows 8..15 alias rows 0..7)
+  int region_bytes;  // operand / attention scratch region
+  size_t smem_bytes;
+};
+int mega_tc_fill(MegaTcP& P, int sm_count);
+int mega_tc_launch(const MegaTcP& P, int sm_count, cudaStream_t s);
+size_t mega_tc_packed_bytes(int N, int K, bool interleave);
+int mega_tc_pack(const bf16* src, const bf16* src2, int N, int K, bool interleave, void* dst,
+                 cudaStream_t s);
+
 void decode_set_sm_count(int n);
 void decode_set_pdl(bool on);
 int decode_prepare(const DecodeDims& d, int cluster);

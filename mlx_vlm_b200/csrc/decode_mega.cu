@@ -13,131 +13,11 @@
 //     boundary; activations cross CTAs through L2 (ld.global.cg).
 // Rounding points follow oracle/qwen2vl.py::lm_layers_forward (same device
 // functions as the multi-kernel path in decode.cu).
-#include "common.cuh"
-#include "decode.cuh"
+#include "mega_common.cuh"
 
 namespace b200 {
 
 namespace {
-
-__device__ __forceinline__ uint32_t s_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
-}
-// bounded wait: a scheduling bug must not hang the GPU (sets *err and falls through)
-__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity, int* err) {
-  uint32_t done;
-  const uint32_t addr = s_u32(bar);
-  unsigned spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1u << 20)) {
-      *err = 2;
-      break;
-    }
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
-                                         uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1], %2, [%3], %4;" ::"r"(s_u32(dst)),
-      "l"(src), "r"(bytes), "r"(s_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-// activations written by other CTAs in an earlier phase: read through L2
-__device__ __forceinline__ uint4 ldcg16(const void* p) {
-  return __ldcg(reinterpret_cast<const uint4*>(p));
-}
-__device__ __forceinline__ float ldcg_bf(const bf16* p) {
-  return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p)) << 16);
-}
-// packed fp32 FMA (Blackwell FFMA2): (d0,d1) += (a0,a1) * (b0,b1), two IEEE fp32 FMAs per issue
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
-      "mov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%0,%1};\n\t"
-      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0,%1}, rc;\n\t}"
-      : "+f"(d0), "+f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-enum { PH_QKV = 0, PH_ORES = 1, PH_GATEUP = 2, PH_DRES = 3, PH_HEAD = 4 };
-
-__device__ __forceinline__ long long gtimer() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-template <int MODE>
-struct PhTraits {
-  static constexpr bool PAIR = (MODE == PH_QKV || MODE == PH_GATEUP);
-  static constexpr bool NORM = (MODE == PH_QKV || MODE == PH_GATEUP || MODE == PH_HEAD);
-  static constexpr int NRW = PAIR ? 2 : 1;
-};
-
-}  // namespace
-
-constexpr int MEGA_THREADS = 288;
-constexpr int MEGA_STAGE = 48 * 1024;
-constexpr int MEGA_ATT_G = 4;
-constexpr int ATT_UN = 8;  // key ranges per (kv head, q-head group) in the attention phase
-
-struct MegaShared {
-  uint64_t full_bar[8], empty_bar[8];
-  float red[2][8][2];
-  float2 wstat[8];
-  float s_m[8][MEGA_ATT_G], s_l[8][MEGA_ATT_G];
-  unsigned long long bar_base;
-  unsigned long long att_base;
-  float lse;
-  unsigned long long best;
-  int feed;
-  int err;
-};
-
-// ring position shared by producer and consumers (each keeps its own copy)
-struct Ring {
-  int cur;        // ring slot of the next tile
-  uint32_t ph;    // its phase parity
-  int n_stages;
-  __device__ __forceinline__ int slot() const { return cur; }
-  __device__ __forceinline__ uint32_t parity() const { return ph; }
-  __device__ __forceinline__ void advance() {  // no integer division on the per-tile path
-    if (++cur == n_stages) {
-      cur = 0;
-      ph ^= 1u;
-    }
-  }
-};
 
 template <int MODE>
 __device__ __forceinline__ const bf16* mega_tile_src(const MegaPhase& g, const bf16* W,
@@ -453,326 +333,7 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
   }
 }
 
-// ---- consumers: attention ------------------------------------------------------
-// Under the weight stream every dependent global round trip costs ~1 us, so the phase
-// is built around the NUMBER of such trips.  CTA (grp, unit): grp = (kv head, q-head
-// group), unit = one of ATT_UN key ranges.
-//   1. scores of the OWN key range (coalesced: 8 lanes per key, 4 keys per warp
-//      instruction, all K loads of the range in flight at once), local (max, sum exp)
-//      per head -> global stats;
-//   2. group barrier among the ATT_UN CTAs of the group (atomic counter);
-//   3. global (M, L) from the ATT_UN stats, p = bf16(exp(s - M) / L), partial P.V
-//      (V rows were requested before the barrier);
-//   4. the last CTA of the group to finish sums the partial outputs in a fixed order.
-// Measured alternatives (tools/mega_timeline.py, ctx ~470): one CTA per (kv head,
-// group) 15.9 us; one CTA per q head 17.1 us; every unit recomputing all scores
-// 11.1 us; this 10.6 us.
-template <int HD>
-__device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const bf16* vc,
-                                           float* scratch, MegaShared* sh, int nkeys, int layer,
-                                           long long* tdbg = nullptr) {
-  int tn = 0;
-#define ATT_STAMP() do { if (tdbg && threadIdx.x == 0 && tn < 30) tdbg[tn++] = gtimer(); } while (0)
-  ATT_STAMP();
-  constexpr int EPL = HD / 32, SEG = HD / 8, AG = MEGA_ATT_G, NV = SEG / 8, UNR = 2;
-  const DecodeDims& d = p.d;
-  const int Gall = d.n_heads / d.n_kv;
-  const int G = Gall / p.hsplit;
-  const int ucap = (d.cap + ATT_UN - 1) / ATT_UN;
-  float* sc = scratch;                       // [AG][ucap]
-  float* red = sc + (long)AG * ucap;         // [8][AG*HD]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = blockIdx.x / ATT_UN, unit = blockIdx.x % ATT_UN;
-  const int kvh = grp / p.hsplit;
-  const int h0 = kvh * Gall + (grp % p.hsplit) * G;
-  const bf16* kb = kc + (long)kvh * d.cap * HD;
-  const bf16* vb = vc + (long)kvh * d.cap * HD;
-  const int per = (nkeys + ATT_UN - 1) / ATT_UN;
-  const int u0 = min(nkeys, unit * per), u1 = min(nkeys, u0 + per);
-  const int seg = lane & 7, ksub = lane >> 3;
-  // ---- all global requests of the phase are issued before the first use: q, the first
-  // 2 x 4 keys of this warp, and the V rows of its first VPRE keys (one round trip) ----
-  constexpr int VPRE = 8;
-  uint4 qraw[AG][NV];
-#pragma unroll
-  for (int g = 0; g < AG; ++g)
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-      qraw[g][v] = (g < G) ? ldcg16(p.qbuf + (long)(h0 + g) * HD + seg * SEG + v * 8)
-                           : make_uint4(0, 0, 0, 0);
-  uint4 kvn[UNR][NV];
-  {
-    const int j0 = u0 + warp * 4;
-#pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      const int j = j0 + 32 * q + ksub;
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-        kvn[q][v] = (j < u1) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8) : make_uint4(0, 0, 0, 0);
-    }
-  }
-  uint2 vraw[VPRE];
-#pragma unroll
-  for (int q = 0; q < VPRE; ++q) {
-    const int j = u0 + warp + 8 * q;
-    vraw[q] = make_uint2(0, 0);
-    if (j < u1) {
-      const bf16* vr = vb + (long)j * HD + lane * EPL;
-      if (EPL == 4) vraw[q] = __ldcg(reinterpret_cast<const uint2*>(vr));
-      else vraw[q].x = __ldcg(reinterpret_cast<const uint32_t*>(vr));
-    }
-  }
-  float qr[AG][SEG];
-#pragma unroll
-  for (int g = 0; g < AG; ++g)
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float f[8];
-      unpack8(qraw[g][v], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) qr[g][v * 8 + i] = rbf(f[i] * d.scale_bf);
-    }
-  ATT_STAMP();  // q loaded
-  // ---- 1. scores of the own range (software-pipelined over trips of 2 x 4 keys) ----
-  float lm[AG];
-#pragma unroll
-  for (int g = 0; g < AG; ++g) lm[g] = -INFINITY;
-  for (int j0 = u0 + warp * 4; j0 < u1; j0 += 32 * UNR) {
-    uint4 kv[UNR][NV];
-#pragma unroll
-    for (int q = 0; q < UNR; ++q)
-#pragma unroll
-      for (int v = 0; v < NV; ++v) kv[q][v] = kvn[q][v];
-    if (j0 + 32 * UNR < u1) {
-#pragma unroll
-      for (int q = 0; q < UNR; ++q) {
-        const int j = j0 + 32 * UNR + 32 * q + ksub;
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-          kvn[q][v] = (j < u1) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8)
-                               : make_uint4(0, 0, 0, 0);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      const int j = j0 + 32 * q + ksub;
-      float s[AG];
-#pragma unroll
-      for (int g = 0; g < AG; ++g) s[g] = 0.f;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        float kf[8];
-        unpack8(kv[q][v], kf);
-#pragma unroll
-        for (int g = 0; g < AG; ++g)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s[g] = fmaf(qr[g][v * 8 + i], kf[i], s[g]);
-      }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1)
-#pragma unroll
-        for (int g = 0; g < AG; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
-      if (j < u1 && seg == 0) {
-#pragma unroll
-        for (int g = 0; g < AG; ++g) {
-          const float r = rbf(s[g]);
-          sc[(long)g * ucap + (j - u0)] = r;
-          lm[g] = fmaxf(lm[g], r);
-        }
-      }
-    }
-  }
-  ATT_STAMP();  // scores done
-  float vpre[VPRE][EPL];
-#pragma unroll
-  for (int q = 0; q < VPRE; ++q) {
-    if (EPL == 4) {
-      float t4[4];
-      unpack4(vraw[q], t4);
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) vpre[q][e] = t4[e];
-    } else {
-      vpre[q][0] = __uint_as_float(vraw[q].x << 16);
-      vpre[q][EPL - 1] = __uint_as_float(vraw[q].x & 0xffff0000u);
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < AG; ++g) {
-    lm[g] = warp_max(lm[g]);
-    if (lane == 0) sh->s_m[warp][g] = lm[g];
-  }
-  cbar();
-  float ml[AG], ls[AG];
-#pragma unroll
-  for (int g = 0; g < AG; ++g) {
-    float m = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) m = fmaxf(m, sh->s_m[w][g]);
-    ml[g] = m;
-    ls[g] = 0.f;
-  }
-  for (int j = threadIdx.x; j < u1 - u0; j += 256) {
-#pragma unroll
-    for (int g = 0; g < AG; ++g) ls[g] += expf(sc[(long)g * ucap + j] - ml[g]);
-  }
-#pragma unroll
-  for (int g = 0; g < AG; ++g) {
-    ls[g] = warp_sum(ls[g]);
-    if (lane == 0) sh->s_l[warp][g] = ls[g];
-  }
-  cbar();
-  ATT_STAMP();  // local stats done
-  // ---- 2. publish the local statistics, group barrier ----
-  float2* gstats = reinterpret_cast<float2*>(p.att_stats) + (long)grp * ATT_UN * AG;
-  if (threadIdx.x < AG) {
-    float l = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) l += sh->s_l[w][threadIdx.x];
-    gstats[unit * AG + threadIdx.x] = make_float2(ml[threadIdx.x], (u1 > u0) ? l : 0.f);
-  }
-  cbar();
-  if (threadIdx.x == 0) {
-    const unsigned long long target = (sh->att_base + (unsigned long long)layer + 1ull) * ATT_UN;
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&p.att_cnt[grp]), "l"(1ull)
-                 : "memory");
-    unsigned spins = 0;
-    while (ld_acquire_u64(&p.att_cnt[grp]) < target) {
-      if (++spins > (1u << 22)) {
-        sh->err = 3;
-        break;
-      }
-    }
-  }
-  cbar();
-  ATT_STAMP();  // group barrier passed
-  // ---- 3. global statistics: ONE warp reads the ATT_UN x AG pairs (lane = u*AG + g) ----
-  if (warp == 0) {
-    static_assert(ATT_UN * MEGA_ATT_G == 32, "one lane per (unit, head)");
-    const float2 stv = __ldcg(&gstats[lane]);
-    // max / rescaled sum over the units of head g = lane % AG: butterfly over the unit bits
-    float m = stv.x;
-#pragma unroll
-    for (int o = AG; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float l = (stv.y > 0.f) ? stv.y * expf(stv.x - m) : 0.f;
-#pragma unroll
-    for (int o = AG; o < 32; o <<= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-    if (lane < AG) {
-      sh->s_m[0][lane] = m;
-      sh->s_l[0][lane] = l;
-    }
-  }
-  cbar();
-  float M[AG], L[AG];
-#pragma unroll
-  for (int g = 0; g < AG; ++g) {
-    M[g] = sh->s_m[0][g];
-    L[g] = sh->s_l[0][g];
-  }
-  // p = bf16(exp(s - M) / L) for the own keys, one key per thread, in place
-  for (int j = threadIdx.x; j < u1 - u0; j += 256) {
-#pragma unroll
-    for (int g = 0; g < AG; ++g)
-      sc[(long)g * ucap + j] = rbf(expf(sc[(long)g * ucap + j] - M[g]) / L[g]);
-  }
-  cbar();
-  ATT_STAMP();  // global stats read
-  float acc[AG][EPL];
-#pragma unroll
-  for (int g = 0; g < AG; ++g)
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[g][e] = 0.f;
-#pragma unroll
-  for (int q = 0; q < VPRE; ++q) {
-    const int j = u0 + warp + 8 * q;
-    if (j < u1) {
-#pragma unroll
-      for (int g = 0; g < AG; ++g) {
-        const float pj = sc[(long)g * ucap + (j - u0)];
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[g][e] = fmaf(pj, vpre[q][e], acc[g][e]);
-      }
-    }
-  }
-  for (int j0 = u0 + warp + 8 * VPRE; j0 < u1; j0 += 32) {  // 4 keys per trip, loads first
-    float vf[4][EPL];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j0 + 8 * q;
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) vf[q][e] = 0.f;
-      if (j < u1) {
-        const bf16* vr = vb + (long)j * HD + lane * EPL;
-        if (EPL == 4) {
-          float t4[4];
-          unpack4(__ldcg(reinterpret_cast<const uint2*>(vr)), t4);
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) vf[q][e] = t4[e];
-        } else {
-          const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(vr));
-          vf[q][0] = __uint_as_float(w << 16);
-          vf[q][EPL - 1] = __uint_as_float(w & 0xffff0000u);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j0 + 8 * q;
-      if (j < u1) {
-#pragma unroll
-        for (int g = 0; g < AG; ++g) {
-          const float pj = sc[(long)g * ucap + (j - u0)];
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) acc[g][e] = fmaf(pj, vf[q][e], acc[g][e]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < AG; ++g)
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) red[((long)warp * AG + g) * HD + lane * EPL + e] = acc[g][e];
-  ATT_STAMP();  // PV done
-  cbar();
-  float* mypart = p.att_part + ((long)grp * ATT_UN + unit) * AG * HD;
-  for (int i = threadIdx.x; i < G * HD; i += 256) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[(long)w * AG * HD + i];
-    mypart[i] = s;
-  }
-  cbar();
-  // (the ATT_UN partial outputs are summed, in a fixed order, by the o_proj prologue)
-  ATT_STAMP();  // end
-#undef ATT_STAMP
-}
-
-__device__ __forceinline__ uint32_t orderable_u(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-// software grid barrier among the consumer threads of all CTAs
-__device__ __forceinline__ void grid_barrier(const MegaP& p, MegaShared* sh, unsigned& idx) {
-  cbar();
-  if (threadIdx.x == 0) {
-    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-      p.dbg[((blockIdx.x ? 1 : 0) * 1024 + idx) * 2] = gtimer();
-    const unsigned long long target = sh->bar_base + (unsigned long long)(idx + 1) * gridDim.x;
-    // release: the CTA's writes (ordered before by bar.sync) become visible before the count
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p.bar), "l"(1ull) : "memory");
-    unsigned spins = 0;
-    while (ld_acquire_u64(p.bar) < target) {
-      if (++spins > (1u << 22)) {
-        sh->err = 1;
-        break;
-      }
-    }
-    if (p.dbg && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-      p.dbg[((blockIdx.x ? 1 : 0) * 1024 + idx) * 2 + 1] = gtimer();
-  }
-  ++idx;
-  cbar();
-}
+}  // namespace
 
 template <int CHH, int CHI>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
@@ -843,9 +404,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     }
     grid_barrier(p, &sh, bidx);
     if ((int)blockIdx.x < p.attn_ctas) {
-      if (d.hd == 128) attn_phase<128>(p, kc, vc, scratch, &sh, ctx + 1, l,
+      const AttnParts ap = {nullptr, 0, 0, nullptr, 0};
+      if (d.hd == 128) attn_phase<128, false>(p, kc, vc, scratch, &sh, ctx + 1, l, ap,
                                        (p.dbg && l == 5 && blockIdx.x < 2) ? p.dbg + 4096 + 128 + 32 * blockIdx.x : nullptr);
-      else attn_phase<64>(p, kc, vc, scratch, &sh, ctx + 1, l);
+      else attn_phase<64, false>(p, kc, vc, scratch, &sh, ctx + 1, l, ap);
     }
     grid_barrier(p, &sh, bidx);
     {
@@ -873,81 +435,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     consume_phase<PH_HEAD, CHH>(p, p.ph[PH_HEAD], io, ring, xs, &sh, rg, 0, 0);
   }
   grid_barrier(p, &sh, bidx);
-  // ---- sampler: logprobs = bf16(logits - bf16(lse)), argmax with lowest index ----
-  if (warp == 0) {
-    float M = -INFINITY;
-    for (int i = lane; i < (int)gridDim.x; i += 32) M = fmaxf(M, __ldcg(&p.partials[i]).x);
-    M = warp_max(M);
-    float L = 0.f;
-    for (int i = lane; i < (int)gridDim.x; i += 32) {
-      const float2 pr = __ldcg(&p.partials[i]);
-      if (pr.y > 0.f) L += pr.y * expf(pr.x - M);
-    }
-    L = warp_sum(L);
-    if (lane == 0) {
-      sh.lse = rbf(M + logf(L));
-      sh.best = 0ull;
-    }
-  }
-  cbar();
-  {
-    const float lse = sh.lse;
-    unsigned long long best = 0ull;
-    const int nvec = d.vocab >> 3;
-    for (int c = blockIdx.x * 256 + threadIdx.x; c < nvec; c += gridDim.x * 256) {
-      float f[8], o[8];
-      unpack8(ldcg16(p.logits + (long)c * 8), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j] = rbf(f[j] - lse);
-        const unsigned long long key =
-            ((unsigned long long)orderable_u(o[j]) << 32) | (0xFFFFFFFFu - (uint32_t)(c * 8 + j));
-        best = key > best ? key : best;
-      }
-      uint4 ov;
-      ov.x = pack2(o[0], o[1]);
-      ov.y = pack2(o[2], o[3]);
-      ov.z = pack2(o[4], o[5]);
-      ov.w = pack2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(p.logprobs + (long)c * 8) = ov;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other > best ? other : best;
-    }
-    if (lane == 0) atomicMax(&sh.best, best);
-    cbar();
-    if (threadIdx.x == 0) atomicMax(&p.st->best_key, sh.best);
-  }
-  grid_barrier(p, &sh, bidx);
-  if (blockIdx.x == 0) {
-    if (threadIdx.x == 0) {
-      const unsigned long long key = ld_acquire_u64(&p.st->best_key);
-      const int tok = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
-      const int n = p.st->n_out;
-      p.token_log[n % p.log_cap] = tok;
-      int feed = tok;
-      if (p.st->use_force) feed = p.force[n % p.log_cap];
-      sh.feed = feed;
-      p.st->tok = feed;
-      p.st->n_out = n + 1;
-      p.st->ctx += p.advance;
-      p.st->pos += p.advance;
-      p.st->best_key = 0ull;
-      p.st->bar_base = sh.bar_base + (unsigned long long)bidx * gridDim.x;
-      p.st->att_base = sh.att_base + (unsigned long long)p.n_layers;
-      if (sh.err) p.st->error = sh.err;
-    }
-    cbar();
-    const int feed = sh.feed;
-    const int nv = d.hidden >> 3;
-    for (int c = threadIdx.x; c < nv; c += 256)
-      *reinterpret_cast<uint4*>(p.h + c * 8) =
-          __ldg(reinterpret_cast<const uint4*>(p.embed + (long)feed * d.hidden + c * 8));
-  } else if (threadIdx.x == 0 && sh.err) {
-    p.st->error = sh.err;
-  }
+  mega_sample_finalize(p, sh, bidx);
 }
 
 // ---------------------------------------------------------------------------

@@ -76,7 +76,13 @@ struct b200_engine {
   int attn_cluster = 8;
   int prepared_cap = -1, prepared_cluster = -1;
   // megakernel
-  bool use_mega = true;
+  int use_mega = 1;  // 0: one kernel per phase, 1: k_mega (CUDA cores), 2: k_mega_tc (tcgen05)
+  MegaTcP tp;
+  uint8_t* packed = nullptr;  // tile images of the LM weights (k_mega_tc)
+  size_t packed_bytes = 0;
+  bool packed_ready = false;
+  float* tc_parts = nullptr;
+  int tc_alias = 1;
   float* att_part = nullptr;
   float* att_stats = nullptr;
   unsigned long long* att_cnt = nullptr;
@@ -167,7 +173,7 @@ static void invalidate_graph(b200_engine* e) {
   }
 }
 
-static int mega_prepare(b200_engine* e) {
+static int mega_prepare(b200_engine* e, cudaStream_t s) {
   const auto& c = e->cfg;
   B200_REQUIRE(c.n_layers <= MEGA_MAX_LAYERS, "mega: %d layers > %d", c.n_layers, MEGA_MAX_LAYERS);
   if (!e->bar) {
@@ -196,7 +202,59 @@ static int mega_prepare(b200_engine* e) {
   p.partials = e->partials; p.st = e->st; p.token_log = e->token_log; p.log_cap = e->log_cap;
   p.force = e->force; p.inv_freq = e->lm_inv_freq; p.bar = e->bar; p.advance = 1;
   p.dbg = e->dbg;
-  int rc = mega_fill(p, e->sm_count);
+  int rc;
+  if (e->use_mega == 2) {
+    // ---- tensor-core variant: tile images of the weights + split-K partial buffers ----
+    const int QKV = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim, H = c.hidden, I = c.inter;
+    const int OK_ = c.n_heads * c.head_dim;
+    const size_t b_qkv = mega_tc_packed_bytes(QKV, H, false), b_o = mega_tc_packed_bytes(H, OK_, false);
+    const size_t b_gu = mega_tc_packed_bytes(I, H, true), b_d = mega_tc_packed_bytes(H, I, false);
+    const size_t b_head = mega_tc_packed_bytes(c.vocab, H, false);
+    const size_t total = (size_t)c.n_layers * (b_qkv + b_o + b_gu + b_d) + b_head;
+    if (!e->packed || e->packed_bytes < total) {
+      if (e->packed) cudaFree(e->packed);
+      e->packed = nullptr;
+      B200_CUDA(cudaMalloc(&e->packed, total));
+      e->packed_bytes = total;
+      e->packed_ready = false;
+    }
+    MegaTcP& P = e->tp;
+    memset(&P, 0, sizeof(P));
+    uint8_t* w = e->packed;
+    for (int l = 0; l < c.n_layers; ++l) {
+      const LayerW& lw = e->layers[l];
+      LayerWT& lt = P.lt[l];
+      lt.wqkv = w; w += b_qkv;
+      lt.wo = w; w += b_o;
+      lt.wgu = w; w += b_gu;
+      lt.wd = w; w += b_d;
+      if (!e->packed_ready) {
+        if ((rc = mega_tc_pack(lw.wqkv, nullptr, QKV, H, false, (void*)lt.wqkv, s))) return rc;
+        if ((rc = mega_tc_pack(lw.wo, nullptr, H, OK_, false, (void*)lt.wo, s))) return rc;
+        if ((rc = mega_tc_pack(lw.wgu, lw.wgu + (long)I * H, I, H, true, (void*)lt.wgu, s))) return rc;
+        if ((rc = mega_tc_pack(lw.wd, nullptr, H, I, false, (void*)lt.wd, s))) return rc;
+      }
+    }
+    P.head_t = w;
+    if (!e->packed_ready)
+      if ((rc = mega_tc_pack(e->head, nullptr, c.vocab, H, false, (void*)w, s))) return rc;
+    e->packed_ready = true;
+    P.part_stride = ((long)(QKV > H ? QKV : H) + 127) & ~127L;
+    if (!e->tc_parts) B200_CUDA(cudaMalloc(&e->tc_parts, (size_t)3 * 64 * 16384 * sizeof(float)));
+    B200_REQUIRE(P.part_stride <= 16384, "mega_tc: %ld rows > 16384", P.part_stride);
+    P.qkv_part = e->tc_parts;
+    P.o_part = e->tc_parts + (size_t)64 * 16384;
+    P.d_part = e->tc_parts + (size_t)2 * 64 * 16384;
+    P.x_kstride = e->tc_alias ? 1024 : 2048;
+    P.x_sbo = e->tc_alias ? 0 : 1024;
+    P.base = p;
+    if ((rc = mega_tc_fill(P, e->sm_count))) return rc;
+    for (int i = 0; i < 5; ++i)
+      B200_REQUIRE(P.ph[i].S <= 64, "mega_tc: %d K splits > 64", P.ph[i].S);
+    e->mega_ready = true;
+    return B200_OK;
+  }
+  rc = mega_fill(p, e->sm_count);
   if (rc) return rc;
   e->mega_ready = true;
   return B200_OK;
@@ -207,6 +265,7 @@ static int enqueue_step(b200_engine* e, cudaStream_t s) {
   const DecodeDims d = e->dims();
   const auto& c = e->cfg;
   int rc;
+  if (e->use_mega == 2) return mega_tc_launch(e->tp, e->sm_count, s);
   if (e->use_mega) return mega_launch(e->mp, e->sm_count, s);
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerW& lw = e->layers[l];
@@ -331,6 +390,7 @@ int b200_engine_set_weight(b200_engine* e, const char* name, const void* ptr, lo
   e->w[name] = (const bf16*)ptr;
   e->wn[name] = n_elems;
   e->resolved = false;
+  e->packed_ready = false;
   invalidate_graph(e);
   return B200_OK;
 }
@@ -608,7 +668,7 @@ int b200_engine_decode(b200_engine* e, int n_steps, const int* force_tokens_host
     e->prepared_cluster = e->attn_cluster;
   }
   if (e->use_mega && !e->mega_ready) {
-    if ((rc = mega_prepare(e))) return rc;
+    if ((rc = mega_prepare(e, s))) return rc;
   }
   if (e->use_graph && !e->gexec) {
     // capture one step on the engine's own stream (capture does not execute)
@@ -656,7 +716,9 @@ int b200_engine_set_graph(b200_engine* e, int enabled) {
 }
 int b200_engine_set_mega(b200_engine* e, int enabled) {
   B200_REQUIRE(e, "set_mega: null engine");
-  e->use_mega = enabled != 0;
+  B200_REQUIRE(enabled >= 0 && enabled <= 3, "set_mega: mode %d (0 off, 1 k_mega, 2 k_mega_tc, 3 k_mega_tc with a 16-row operand)", enabled);
+  e->use_mega = enabled == 3 ? 2 : enabled;
+  e->tc_alias = enabled == 3 ? 0 : 1;
   invalidate_graph(e);
   return B200_OK;
 }

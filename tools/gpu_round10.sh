@@ -10,7 +10,7 @@ echo "bench exit $?" >> gpurun_out/summary.txt
 timeout -s KILL 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r1_reference.json 2>> gpurun_out/bench_r1.err
 echo "bench ref exit $?" >> gpurun_out/summary.txt
 timeout -s KILL 300 python tools/mega_timeline.py > gpurun_out/mega_timeline_r1.txt 2>&1
-timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:b200" -c 2000 --csv --log-file gpurun_out/launches_request_r1.csv python tools/profile_decode.py 3 > gpurun_out/prof.log 2>&1
+timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:attention_kernel|cast_f32|embed_merge|k_attn|k_mega|k_sample|k_set_state|k_stream|layer_norm|mrope_kv|rms_norm|swiglu_kernel|vision_rope|gemm" -c 3000 --csv --log-file gpurun_out/launches_request_r1.csv python tools/profile_decode.py 3 > gpurun_out/prof.log 2>&1
 echo "ncu list exit $?" >> gpurun_out/summary.txt
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:k_mega" -s 2 -c 1 -o gpurun_out/prof_mega_r1 -f python tools/profile_decode.py 3 > gpurun_out/prof2.log 2>&1
 echo "ncu full exit $?" >> gpurun_out/summary.txt
