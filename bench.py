@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--no-mega", action="store_true")
+    ap.add_argument("--mega-mode", type=int, default=None,
+                    help="decode kernel: 0 per-phase kernels, 1 k_mega (CUDA cores), 2 k_mega_tc (tcgen05)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -244,6 +246,8 @@ def main():
         eng.set_pdl(True)
     if args.no_mega:
         eng.set_mega(False)
+    if args.mega_mode is not None:
+        eng.set_mega(args.mega_mode)
     if world > 1:
         # the single collective of the design: rank 0's weights broadcast over NVLink (NCCL)
         for name in sorted(eng.weights):

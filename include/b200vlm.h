@@ -186,9 +186,15 @@ long b200_engine_tokens_launched(const b200_engine* e);
 long b200_engine_launch_count(const b200_engine* e);
 /* 0: decode via plain launches, 1: CUDA-graph replay (default) */
 int b200_engine_set_graph(b200_engine* e, int enabled);
-/* 1 (default): the decode step is ONE persistent kernel (k_mega: weight ring +
- * software grid barrier); 0: one kernel per phase (28 x 5 + 2 launches). */
+/* decode-step implementation.  0: one kernel per phase (28 x 5 + 2 launches);
+ * 1: ONE persistent kernel, CUDA-core GEMV consumers (k_mega: weight ring + software grid
+ * barrier); 2: the same step with tcgen05 GEMV consumers on pre-packed tile images of
+ * the weights (k_mega_tc; the engine allocates the packed copy on first use);
+ * 3: as 2 with a full 16-row activation operand (debugging). */
 int b200_engine_set_mega(b200_engine* e, int enabled);
+/* debugging / test aid: device pointer and size of an internal buffer.  names: "h", "act",
+ * "tc_acc" (k_mega_tc fixed-point split-K accumulators, 3 x rows int64). */
+int b200_engine_debug_buffer(b200_engine* e, const char* name, void** ptr, long* bytes);
 /* synchronous: reads the device-side error flag (0 = none; a bounded wait gave up) */
 int b200_engine_device_error(b200_engine* e, int* out);
 /* debugging aid (k_mega): first call enables per-barrier globaltimer stamps, later

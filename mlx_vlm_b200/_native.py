@@ -70,6 +70,7 @@ SIGNATURES = {
     "b200_engine_set_pdl": (_I, [_P, _I]),
     "b200_engine_set_mega": (_I, [_P, _I]),
     "b200_engine_mega_timeline": (_I, [_P, _P]),
+    "b200_engine_debug_buffer": (_I, [_P, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long)]),
     "b200_engine_device_error": (_I, [_P, C.POINTER(_I)]),
     "b200_engine_fetch_tokens": (_I, [_P, _L, _I, _P, _P]),
     "b200_memcpy_d2d": (_I, [_P, _P, _L, _P]),

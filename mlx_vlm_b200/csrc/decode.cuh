@@ -82,9 +82,9 @@ struct MegaTcP {
   MegaP base;
   LayerWT lt[MEGA_MAX_LAYERS];
   const uint8_t* head_t;
-  float *qkv_part, *o_part, *d_part;  // [S][part_stride] fp32 split-K partial sums
-  long part_stride;
+  long long *qkv_acc, *o_acc, *d_acc;  // fixed-point split-K sums, one per output row
   MegaTcPhase ph[5];
+  int max_inflight;  // weight tiles requested but not yet landed, per SM
   int sps;           // K blocks per ring stage
   int x_kstride;     // bytes between K blocks of the activation operand (1024: 8 rows, 2048: 16)
   int x_sbo;         // stride between its 8-row groups (0: rows 8..15 alias rows 0..7)

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     }
     grid_barrier(p, &sh, bidx);
     if ((int)blockIdx.x < p.attn_ctas) {
-      const AttnParts ap = {nullptr, 0, 0, nullptr, 0};
+      const AttnParts ap = {nullptr, nullptr, 0};
       if (d.hd == 128) attn_phase<128, false>(p, kc, vc, scratch, &sh, ctx + 1, l, ap,
                                        (p.dbg && l == 5 && blockIdx.x < 2) ? p.dbg + 4096 + 128 + 32 * blockIdx.x : nullptr);
       else attn_phase<64, false>(p, kc, vc, scratch, &sh, ctx + 1, l, ap);

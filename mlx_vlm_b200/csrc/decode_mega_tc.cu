@@ -47,13 +47,19 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
+// descriptors are passed as (lo, hi) 32-bit words: the start-address field lives in the low
+// word, so walking an operand is ONE 32-bit add per MMA on the issuing thread (which is the
+// only thread feeding the tensor core: ~25 instructions per MMA made the first version
+// issue-bound at ~1 us per 48 KB tile)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                          uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -61,15 +67,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    s_u32(bar))
                : "memory");
 }
-// K-major operand, 128B swizzle: rows of 128 B, 8-row groups `sbo` bytes apart
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+// K-major operand, 128B swizzle: rows of 128 B, 8-row groups `sbo` bytes apart.
+// low word: start address >> 4 [0,14), LBO (unused) [16,30); high word: SBO >> 4 [0,14),
+// descriptor version 1 at bit 14 (46), SWIZZLE_128B = 2 at bits 29..31 (61..63)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) {
+  return ((addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) {
+  return (sbo >> 4) | (1u << 14) | (2u << 29);
 }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   uint32_t r;
@@ -93,14 +98,29 @@ __device__ __forceinline__ TcUnit tc_unit(const MegaTcPhase& g, int u) {
 }
 
 // ---- producer ----------------------------------------------------------------------
+// In-flight throttle: the bandwidth-delay product of one SM's HBM share (~44 GB/s x ~1 us) is
+// about ONE 48 KB tile; more requests in flight add no throughput but queue ahead of the
+// consumers' small latency-critical loads (measured: with 4 tiles in flight a 1.5 KB L2-hit
+// load at a phase start took 3.6 us).  So tile i is requested only after tile i - max_inflight
+// has landed; the ring still fills up completely while the consumers are stalled.
+struct Producer {
+  Ring rg, lag;
+  int issued;
+};
 __device__ __forceinline__ void tc_produce(const MegaTcP& P, const MegaTcPhase& g,
                                            const uint8_t* Wt, uint8_t* ring, TcShared* sh,
-                                           Ring& rg, uint64_t pol) {
+                                           Producer& pr, uint64_t pol) {
+  Ring& rg = pr.rg;
   for (int u = blockIdx.x; u < g.units; u += gridDim.x) {
     const TcUnit t = tc_unit(g, u);
     for (int kb = t.kb0; kb < t.kb1; kb += P.sps) {
       const int n = min(P.sps, t.kb1 - kb);
       const int s = rg.slot();
+      if (pr.issued >= P.max_inflight) {
+        mb_wait(&sh->m.full_bar[pr.lag.slot()], pr.lag.parity(), &sh->m.err);
+        pr.lag.advance();
+      }
+      ++pr.issued;
       mb_wait(&sh->m.empty_bar[s], rg.parity() ^ 1u, &sh->m.err);
       const uint32_t bytes = (uint32_t)n * TC_SUB;
       mb_expect_tx(&sh->m.full_bar[s], bytes);
@@ -114,11 +134,17 @@ __device__ __forceinline__ void tc_produce(const MegaTcP& P, const MegaTcPhase& 
 // ---- MMA issuer (one thread) ---------------------------------------------------------
 __device__ __forceinline__ void tc_mma(const MegaTcP& P, const MegaTcPhase& g, uint8_t* ring,
                                        const uint8_t* xop, TcShared* sh, Ring& rg,
-                                       uint32_t& acc_it, uint32_t tmem_base) {
+                                       uint32_t& acc_it, uint32_t tmem_base, bool xfull,
+                                       long long* tdbg) {
+  int tn = 0;
+  if (tdbg) tdbg[tn++] = gtimer();
   // D = f32, A = B = bf16, both K-major, N = 16, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_ACC_COLS >> 3) << 17) |
                          ((uint32_t)(128 >> 4) << 24);
-  const uint32_t xop_a = s_u32(xop);
+  const uint32_t xop_lo = desc_lo(s_u32(xop));
+  const uint32_t ring_lo = desc_lo(s_u32(ring));
+  const uint32_t a_hi = desc_hi(1024), b_hi = desc_hi((uint32_t)P.x_sbo);
+  const uint32_t kstep = (uint32_t)P.x_kstride >> 4, stage16 = (uint32_t)P.base.stage_bytes >> 4;
   for (int u = blockIdx.x; u < g.units; u += gridDim.x) {
     const TcUnit t = tc_unit(g, u);
     const uint32_t slot = acc_it % TC_ACC_SLOTS, par = (acc_it / TC_ACC_SLOTS) & 1u;
@@ -132,17 +158,23 @@ __device__ __forceinline__ void tc_mma(const MegaTcP& P, const MegaTcPhase& g, u
       const int s = rg.slot();
       mb_wait(&sh->m.full_bar[s], rg.parity(), &sh->m.err);
       tc_fence_after();
-      const uint32_t a0 = s_u32(ring + (long)s * P.base.stage_bytes);
-      for (int sb = 0; sb < n; ++sb) {
-        const uint32_t b0 = xop_a + (uint32_t)(kb - t.kb0 + sb) * (uint32_t)P.x_kstride;
+      if (tdbg && tn < 27) tdbg[tn++] = gtimer();
+      const uint32_t a0 = ring_lo + (uint32_t)s * stage16;
+      // the operand holds either the whole vector (norm phases) or this unit's K slice
+      const uint32_t b0 = xop_lo + (uint32_t)(kb - (xfull ? 0 : t.kb0)) * kstep;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          umma_bf16(dcol, smem_desc(a0 + sb * TC_SUB + kk * 32, 1024),
-                    smem_desc(b0 + kk * 32, (uint32_t)P.x_sbo), idesc, accum);
-          accum = 1;
+      for (int sb = 0; sb < 3; ++sb) {
+        if (sb < n) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_bf16(dcol, a0 + sb * (TC_SUB >> 4) + kk * 2, a_hi, b0 + sb * kstep + kk * 2, b_hi,
+                      idesc, accum);
+            accum = 1;
+          }
         }
       }
       umma_commit(&sh->m.empty_bar[s]);  // the ring slot is free once these MMAs retire
+      if (tdbg && tn < 27) tdbg[tn++] = gtimer();
       rg.advance();
     }
     umma_commit(&sh->acc_full[slot]);
@@ -161,56 +193,80 @@ __device__ __forceinline__ void xop_zero_rows(uint8_t* xop, int kstride, int nkb
     *reinterpret_cast<uint4*>(xop + (long)kb * kstride + 128 + o * 16) = make_uint4(0, 0, 0, 0);
   }
 }
-__device__ __forceinline__ void sum_parts8(const float* base, long stride, int S, float* out) {
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-#pragma unroll 4
-  for (int ks = 0; ks < S; ++ks) {
-    const float4 u = __ldcg(reinterpret_cast<const float4*>(base + (long)ks * stride));
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (long)ks * stride + 4));
-    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
-    b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+// sum of the ATT_UN partial attention outputs of 4 consecutive channels: all loads in flight at
+// once (one L2 round trip), added in unit order (deterministic)
+__device__ __forceinline__ float4 sum_parts4(const float* base, long stride, int S) {
+  float4 v[ATT_UN];
+#pragma unroll
+  for (int ks = 0; ks < ATT_UN; ++ks)
+    v[ks] = (ks < S) ? __ldcg(reinterpret_cast<const float4*>(base + (long)ks * stride))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a = v[0];
+#pragma unroll
+  for (int ks = 1; ks < ATT_UN; ++ks) {
+    a.x += v[ks].x; a.y += v[ks].y; a.z += v[ks].z; a.w += v[ks].w;
   }
-  out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
-  out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  return a;
 }
 
 // residual update + RMSNorm -> operand.  h_new = first ? h_global : bf16(hres + bf16(sum parts))
+__device__ __forceinline__ void zero_acc(long long* acc, int n) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) acc[i] = 0ll;
+}
+
 __device__ __forceinline__ void pro_norm(const MegaTcP& P, uint8_t* xop, uint16_t* hres,
-                                         TcShared* sh, const float* parts, int S, bool first,
-                                         const bf16* lnw) {
+                                         TcShared* sh, const long long* acc, bool first,
+                                         const bf16* lnw, long long* tdbg = nullptr) {
+  int tn = 0;
+#define PRO_STAMP() do { if (tdbg && threadIdx.x == 128) tdbg[tn++] = gtimer(); } while (0)
+  PRO_STAMP();
   const DecodeDims& d = P.base.d;
   const int nvec = d.hidden >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // RMSNorm weights are requested together with the partial sums (one round trip, not two)
+  constexpr int NW = 4;
+  uint4 lw8[NW];
+#pragma unroll
+  for (int u = 0; u < NW; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    lw8[u] = (c < nvec) ? __ldg(reinterpret_cast<const uint4*>(lnw + (long)c * 8)) : make_uint4(0, 0, 0, 0);
+  }
   xop_zero_rows(xop, P.x_kstride, (d.hidden + 63) >> 6);
   float ss = 0.f;
-  for (int c = threadIdx.x; c < nvec; c += 256) {
-    float f[8];
+  for (int c = threadIdx.x; c < 2 * nvec; c += 256) {  // 4 elements per thread and trip
+    float f[4];
     if (first) {
-      unpack8(ldcg16(P.base.h + (long)c * 8), f);
+      unpack4(__ldcg(reinterpret_cast<const uint2*>(P.base.h + (long)c * 4)), f);
     } else {
-      float s8[8], hv[8];
-      sum_parts8(parts + (long)c * 8, P.part_stride, S, s8);
-      unpack8(*reinterpret_cast<const uint4*>(hres + c * 8), hv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = rbf(hv[j] + rbf(s8[j]));
+      const longlong2 q0 = __ldcg(reinterpret_cast<const longlong2*>(acc + (long)c * 4));
+      const longlong2 q1 = __ldcg(reinterpret_cast<const longlong2*>(acc + (long)c * 4 + 2));
+      float hv[4];
+      unpack4(*reinterpret_cast<const uint2*>(hres + c * 4), hv);
+      f[0] = rbf(hv[0] + rbf(__ll2float_rn(q0.x) * TC_FIX_INV));
+      f[1] = rbf(hv[1] + rbf(__ll2float_rn(q0.y) * TC_FIX_INV));
+      f[2] = rbf(hv[2] + rbf(__ll2float_rn(q1.x) * TC_FIX_INV));
+      f[3] = rbf(hv[3] + rbf(__ll2float_rn(q1.y) * TC_FIX_INV));
     }
-    uint4 o;
-    o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(hres + c * 8) = o;
+    *reinterpret_cast<uint2*>(hres + c * 4) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+    for (int j = 0; j < 4; ++j) ss = fmaf(f[j], f[j], ss);
   }
+  PRO_STAMP();  // partial sums loaded, residual updated
   ss = warp_sum(ss);
   if (lane == 0) sh->redf[warp] = ss;
   cbar();
+  PRO_STAMP();
   float tot = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += sh->redf[w];
   const float rs = 1.0f / sqrtf(tot / (float)d.hidden + d.eps);
-  for (int c = threadIdx.x; c < nvec; c += 256) {
+#pragma unroll
+  for (int u = 0; u < NW; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    if (c >= nvec) break;
     float f[8], lf[8];
     unpack8(*reinterpret_cast<const uint4*>(hres + c * 8), f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(lnw + (long)c * 8)), lf);
+    unpack8(lw8[u], lf);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = rbf(rbf(f[j] * rs) * lf[j]);
     uint4 o;
@@ -220,8 +276,11 @@ __device__ __forceinline__ void pro_norm(const MegaTcP& P, uint8_t* xop, uint16_
   // K padding (hidden not a multiple of 64): the tail chunks of the last block are zero
   for (int c = nvec + threadIdx.x; c < ((d.hidden + 63) >> 6) * 8; c += 256)
     *xop_chunk(xop, P.x_kstride, c) = make_uint4(0, 0, 0, 0);
+  PRO_STAMP();  // normalised operand written
   fence_async_smem();
+  PRO_STAMP();
   cbar();
+  PRO_STAMP();
 }
 
 // K slice of the attention output: x = bf16(sum over the ATT_UN key ranges of the partials)
@@ -236,10 +295,10 @@ __device__ __forceinline__ void pro_attn_slice(const MegaTcP& P, uint8_t* xop, c
       const int d0 = c * 8, h = d0 / d.hd, Gall = d.n_heads / d.n_kv, G = Gall / p.hsplit;
       const int grp = (h / Gall) * p.hsplit + (h % Gall) / G, gi = (h % Gall) % G;
       const float* src = p.att_part + (long)grp * ATT_UN * MEGA_ATT_G * d.hd + (long)gi * d.hd + (d0 % d.hd);
-      float s8[8];
-      sum_parts8(src, (long)MEGA_ATT_G * d.hd, ATT_UN, s8);
+      const float4 sa = sum_parts4(src, (long)MEGA_ATT_G * d.hd, ATT_UN);
+      const float4 sb = sum_parts4(src + 4, (long)MEGA_ATT_G * d.hd, ATT_UN);
       uint4 o;
-      o.x = pack2(s8[0], s8[1]); o.y = pack2(s8[2], s8[3]); o.z = pack2(s8[4], s8[5]); o.w = pack2(s8[6], s8[7]);
+      o.x = pack2(sa.x, sa.y); o.y = pack2(sa.z, sa.w); o.z = pack2(sb.x, sb.y); o.w = pack2(sb.z, sb.w);
       *xop_chunk(xop, P.x_kstride, c - c0) = o;
     }
     // K padding (K not a multiple of 64): the tail chunks of the last block stay zero
@@ -252,7 +311,9 @@ __device__ __forceinline__ void pro_attn_slice(const MegaTcP& P, uint8_t* xop, c
 
 // K slice of a bf16 activation vector in global memory (down projection input)
 __device__ __forceinline__ void pro_slice(const MegaTcP& P, uint8_t* xop, const MegaTcPhase& g,
-                                          const bf16* x) {
+                                          const bf16* x, long long* tdbg = nullptr) {
+  int tn = 0;
+  PRO_STAMP();
   if ((int)blockIdx.x < g.units) {
     const TcUnit t = tc_unit(g, blockIdx.x);
     xop_zero_rows(xop, P.x_kstride, t.kb1 - t.kb0);
@@ -260,14 +321,17 @@ __device__ __forceinline__ void pro_slice(const MegaTcP& P, uint8_t* xop, const 
     for (int c = c0 + threadIdx.x; c < t.kb1 * 8; c += 256)
       *xop_chunk(xop, P.x_kstride, c - c0) = (c < c1) ? ldcg16(x + (long)c * 8) : make_uint4(0, 0, 0, 0);
   }
+  PRO_STAMP();
   fence_async_smem();
+  PRO_STAMP();
   cbar();
+  PRO_STAMP();
 }
 
 // ---- epilogues (warps 0..3, thread = one row of the row block) ---------------------------
 template <int MODE>
 __device__ __forceinline__ void tc_epilogue(const MegaTcP& P, const MegaTcPhase& g, TcShared* sh,
-                                            uint32_t& acc_it, uint32_t tmem_base, float* part_out,
+                                            uint32_t& acc_it, uint32_t tmem_base, long long* acc_out,
                                             bf16* out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = warp * 32 + lane;
@@ -303,7 +367,7 @@ __device__ __forceinline__ void tc_epilogue(const MegaTcP& P, const MegaTcPhase&
       }
     } else {
       const int row = t.rb * 128 + r;
-      if (row < g.N) part_out[(long)t.ks * P.part_stride + row] = v;
+      if (row < g.N) fix_add(acc_out + row, v);
     }
   }
   if (MODE == PH_HEAD) {
@@ -326,16 +390,20 @@ __device__ __forceinline__ void tc_epilogue(const MegaTcP& P, const MegaTcPhase&
 template <int MODE>
 __device__ __forceinline__ void tc_run(const MegaTcP& P, const MegaTcPhase& g, uint8_t* ring,
                                        const uint8_t* xop, TcShared* sh, Ring& rg, uint32_t& acc_it,
-                                       uint32_t tmem_base, float* part_out, bf16* out) {
+                                       uint32_t tmem_base, long long* acc_out, bf16* out,
+                                       long long* tdbg = nullptr) {
   const int warp = threadIdx.x >> 5;
   if (warp == 4) {
-    if ((threadIdx.x & 31) == 0) tc_mma(P, g, ring, xop, sh, rg, acc_it, tmem_base);
+    if ((threadIdx.x & 31) == 0)
+      tc_mma(P, g, ring, xop, sh, rg, acc_it, tmem_base,
+             MODE == PH_QKV || MODE == PH_GATEUP || MODE == PH_HEAD, tdbg);
     else {
       for (int u = blockIdx.x; u < g.units; u += gridDim.x) ++acc_it;
     }
     __syncwarp();
   } else if (warp < 4) {
-    tc_epilogue<MODE>(P, g, sh, acc_it, tmem_base, part_out, out);
+    tc_epilogue<MODE>(P, g, sh, acc_it, tmem_base, acc_out, out);
+    if (tdbg && threadIdx.x == 0) tdbg[28] = gtimer();
   } else {
     for (int u = blockIdx.x; u < g.units; u += gridDim.x) ++acc_it;
   }
@@ -366,6 +434,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_tc(const __grid_consta
       mb_init(&sh.acc_empty[s], 4);
     }
     sh.m.err = 0;
+    for (int i = 0; i < d.hd / 2; ++i) sh.m.invf[i] = p.inv_freq[i];
     sh.m.bar_base = p.st->bar_base;
     sh.m.att_base = p.st->att_base;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -391,14 +460,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_tc(const __grid_consta
     // ===== producer: the whole step's weight stream =====
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
+      Producer pr;
+      pr.rg = rg;
+      pr.lag = rg;
+      pr.issued = 0;
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerWT& lt = P.lt[l];
-        tc_produce(P, P.ph[PH_QKV], lt.wqkv, ring, &sh, rg, pol);
-        tc_produce(P, P.ph[PH_ORES], lt.wo, ring, &sh, rg, pol);
-        tc_produce(P, P.ph[PH_GATEUP], lt.wgu, ring, &sh, rg, pol);
-        tc_produce(P, P.ph[PH_DRES], lt.wd, ring, &sh, rg, pol);
+        tc_produce(P, P.ph[PH_QKV], lt.wqkv, ring, &sh, pr, pol);
+        tc_produce(P, P.ph[PH_ORES], lt.wo, ring, &sh, pr, pol);
+        tc_produce(P, P.ph[PH_GATEUP], lt.wgu, ring, &sh, pr, pol);
+        tc_produce(P, P.ph[PH_DRES], lt.wd, ring, &sh, pr, pol);
       }
-      tc_produce(P, P.ph[PH_HEAD], P.head_t, ring, &sh, rg, pol);
+      tc_produce(P, P.ph[PH_HEAD], P.head_t, ring, &sh, pr, pol);
     }
     return;
   }
@@ -412,30 +485,39 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_tc(const __grid_consta
     bf16* kc = p.kv + (long)l * p.kv_layer_stride;
     bf16* vc = kc + p.kv_v_offset;
     // ---- qkv: h (+ previous layer's down partials) -> norm -> split-K partials ----
-    pro_norm(P, xop, hres, &sh, P.d_part, P.ph[PH_DRES].S, l == 0, lw.ln1);
-    tc_run<PH_QKV>(P, P.ph[PH_QKV], ring, xop, &sh, rg, acc_it, tmem_base, P.qkv_part, nullptr);
+    pro_norm(P, xop, hres, &sh, P.d_acc, l == 0, lw.ln1);
+    tc_run<PH_QKV>(P, P.ph[PH_QKV], ring, xop, &sh, rg, acc_it, tmem_base, P.qkv_acc, nullptr);
     grid_barrier(p, &sh.m, bidx);
     // ---- attention (finishes q/k/v from the partials) ----
     if ((int)blockIdx.x < p.attn_ctas) {
-      const AttnParts ap = {P.qkv_part, P.part_stride, P.ph[PH_QKV].S, lw.bqkv, pos};
+      const AttnParts ap = {P.qkv_acc, lw.bqkv, pos};
       if (d.hd == 128) attn_phase<128, true>(p, kc, vc, scratch, &sh.m, ctx + 1, l, ap);
       else attn_phase<64, true>(p, kc, vc, scratch, &sh.m, ctx + 1, l, ap);
     }
     grid_barrier(p, &sh.m, bidx);
     // ---- o_proj: split-K partials ----
+    zero_acc(P.d_acc, d.hidden);  // last read by this layer's qkv prologue, next written by down
     pro_attn_slice(P, xop, P.ph[PH_ORES]);
-    tc_run<PH_ORES>(P, P.ph[PH_ORES], ring, xop, &sh, rg, acc_it, tmem_base, P.o_part, nullptr);
+    tc_run<PH_ORES>(P, P.ph[PH_ORES], ring, xop, &sh, rg, acc_it, tmem_base, P.o_acc, nullptr);
     grid_barrier(p, &sh.m, bidx);
     // ---- gate/up: h += o ; norm ; SwiGLU ----
-    pro_norm(P, xop, hres, &sh, P.o_part, P.ph[PH_ORES].S, false, lw.ln2);
-    tc_run<PH_GATEUP>(P, P.ph[PH_GATEUP], ring, xop, &sh, rg, acc_it, tmem_base, nullptr, p.act);
+    long long* td = (p.dbg && l == 5 && blockIdx.x == 0) ? p.dbg + 4096 : nullptr;
+    if (td && threadIdx.x == 128) td[0] = gtimer();
+    zero_acc(P.qkv_acc, P.ph[PH_QKV].N);  // read by this layer's attention, next written by qkv
+    pro_norm(P, xop, hres, &sh, P.o_acc, false, lw.ln2, td ? p.dbg + 4096 + 160 : nullptr);
+    tc_run<PH_GATEUP>(P, P.ph[PH_GATEUP], ring, xop, &sh, rg, acc_it, tmem_base, nullptr, p.act,
+                      td ? td + 1 : nullptr);
     grid_barrier(p, &sh.m, bidx);
     // ---- down: split-K partials ----
-    pro_slice(P, xop, P.ph[PH_DRES], p.act);
-    tc_run<PH_DRES>(P, P.ph[PH_DRES], ring, xop, &sh, rg, acc_it, tmem_base, P.d_part, nullptr);
+    td = (p.dbg && l == 5 && blockIdx.x == 0) ? p.dbg + 4096 + 64 : nullptr;
+    if (td && threadIdx.x == 128) td[0] = gtimer();
+    zero_acc(P.o_acc, d.hidden);  // read by this layer's gate/up prologue, next written by o_proj
+    pro_slice(P, xop, P.ph[PH_DRES], p.act, td ? p.dbg + 4096 + 176 : nullptr);
+    tc_run<PH_DRES>(P, P.ph[PH_DRES], ring, xop, &sh, rg, acc_it, tmem_base, P.d_acc, nullptr,
+                    td ? td + 1 : nullptr);
     grid_barrier(p, &sh.m, bidx);
   }
-  pro_norm(P, xop, hres, &sh, P.d_part, P.ph[PH_DRES].S, p.n_layers == 0, p.final_norm);
+  pro_norm(P, xop, hres, &sh, P.d_acc, p.n_layers == 0, p.final_norm);
   tc_run<PH_HEAD>(P, P.ph[PH_HEAD], ring, xop, &sh, rg, acc_it, tmem_base, nullptr, p.logits);
   grid_barrier(p, &sh.m, bidx);
   if (warp == 4) {
@@ -525,7 +607,7 @@ int mega_tc_fill(MegaTcP& P, int sm_count) {
   MegaP& p = P.base;
   const DecodeDims& d = p.d;
   const int grid = sm_count;
-  P.sps = 3;
+  P.sps = 3;  // K blocks per ring stage (tc_mma unrolls 3)
   p.stage_bytes = P.sps * TC_SUB;
   const int qkv_rows = (d.n_heads + 2 * d.n_kv) * d.hd;
   tc_geometry(P.ph[PH_QKV], d.hidden, qkv_rows, 128, grid, P.sps, true);
@@ -547,6 +629,7 @@ int mega_tc_fill(MegaTcP& P, int sm_count) {
   p.attn_ctas = d.n_kv * hs * ATT_UN;
   B200_REQUIRE(p.attn_ctas <= grid, "mega_tc: %d attention CTAs > %d SMs", p.attn_ctas, grid);
   B200_REQUIRE(d.hd == 64 || d.hd == 128, "mega_tc: head_dim %d (64|128)", d.hd);
+  B200_REQUIRE(d.hidden <= 8192, "mega_tc: hidden %d > 8192", d.hidden);
   // operand region: the largest K range any CTA multiplies in one phase
   int max_kb = 0;
   for (int i = 0; i < 5; ++i) {

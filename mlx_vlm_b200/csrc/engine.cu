@@ -81,8 +81,10 @@ struct b200_engine {
   uint8_t* packed = nullptr;  // tile images of the LM weights (k_mega_tc)
   size_t packed_bytes = 0;
   bool packed_ready = false;
-  float* tc_parts = nullptr;
+  long long* tc_acc = nullptr;  // fixed-point split-K accumulators (k_mega_tc)
+  long tc_acc_rows = 0;
   int tc_alias = 1;
+  int tc_inflight = 2;
   float* att_part = nullptr;
   float* att_stats = nullptr;
   unsigned long long* att_cnt = nullptr;
@@ -239,18 +241,25 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
     if (!e->packed_ready)
       if ((rc = mega_tc_pack(e->head, nullptr, c.vocab, H, false, (void*)w, s))) return rc;
     e->packed_ready = true;
-    P.part_stride = ((long)(QKV > H ? QKV : H) + 127) & ~127L;
-    if (!e->tc_parts) B200_CUDA(cudaMalloc(&e->tc_parts, (size_t)3 * 64 * 16384 * sizeof(float)));
-    B200_REQUIRE(P.part_stride <= 16384, "mega_tc: %ld rows > 16384", P.part_stride);
-    P.qkv_part = e->tc_parts;
-    P.o_part = e->tc_parts + (size_t)64 * 16384;
-    P.d_part = e->tc_parts + (size_t)2 * 64 * 16384;
+    const long acc_rows = ((long)(QKV > H ? QKV : H) + 127) & ~127L;
+    if (!e->tc_acc || e->tc_acc_rows < acc_rows) {
+      if (e->tc_acc) cudaFree(e->tc_acc);
+      e->tc_acc = nullptr;
+      B200_CUDA(cudaMalloc(&e->tc_acc, (size_t)3 * acc_rows * sizeof(long long)));
+      e->tc_acc_rows = acc_rows;
+    }
+    // the kernel keeps the accumulators zero between uses; (re)establish that here
+    B200_CUDA(cudaMemsetAsync(e->tc_acc, 0, (size_t)3 * acc_rows * sizeof(long long), s));
+    P.qkv_acc = e->tc_acc;
+    P.o_acc = e->tc_acc + acc_rows;
+    P.d_acc = e->tc_acc + 2 * acc_rows;
+    P.max_inflight = e->tc_inflight;  // clamped below to n_stages - 1 (a lagging slot must not be reused)
     P.x_kstride = e->tc_alias ? 1024 : 2048;
     P.x_sbo = e->tc_alias ? 0 : 1024;
     P.base = p;
     if ((rc = mega_tc_fill(P, e->sm_count))) return rc;
-    for (int i = 0; i < 5; ++i)
-      B200_REQUIRE(P.ph[i].S <= 64, "mega_tc: %d K splits > 64", P.ph[i].S);
+    if (P.max_inflight > P.base.n_stages - 1) P.max_inflight = P.base.n_stages - 1;
+    if (P.max_inflight < 1) P.max_inflight = 1;
     e->mega_ready = true;
     return B200_OK;
   }
@@ -719,7 +728,20 @@ int b200_engine_set_mega(b200_engine* e, int enabled) {
   B200_REQUIRE(enabled >= 0 && enabled <= 3, "set_mega: mode %d (0 off, 1 k_mega, 2 k_mega_tc, 3 k_mega_tc with a 16-row operand)", enabled);
   e->use_mega = enabled == 3 ? 2 : enabled;
   e->tc_alias = enabled == 3 ? 0 : 1;
+  if (const char* v = getenv("B200_TC_INFLIGHT")) e->tc_inflight = atoi(v) > 0 ? atoi(v) : 2;  // tuning aid
   invalidate_graph(e);
+  return B200_OK;
+}
+int b200_engine_debug_buffer(b200_engine* e, const char* name, void** ptr, long* bytes) {
+  B200_REQUIRE(e && name && ptr && bytes, "debug_buffer: null argument");
+  const std::string n(name);
+  if (n == "h") { *ptr = e->h; *bytes = (long)e->cfg.hidden * 2; }
+  else if (n == "act") { *ptr = e->act; *bytes = (long)e->cfg.inter * 2; }
+  else if (n == "tc_acc" && e->tc_acc) { *ptr = e->tc_acc; *bytes = 3 * e->tc_acc_rows * 8; }
+  else {
+    set_error("debug_buffer: unknown or unallocated buffer '%s'", name);
+    return B200_ERR_INVALID;
+  }
   return B200_OK;
 }
 int b200_engine_device_error(b200_engine* e, int* out) {

@@ -99,6 +99,19 @@ constexpr int MEGA_THREADS = 288;
 constexpr int MEGA_STAGE = 48 * 1024;
 constexpr int MEGA_ATT_G = 4;
 constexpr int ATT_UN = 8;  // key ranges per (kv head, q-head group) in the attention phase
+// k_mega_tc: split-K partial sums are accumulated EXACTLY in 64-bit fixed point (2^-32 units)
+// with red.global.add.u64: the sum is independent of the arrival order (deterministic) and the
+// reader needs ONE load per row instead of one per split.  fp32 -> fixed is exact for
+// |v| >= 2^-9 and within 2^-33 absolute below; |v| < 2^31.
+constexpr float TC_FIX_SCALE = 4294967296.0f;
+constexpr float TC_FIX_INV = 1.0f / 4294967296.0f;
+__device__ __forceinline__ void fix_add(long long* acc, float v) {
+  const long long q = __float2ll_rn(v * TC_FIX_SCALE);
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(acc), "l"(q) : "memory");
+}
+__device__ __forceinline__ float fix_get(const long long* acc) {
+  return __ll2float_rn(__ldcg(acc)) * TC_FIX_INV;
+}
 
 struct MegaShared {
   uint64_t full_bar[8], empty_bar[8];
@@ -111,6 +124,7 @@ struct MegaShared {
   unsigned long long best;
   int feed;
   int err;
+  float invf[64];  // rotary inverse frequencies (k_mega_tc: no global round trip in the prologue)
 };
 
 // ring position shared by producer and consumers (each keeps its own copy)
@@ -145,14 +159,12 @@ namespace {
 // Measured alternatives (tools/mega_timeline.py, ctx ~470): one CTA per (kv head,
 // group) 15.9 us; one CTA per q head 17.1 us; every unit recomputing all scores
 // 11.1 us; this 10.6 us.
-// PARTS (k_mega_tc): q / k / v of this step arrive as split-K fp32 partial sums of the qkv
-// GEMV; the phase prologue finishes them (sum in a fixed order, + bias, round, rotary, q *
-// scale) in shared memory, the unit that owns the new key scores it from there and one CTA
-// per kv head appends it to the cache.
+// PARTS (k_mega_tc): q / k / v of this step arrive as fixed-point split-K sums of the qkv
+// GEMV; the phase prologue finishes them (+ bias, round, rotary, q * scale) in shared
+// memory, the unit that owns the new key scores it from there and one CTA per kv head
+// appends it to the cache.
 struct AttnParts {
-  const float* part;  // [S][stride]
-  long stride;
-  int S;
+  const long long* acc;  // [qkv rows]
   const bf16* bias;
   int pos;
 };
@@ -227,9 +239,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
       const int slot = i / HD, j = i % HD;
       const int row = (slot < G) ? (h0 + slot) * HD + j
                                  : ((slot == G ? d.n_heads + kvh : d.n_heads + d.n_kv + kvh) * HD + j);
-      float s = 0.f;
-#pragma unroll 4
-      for (int ks = 0; ks < ap.S; ++ks) s += __ldcg(ap.part + (long)ks * ap.stride + row);
+      const float s = fix_get(ap.acc + row);
       (slot < G ? qs + (long)slot * HD : (slot == G ? kn : vn))[j] = rbf(s + bf2f(ap.bias[row]));
     }
     cbar();
@@ -238,7 +248,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
       const int slot = i / half, j = i % half;
       float* v = (slot < G) ? qs + (long)slot * HD : kn;
       const float y1 = v[j], y2 = v[j + half];
-      const float ang = (float)ap.pos * p.inv_freq[j];
+      const float ang = (float)ap.pos * sh->invf[j];
       const float c = rbf(cosf(ang)), sn = rbf(sinf(ang));
       float o1 = rbf(rbf(y1 * c) + rbf((-y2) * sn));
       float o2 = rbf(rbf(y2 * c) + rbf(y1 * sn));

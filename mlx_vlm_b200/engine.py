@@ -174,8 +174,20 @@ class Engine:
     def set_graph(self, enabled: bool):
         N.check(self.lib.b200_engine_set_graph(self.h, int(enabled)), "set_graph")
 
-    def set_mega(self, enabled: bool):
+    def set_mega(self, enabled):
+        """0/False: one kernel per phase; 1/True: k_mega (CUDA-core consumers); 2: k_mega_tc
+        (tcgen05 consumers); 3: k_mega_tc with a full 16-row activation operand."""
         N.check(self.lib.b200_engine_set_mega(self.h, int(enabled)), "set_mega")
+
+    def debug_buffer(self, name: str, dtype=torch.float32) -> torch.Tensor:
+        """Copy of an internal device buffer (tests / debugging only)."""
+        ptr, nbytes = C.c_void_p(), C.c_long()
+        N.check(self.lib.b200_engine_debug_buffer(self.h, name.encode(), C.byref(ptr), C.byref(nbytes)),
+                "debug_buffer")
+        out = self.empty((nbytes.value // torch.empty((), dtype=dtype).element_size(),), dtype)
+        N.check(self.lib.b200_memcpy_d2d(out.data_ptr(), ptr, nbytes.value, self.s), "memcpy_d2d")
+        self.stream.synchronize()
+        return out
 
     def device_error(self) -> int:
         v = C.c_int(0)

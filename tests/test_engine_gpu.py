@@ -212,6 +212,53 @@ def test_multi_kernel_decode_equals_megakernel():
         assert rl2(a, b) <= 1e-3
 
 
+@pytest.mark.parametrize("kind,mode", [("tiny", 2), ("wide2", 2), ("wide2", 3)])
+def test_tensor_core_megakernel_parity(kind, mode):
+    """k_mega_tc (decode_mega_tc.cu: tcgen05 GEMV phases on pre-packed weight tile images,
+    exact fixed-point split-K accumulation) against the oracle, teacher-forced, and against
+    k_mega on the same cache; the appended K/V rows of layer 0 must be bit-identical (same
+    inputs, one Linear + rotary, fp32 accumulation differences stay below one bf16 ulp almost
+    everywhere)."""
+    from mlx_vlm_b200.models.cache import make_prompt_cache
+    from oracle import qwen2vl as O
+    n_dec = 5
+    c, W, model, req = _build(kind, 16, (56, 56))
+    ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
+    eng = model.engine
+    ref = O.greedy_generate(c, W, ids, pv, grid, n_dec)
+    toks = ref["tokens"][0].tolist()
+    ex = O.greedy_generate(c, W, ids, pv, grid, n_dec, dtype="f32", force_tokens=toks[:])
+    pvd = torch.from_numpy(pv).cuda()
+    T = ids.shape[1]
+    delta = int(ref["prefill"].rope_deltas[0, 0])
+    got = {}
+    try:
+        for m in (1, mode):
+            eng.set_mega(m)
+            cache = make_prompt_cache(model.language_model)
+            emb = model.get_input_embeddings(ids, pvd, image_grid_thw=grid)
+            model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache,
+                                 position_ids=emb.position_ids, rope_deltas=emb.rope_deltas)
+            eng.set_next(toks[0], T, T + delta)
+            logs = []
+            for n in range(1, n_dec):
+                eng.decode(1, force_tokens=np.asarray([toks[n]], dtype=np.int32))
+                eng.stream.synchronize()
+                logs.append(eng.logits_view().float().cpu().clone())
+                if m == mode:
+                    cmp_noise(logs[-1], ref["logits"][n][0], ex["logits"][n][0],
+                              f"{kind} k_mega_tc (mode {mode}) decode step {n} logits")
+            assert eng.device_error() == 0, f"device error flag (mode {m})"
+            got[m] = (logs, cache[0].keys[0, :, T:T + n_dec - 1].float().cpu().clone(),
+                      cache[0].values[0, :, T:T + n_dec - 1].float().cpu().clone())
+    finally:
+        eng.set_mega(1)
+    for a, b in zip(got[1][0], got[mode][0]):
+        assert rl2(a, b) <= 2e-2, "k_mega_tc vs k_mega logits"
+    cmp_bf16(got[mode][1], got[1][1], f"{kind} appended K rows, layer 0", rel_l2=1e-3, max_mismatch=0.02)
+    cmp_bf16(got[mode][2], got[1][2], f"{kind} appended V rows, layer 0", rel_l2=1e-3, max_mismatch=0.02)
+
+
 def test_text_only_and_cache_reuse():
     """text-only request (qwen2_vl.py:34-42) + chunked prefill == one-shot prefill
     (reference tests/cache_invariants.py:47-115)."""

@@ -9,6 +9,8 @@ from mlx_vlm_b200.utils import load_synthetic, prepare_inputs
 model, proc = load_synthetic("qwen2-vl-2b", seed=0, device="cuda:0", n_text_tokens=128)
 eng = model.engine
 eng.set_graph(False)
+if len(sys.argv) > 1:
+    eng.set_mega(int(sys.argv[1]))  # 1: k_mega, 2: k_mega_tc
 N.check(eng.lib.b200_engine_mega_timeline(eng.h, 0))
 img = np.random.default_rng(0).integers(0, 256, size=(336, 336, 3), dtype=np.uint8)
 inp = prepare_inputs(proc, images=[img], prompts="x", device=eng.device, stream=eng.stream)
@@ -42,7 +44,7 @@ for cta in (0, 1):
     print("  layer 5 raw (compute, wait) us:", [(round(comp[25+k]/1e3,2), round(wait[25+k]/1e3,2)) for k in range(5)])
 
 for name, off in (("gateup CTA0", 4096), ("gateup CTA77", 4096 + 32), ("dres CTA0", 4096 + 64)):
-    t = raw[off:off + 30]
+    t = raw[off:off + 28]
     t = t[t > 0]
     if len(t) > 2:
         d = np.diff(t) / 1e3
@@ -62,3 +64,9 @@ for cta in (0, 1):
     t = raw[4096 + 128 + 32 * cta:4096 + 128 + 32 * cta + 12]; t = t[t > 0]
     if len(t) > 2:
         print(f"attention CTA{cta} (layer 5) step durations us:", list(zip(names[1:], [round(x / 1e3, 2) for x in np.diff(t)])))
+
+for name, off, labels in (("gateup prologue (k_mega_tc, CTA0 layer 5)", 4096 + 160, ["partials+residual", "cbar", "normalise+write", "fence.proxy.async", "cbar"]),
+                          ("down prologue (k_mega_tc, CTA0 layer 5)", 4096 + 176, ["load+write slice", "fence.proxy.async", "cbar"])):
+    t = raw[off:off + 8]; t = t[t > 0]
+    if len(t) > 2:
+        print(name, list(zip(labels, [round(x / 1e3, 2) for x in np.diff(t)])))
