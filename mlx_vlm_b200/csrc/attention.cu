@@ -8,6 +8,8 @@
 //
 // v1: CUDA-core FMA, one CTA per (16 query rows, head); K/V tiles are re-read
 // through L1 by the 8 warps of the CTA.  [round 2: HMMA/tcgen05 version]
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -129,11 +131,30 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
   }
 }
 
+// attention_tc.cu: the tensor-core kernel (default whenever the layout allows 16-byte tiles)
+bool attention_tc_supported(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
+                            const void* v, long v_ts, long v_hs, const void* out, long o_ts, int hd);
+int attention_tc(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
+                 const void* v, long v_ts, long v_hs, void* out, long o_ts, int n_heads, int n_kv,
+                 int hd, int Lq, int S, int causal, float scale, cudaStream_t st);
+
+static int g_attn_impl = -1;  // -1: read B200_ATTN_V1 once; 0: tensor cores; 1: CUDA-core v1
+void attention_set_impl(int v1) { g_attn_impl = v1 ? 1 : 0; }
+
 int attention(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
               const void* v, long v_ts, long v_hs, void* out, long o_ts, int n_heads, int n_kv,
               int hd, int Lq, int S, int causal, float scale, cudaStream_t st) {
   B200_REQUIRE(Lq > 0 && S > 0 && n_heads > 0 && n_kv > 0 && n_heads % n_kv == 0,
                "attention: bad shape Lq=%d S=%d heads=%d kv=%d", Lq, S, n_heads, n_kv);
+  B200_REQUIRE(!causal || S >= Lq, "attention: causal needs S >= Lq");
+  if (g_attn_impl < 0) {
+    const char* e = getenv("B200_ATTN_V1");
+    g_attn_impl = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (g_attn_impl == 0 &&
+      attention_tc_supported(q, q_ts, q_hs, k, k_ts, k_hs, v, v_ts, v_hs, out, o_ts, hd))
+    return attention_tc(q, q_ts, q_hs, k, k_ts, k_hs, v, v_ts, v_hs, out, o_ts, n_heads, n_kv, hd,
+                        Lq, S, causal, scale, st);
   B200_REQUIRE(hd % 8 == 0 && hd <= 128, "attention: head_dim %d unsupported (need %%8, <=128)", hd);
   B200_REQUIRE((k_ts % 8) == 0 && (k_hs % 8) == 0 && (v_ts % 2) == 0 && (v_hs % 2) == 0 &&
                    (o_ts % 2) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 3) == 0,
