@@ -2,16 +2,20 @@
 
 `import mlx_vlm_b200 as mlx_vlm` gives the reference's generate-path surface
 (reference mlx_vlm/__init__.py:7-20): load, generate, stream_generate,
-generate_step, prepare_inputs, GenerationResult, PromptCacheState.  The
+generate_step, batch_generate / BatchGenerator, prepare_inputs, GenerationResult,
+PromptCacheState.  The
 arithmetic lives in libb200vlm.so (hand-written sm_100a CUDA behind the C ABI of
 include/b200vlm.h); importing the package does not need a GPU, calling a model
 does (there is no CPU fallback).
 """
 from .generate import (GenerationResult, PromptCacheState, generate, generate_step,
                        stream_generate)
+from .generate_batch import (BatchGenerator, BatchResponse, BatchStats, GenerationBatch,
+                             PromptProgress, batch_generate)
 from .utils import load, load_synthetic, prepare_inputs, process_image
 from .version import __version__
 
-__all__ = ["GenerationResult", "PromptCacheState", "generate", "generate_step",
+__all__ = ["BatchGenerator", "BatchResponse", "BatchStats", "GenerationBatch", "PromptProgress",
+           "batch_generate", "GenerationResult", "PromptCacheState", "generate", "generate_step",
            "stream_generate", "load", "load_synthetic", "prepare_inputs", "process_image",
            "__version__"]

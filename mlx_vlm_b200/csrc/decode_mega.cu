@@ -36,12 +36,20 @@ __device__ __forceinline__ const bf16* mega_tile_src(const MegaPhase& g, const b
 template <int MODE>
 __device__ __forceinline__ void produce_phase(const MegaPhase& g, const bf16* W, const bf16* W2,
                                               int hd, uint8_t* ring, MegaShared* sh, Ring& rg,
-                                              uint64_t pol, long long* tdbg = nullptr) {
+                                              uint64_t pol, Ring& lag, int& issued, int max_inflight,
+                                              long long* tdbg = nullptr) {
   using T = PhTraits<MODE>;
   const int rows_unit = g.K * 2;
   int tn = 0;
   for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
     const int s = rg.slot();
+    if (max_inflight > 0) {  // in-flight throttle (see decode_mega_tc.cu::Producer)
+      if (issued >= max_inflight) {
+        mb_wait(&sh->full_bar[lag.slot()], lag.parity(), &sh->err);
+        lag.advance();
+      }
+      ++issued;
+    }
     mb_wait(&sh->empty_bar[s], rg.parity() ^ 1u, &sh->err);
     if (tdbg && tn < 30) tdbg[tn++] = gtimer();
     int rows = g.R;
@@ -366,6 +374,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     // ===== producer: the whole step's weight stream, never blocked by a phase =====
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
+      Ring lag = rg;
+      int issued = 0;
+      const int mif = p.max_inflight;
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerW& lw = p.layers[l];
         // the qkv/attention/o_proj chain is latency-bound (~20 us with ~11 MB of weights):
@@ -377,14 +388,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
           l2_prefetch_phase<PH_GATEUP>(p.ph[PH_GATEUP], lw.wgu, lw.wgu + (long)d.inter * d.hidden);
           l2_prefetch_phase<PH_DRES>(p.ph[PH_DRES], lw.wd, nullptr);
         }
-        produce_phase<PH_QKV>(p.ph[PH_QKV], lw.wqkv, nullptr, d.hd, ring, &sh, rg, pol);
-        produce_phase<PH_ORES>(p.ph[PH_ORES], lw.wo, nullptr, d.hd, ring, &sh, rg, pol);
+        produce_phase<PH_QKV>(p.ph[PH_QKV], lw.wqkv, nullptr, d.hd, ring, &sh, rg, pol, lag, issued, mif);
+        produce_phase<PH_ORES>(p.ph[PH_ORES], lw.wo, nullptr, d.hd, ring, &sh, rg, pol, lag, issued, mif);
         produce_phase<PH_GATEUP>(p.ph[PH_GATEUP], lw.wgu, lw.wgu + (long)d.inter * d.hidden, d.hd,
-                                 ring, &sh, rg, pol,
+                                 ring, &sh, rg, pol, lag, issued, mif,
                                  (p.dbg && l == 5 && blockIdx.x == 0) ? p.dbg + 4096 + 96 : nullptr);
-        produce_phase<PH_DRES>(p.ph[PH_DRES], lw.wd, nullptr, d.hd, ring, &sh, rg, pol);
+        produce_phase<PH_DRES>(p.ph[PH_DRES], lw.wd, nullptr, d.hd, ring, &sh, rg, pol, lag, issued, mif);
       }
-      produce_phase<PH_HEAD>(p.ph[PH_HEAD], p.head, nullptr, d.hd, ring, &sh, rg, pol);
+      produce_phase<PH_HEAD>(p.ph[PH_HEAD], p.head, nullptr, d.hd, ring, &sh, rg, pol, lag, issued, mif);
     }
     return;
   }

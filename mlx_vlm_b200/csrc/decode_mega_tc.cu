@@ -131,6 +131,22 @@ __device__ __forceinline__ void tc_produce(const MegaTcP& P, const MegaTcPhase& 
   }
 }
 
+// L2 prefetch of this CTA's tiles of a phase (fire and forget): issued at the start of a layer
+// for the MLP weights, so that the ring refills from L2 while the qkv / attention / o_proj
+// chain (latency-bound, ~12 % of the layer's bytes) would otherwise leave HBM idle
+__device__ __forceinline__ void tc_l2_prefetch(const MegaTcP& P, const MegaTcPhase& g,
+                                               const uint8_t* Wt) {
+  for (int u = blockIdx.x; u < g.units; u += gridDim.x) {
+    const TcUnit t = tc_unit(g, u);
+    for (int kb = t.kb0; kb < t.kb1; kb += P.sps) {
+      const int n = min(P.sps, t.kb1 - kb);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Wt + ((long)t.rb * g.KB + kb) * TC_SUB),
+                   "r"((uint32_t)n * TC_SUB)
+                   : "memory");
+    }
+  }
+}
+
 // ---- MMA issuer (one thread) ---------------------------------------------------------
 __device__ __forceinline__ void tc_mma(const MegaTcP& P, const MegaTcPhase& g, uint8_t* ring,
                                        const uint8_t* xop, TcShared* sh, Ring& rg,
@@ -466,6 +482,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_tc(const __grid_consta
       pr.issued = 0;
       for (int l = 0; l < p.n_layers; ++l) {
         const LayerWT& lt = P.lt[l];
+        if (p.l2_prefetch >= 1) tc_l2_prefetch(P, P.ph[PH_GATEUP], lt.wgu);
+        if (p.l2_prefetch >= 2) tc_l2_prefetch(P, P.ph[PH_DRES], lt.wd);
         tc_produce(P, P.ph[PH_QKV], lt.wqkv, ring, &sh, pr, pol);
         tc_produce(P, P.ph[PH_ORES], lt.wo, ring, &sh, pr, pol);
         tc_produce(P, P.ph[PH_GATEUP], lt.wgu, ring, &sh, pr, pol);

@@ -85,6 +85,7 @@ struct b200_engine {
   long tc_acc_rows = 0;
   int tc_alias = 1;
   int tc_inflight = 2;
+  int kv_keep = 0, fma_inflight = 0, l2_prefetch = 0;
   float* att_part = nullptr;
   float* att_stats = nullptr;
   unsigned long long* att_cnt = nullptr;
@@ -204,6 +205,10 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
   p.partials = e->partials; p.st = e->st; p.token_log = e->token_log; p.log_cap = e->log_cap;
   p.force = e->force; p.inv_freq = e->lm_inv_freq; p.bar = e->bar; p.advance = 1;
   p.dbg = e->dbg;
+  // tuning aids (defaults chosen from the sweeps recorded in profiles/)
+  p.kv_keep = e->kv_keep;
+  p.max_inflight = e->fma_inflight;
+  p.l2_prefetch = e->l2_prefetch;
   int rc;
   if (e->use_mega == 2) {
     // ---- tensor-core variant: tile images of the weights + split-K partial buffers ----
@@ -265,6 +270,7 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
   }
   rc = mega_fill(p, e->sm_count);
   if (rc) return rc;
+  if (p.max_inflight >= p.n_stages) p.max_inflight = p.n_stages - 1;  // a lagging slot must not be reused
   e->mega_ready = true;
   return B200_OK;
 }
@@ -728,7 +734,10 @@ int b200_engine_set_mega(b200_engine* e, int enabled) {
   B200_REQUIRE(enabled >= 0 && enabled <= 3, "set_mega: mode %d (0 off, 1 k_mega, 2 k_mega_tc, 3 k_mega_tc with a 16-row operand)", enabled);
   e->use_mega = enabled == 3 ? 2 : enabled;
   e->tc_alias = enabled == 3 ? 0 : 1;
-  if (const char* v = getenv("B200_TC_INFLIGHT")) e->tc_inflight = atoi(v) > 0 ? atoi(v) : 2;  // tuning aid
+  if (const char* v = getenv("B200_TC_INFLIGHT")) e->tc_inflight = atoi(v) > 0 ? atoi(v) : 2;  // tuning aids
+  if (const char* v = getenv("B200_KV_KEEP")) e->kv_keep = atoi(v);
+  if (const char* v = getenv("B200_FMA_INFLIGHT")) e->fma_inflight = atoi(v);
+  if (const char* v = getenv("B200_L2_PREFETCH")) e->l2_prefetch = atoi(v);
   invalidate_graph(e);
   return B200_OK;
 }

@@ -1,0 +1,391 @@
+"""Continuous batching surface of the reference (generate/ar.py: `BatchGenerator` :2178-2887,
+`GenerationBatch.Response` :937-944, `BatchStats` / `BatchResponse` / `PromptProgress` :863-914,
+`BatchGenerationResult` :519-545, `_left_pad_prompts` / `_right_pad_prompts` :548-560,
+`batch_generate` :2890-3097).
+
+How the rows run on the B200 engine (round 1): the decode engine is a batch-1 persistent
+kernel, so the rows of a batch are TIME-MULTIPLEXED: every request keeps its own KV pool
+(`models/cache.py::KVPool`) and the generator hands the engine to one row at a time for a
+slice of `decode_slice` greedy steps that run entirely on the device (token feedback through
+device memory); the tokens are buffered and surfaced one per `next()` call, exactly as a
+lock-step batch would.  Scheduling policy is the reference's: decode-first, then admit up to
+`prefill_batch_size` waiting prompts (shortest first) while fewer than
+`completion_batch_size` rows are active.  The rows are independent (own cache, own M-RoPE
+delta), which is also how requests are spread over GPUs (`parallel.shard_requests`).
+[round 2: the tcgen05 decode kernel (decode_mega_tc.cu) has 16 activation columns per
+weight tile; a lock-step batch of <= 16 rows costs one weight stream.]
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .models import cache as cache_mod
+
+DEFAULT_MAX_TOKENS = 256
+DEFAULT_COMPLETION_BATCH_SIZE = 32
+DEFAULT_PREFILL_BATCH_SIZE = 8
+
+
+def _host_buf(n: int) -> torch.Tensor:
+    t = torch.empty(n, dtype=torch.int32)
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def _left_pad_prompts(prompts, max_length=None):
+    """ar.py:548-553: rows right-aligned, zeros in front."""
+    if max_length is None:
+        max_length = max(len(p) for p in prompts)
+    return np.asarray([[0] * (max_length - len(p)) + list(p) for p in prompts])
+
+
+def _right_pad_prompts(prompts, max_length=None):
+    """ar.py:555-560."""
+    if max_length is None:
+        max_length = max(len(p) for p in prompts)
+    return np.asarray([list(p) + [0] * (max_length - len(p)) for p in prompts])
+
+
+@dataclass
+class BatchGenerationResult:
+    texts: List[str]
+    tokens: List[Optional[int]]
+    logprobs: List[Optional[List[float]]]
+    prompt_tokens: List[int]
+    generation_tokens: List[int]
+    total_tokens: List[int]
+    prompt_tps: List[float]
+    generation_tps: List[float]
+    peak_memory: float = 0.0
+    image_sizes: Optional[List[Tuple[int, int]]] = None
+
+
+@dataclass
+class BatchStats:
+    prompt_tokens: int = 0
+    prompt_tps: float = 0
+    prompt_time: float = 0
+    generation_tokens: int = 0
+    generation_tps: float = 0
+    generation_time: float = 0
+    peak_memory: float = 0
+
+
+@dataclass
+class BatchResponse:
+    texts: List[str]
+    stats: BatchStats
+    image_sizes: Optional[List[Tuple[int, int]]] = None
+
+
+@dataclass
+class PromptProgress:
+    uid: int
+    prompt_tokens: int
+    prompt_tps: float = 0.0
+    prompt_time: float = 0.0
+    cached_tokens: int = 0
+
+
+class GenerationBatch:
+    """Namespace parity: the reference nests the response type in GenerationBatch."""
+
+    @dataclass
+    class Response:
+        uid: int
+        token: int
+        token_logprob: float
+        finish_reason: Optional[str]
+        top_logprobs: Optional[List[Tuple[int, float]]] = None
+
+
+@dataclass
+class _Row:
+    uid: int
+    ids: List[int]
+    max_tokens: int
+    kwargs: Dict[str, Any]
+    cache: Optional[list] = None
+    delta: int = 0
+    n_tokens: int = 0          # tokens surfaced so far
+    n_decoded: int = 0         # tokens computed so far (>= n_tokens: the slice buffer)
+    last_token: int = -1       # last computed token (input of the next decode step)
+    buffer: List[Tuple[int, float]] = field(default_factory=list)
+    reserve: int = 0
+
+
+class BatchGenerator:
+    """`insert()` prompts (token-id lists), then call `next()` until `has_work` is False.
+
+    next() -> (prompt_responses: List[PromptProgress], generation_responses:
+    List[GenerationBatch.Response]) — one response per active row per call; a row's last
+    response carries finish_reason "stop" (EOS) or "length"."""
+
+    def __init__(self, model, processor, *, max_tokens: int = DEFAULT_MAX_TOKENS,
+                 stop_tokens: Optional[set] = None, sampler: Optional[Callable] = None,
+                 completion_batch_size: int = DEFAULT_COMPLETION_BATCH_SIZE,
+                 prefill_batch_size: int = DEFAULT_PREFILL_BATCH_SIZE,
+                 prefill_step_size: Optional[int] = None, compute_logprobs: bool = False,
+                 top_logprobs_k: int = 0, logits_processors=None, greedy_sampling: bool = False,
+                 decode_slice: int = 16, **unsupported):
+        for k in ("kv_bits", "kv_key_bits", "kv_value_bits", "draft_model", "apc_manager", "prompt_cache"):
+            if unsupported.pop(k, None) is not None:
+                raise NotImplementedError(f"BatchGenerator: `{k}` is outside the B200 hot-path scope")
+        if logits_processors:
+            raise NotImplementedError("BatchGenerator: logits processors run on the single-request path only")
+        if top_logprobs_k:
+            raise NotImplementedError("BatchGenerator: top_logprobs_k > 0 is not supported")
+        self.model, self.processor = model, processor
+        self.max_tokens = max_tokens
+        self.sampler = sampler
+        self.greedy_sampling = greedy_sampling or sampler is None or getattr(sampler, "is_greedy", False)
+        self.compute_logprobs = compute_logprobs
+        self.completion_batch_size = completion_batch_size
+        self.prefill_batch_size = prefill_batch_size
+        self.prefill_step_size = prefill_step_size
+        self.decode_slice = max(1, int(decode_slice))
+        self.tokenizer = processor.tokenizer if hasattr(processor, "tokenizer") else processor
+        from .utils import StoppingCriteria
+        if getattr(self.tokenizer, "stopping_criteria", None) is None:
+            eos = getattr(getattr(model, "config", None), "eos_token_id", None)
+            self.tokenizer.stopping_criteria = StoppingCriteria(eos if eos is not None else [], self.tokenizer)
+        if stop_tokens:
+            self.tokenizer.stopping_criteria.add_eos_token_ids(list(stop_tokens))
+        self.uid_count = 0
+        self._unprocessed_sequences: List[_Row] = []
+        self._active: List[_Row] = []
+        self._prompt_tokens_counter = 0
+        self._prompt_time_counter = 0.0
+        self._gen_tokens_counter = 0
+        self._gen_time_counter = 0.0
+
+    # ------------------------------------------------------------------ queueing
+    def insert(self, prompts, max_tokens: Union[List[int], int, None] = None,
+               prompt_kwargs: Optional[List[dict]] = None) -> List[int]:
+        if max_tokens is None or isinstance(max_tokens, int):
+            max_tokens = [max_tokens or self.max_tokens] * len(prompts)
+        if prompt_kwargs is None:
+            prompt_kwargs = [{} for _ in prompts]
+        if len(max_tokens) != len(prompts) or len(prompt_kwargs) != len(prompts):
+            raise ValueError("insert: max_tokens / prompt_kwargs must match the number of prompts")
+        uids = []
+        for p, m, kw in zip(prompts, max_tokens, prompt_kwargs):
+            ids = np.asarray(p.cpu() if isinstance(p, torch.Tensor) else p).reshape(-1).tolist()
+            self._unprocessed_sequences.append(_Row(self.uid_count, ids, int(m), dict(kw or {})))
+            uids.append(self.uid_count)
+            self.uid_count += 1
+        self._unprocessed_sequences.sort(key=lambda r: len(r.ids))  # shortest first (ar.py:2620-2623)
+        return uids
+
+    def remove(self, uid) -> bool:
+        for lst in (self._unprocessed_sequences, self._active):
+            for i, r in enumerate(lst):
+                if r.uid == uid:
+                    lst.pop(i)
+                    return True
+        return False
+
+    @property
+    def unprocessed_prompts(self):
+        return self._unprocessed_sequences
+
+    @property
+    def has_pending_prompts(self) -> bool:
+        return len(self._unprocessed_sequences) > 0
+
+    @property
+    def has_work(self) -> bool:
+        return bool(self._active) or bool(self._unprocessed_sequences)
+
+    @property
+    def active_uids(self) -> List[int]:
+        return [r.uid for r in self._active]
+
+    def stats(self) -> BatchStats:
+        s = BatchStats()
+        s.prompt_tokens = self._prompt_tokens_counter
+        s.prompt_time = self._prompt_time_counter
+        s.prompt_tps = s.prompt_tokens / s.prompt_time if s.prompt_time > 0 else 0
+        s.generation_tokens = self._gen_tokens_counter
+        s.generation_time = self._gen_time_counter
+        s.generation_tps = s.generation_tokens / s.generation_time if s.generation_time > 0 else 0
+        eng = getattr(self.model, "engine", None)
+        if eng is not None and torch.cuda.is_available():
+            s.peak_memory = torch.cuda.max_memory_allocated(eng.device) / 1e9
+        return s
+
+    def close(self):
+        self._active.clear()
+        self._unprocessed_sequences.clear()
+
+    # ------------------------------------------------------------------ device work
+    def _logprob_of(self, tok: int) -> float:
+        lp = self.model.engine.snapshot("logprobs")
+        return float(lp.view(-1)[tok].float().item())
+
+    def _prefill(self, row: _Row) -> PromptProgress:
+        """Embeddings + prefill for one row; the fused head + sampler leave the first token in
+        the engine's token log."""
+        model, lm, eng = self.model, self.model.language_model, self.model.engine
+        tic = time.perf_counter()
+        kw = dict(row.kwargs)
+        ids = np.asarray([row.ids])
+        emb = kw.pop("inputs_embeds", None)
+        pos, deltas = kw.pop("position_ids", None), kw.pop("rope_deltas", None)
+        if emb is None:
+            out = model.get_input_embeddings(ids, kw.pop("pixel_values", None), mask=kw.pop("mask", None), **kw)
+            emb, pos, deltas = out.inputs_embeds, out.position_ids, out.rope_deltas
+        row.cache = cache_mod.make_prompt_cache(lm)
+        T = emb.shape[1]
+        row.reserve = T + row.max_tokens + 1
+        row.delta = int(np.asarray(deltas).reshape(-1)[0]) if deltas is not None else 0
+        step = self.prefill_step_size
+        ids_left = ids
+        while step is not None and emb.shape[1] > step + 1:   # chunked prefill (ar.py:426-472)
+            lm(ids_left[:, :step], inputs_embeds=emb[:, :step], cache=row.cache, position_ids=pos,
+               rope_deltas=deltas, logits_to_keep=1, reserve_tokens=row.reserve)
+            emb, ids_left = emb[:, step:], ids_left[:, step:]
+        out = lm(ids_left, inputs_embeds=emb, cache=row.cache, position_ids=pos, rope_deltas=deltas,
+                 logits_to_keep=1, reserve_tokens=row.reserve)
+        if self.greedy_sampling:
+            host = _host_buf(1)
+            eng.fetch_tokens(eng.tokens_launched - 1, 1, host)
+            eng.stream.synchronize()
+            tok = int(host[0])
+            lp = self._logprob_of(tok) if self.compute_logprobs else 0.0
+        else:
+            tok, lp = self._sample(out.logits[:, -1, :])
+        row.last_token, row.n_decoded = tok, 1
+        row.buffer.append((tok, lp))
+        dt = time.perf_counter() - tic
+        self._prompt_tokens_counter += len(row.ids)
+        self._prompt_time_counter += dt
+        return PromptProgress(uid=row.uid, prompt_tokens=len(row.ids), prompt_time=dt,
+                              prompt_tps=len(row.ids) / dt if dt > 0 else 0.0)
+
+    def _sample(self, logits: torch.Tensor) -> Tuple[int, float]:
+        lf = logits.float()
+        logprobs = logits - torch.logsumexp(lf, dim=-1, keepdim=True).to(logits.dtype)
+        y = self.sampler(logprobs)
+        tok = int(y.reshape(-1)[0].item())
+        return tok, float(logprobs.reshape(-1)[tok].float().item())
+
+    def _decode_slice(self, row: _Row):
+        """Refill the row's token buffer: hand the engine to this row for up to `decode_slice`
+        steps (device-resident token feedback when greedy)."""
+        lm, eng = self.model.language_model, self.model.engine
+        left = row.max_tokens - row.n_decoded
+        if left <= 0:
+            return
+        ctx = int(row.cache[0].offset)
+        if self.greedy_sampling and not self.compute_logprobs:
+            k = min(self.decode_slice, left)
+            eng.set_next(row.last_token, ctx, ctx + row.delta)
+            base = eng.tokens_launched
+            lm.fused_greedy_decode(k, row.cache, reserve_tokens=row.reserve)
+            host = _host_buf(k)
+            eng.fetch_tokens(base, k, host)
+            eng.stream.synchronize()
+            toks = [int(t) for t in host.tolist()]
+            row.buffer.extend((t, 0.0) for t in toks)
+            row.last_token, row.n_decoded = toks[-1], row.n_decoded + k
+        else:
+            out = lm(np.asarray([[row.last_token]]), cache=row.cache,
+                     rope_deltas=np.asarray([[row.delta]]), reserve_tokens=row.reserve)
+            if self.greedy_sampling:
+                lp = eng.snapshot("logprobs").view(-1)
+                eng.stream.synchronize()
+                tok = int(torch.argmax(lp.float()).item())
+                lpv = float(lp[tok].float().item())
+            else:
+                tok, lpv = self._sample(out.logits[:, -1, :])
+            row.buffer.append((tok, lpv))
+            row.last_token, row.n_decoded = tok, row.n_decoded + 1
+
+    # ------------------------------------------------------------------ scheduling
+    def next(self, **kwargs):
+        prompt_responses: List[PromptProgress] = []
+        generation_responses: List[GenerationBatch.Response] = []
+        stop = self.tokenizer.stopping_criteria
+        # 1. decode-first: one token per active row
+        if self._active:
+            tic = time.perf_counter()
+            keep = []
+            for row in self._active:
+                if not row.buffer:
+                    self._decode_slice(row)
+                tok, lp = row.buffer.pop(0)
+                row.n_tokens += 1
+                finish = None
+                if stop(tok):
+                    finish = "stop"
+                elif row.n_tokens >= row.max_tokens:
+                    finish = "length"
+                generation_responses.append(GenerationBatch.Response(
+                    uid=row.uid, token=tok, token_logprob=lp, finish_reason=finish))
+                if finish is None:
+                    keep.append(row)
+            self._gen_tokens_counter += len(self._active)
+            self._gen_time_counter += time.perf_counter() - tic
+            self._active = keep
+        # 2. admit waiting prompts while there is room (shortest first)
+        room = self.completion_batch_size - len(self._active)
+        n_admit = min(room, self.prefill_batch_size, len(self._unprocessed_sequences))
+        for _ in range(max(0, n_admit)):
+            row = self._unprocessed_sequences.pop(0)
+            prompt_responses.append(self._prefill(row))
+            self._active.append(row)
+        return prompt_responses, generation_responses
+
+
+def batch_generate(model, processor, images=None, prompts: Optional[List[str]] = None,
+                   max_tokens: Union[int, List[int]] = 128, verbose: bool = False,
+                   resize_shape=None, **kwargs) -> BatchResponse:
+    """ar.py:2890-3097: one prompt (and optionally one image) per row -> texts in input order."""
+    from .generate import _make_detokenizer
+    from .utils import prepare_inputs
+    if prompts is None:
+        raise ValueError("batch_generate: prompts is required")
+    if isinstance(prompts, str):
+        prompts = [prompts]
+    if images is not None and not isinstance(images, (list, tuple)):
+        images = [images]
+    if images is not None and len(images) not in (0, len(prompts)):
+        raise ValueError("batch_generate: give one image per prompt (or none)")
+    eng = model.engine
+    gen = BatchGenerator(model, processor, max_tokens=max_tokens if isinstance(max_tokens, int) else DEFAULT_MAX_TOKENS,
+                         **kwargs)
+    ids_list, kw_list, sizes = [], [], []
+    for i, prompt in enumerate(prompts):
+        img = images[i] if images else None
+        inp = prepare_inputs(processor, images=[img] if img is not None else None, prompts=prompt,
+                             resize_shape=resize_shape, device=eng.device, stream=eng.stream)
+        ids_list.append(np.asarray(inp["input_ids"].cpu() if isinstance(inp["input_ids"], torch.Tensor)
+                                   else inp["input_ids"]).reshape(-1).tolist())
+        kw_list.append({k: v for k, v in inp.items() if k not in ("input_ids", "attention_mask") and v is not None})
+        if img is not None and hasattr(img, "shape"):
+            sizes.append((int(img.shape[0]), int(img.shape[1])))
+    uids = gen.insert(ids_list, max_tokens if not isinstance(max_tokens, int) else None, kw_list)
+    if isinstance(max_tokens, int):
+        for r in gen.unprocessed_prompts:
+            r.max_tokens = max_tokens
+    detok = {u: _make_detokenizer(processor) for u in uids}
+    stop = gen.tokenizer.stopping_criteria
+    while gen.has_work:
+        _, responses = gen.next()
+        for r in responses:
+            if not (r.finish_reason == "stop" and stop(r.token)):
+                detok[r.uid].add_token(r.token)
+    texts = []
+    for u in uids:
+        detok[u].finalize()
+        texts.append(detok[u].text)
+    stats = gen.stats()
+    if verbose:
+        print(f"Prompt: {stats.prompt_tokens} tokens, {stats.prompt_tps:.1f} tokens-per-sec")
+        print(f"Generation: {stats.generation_tokens} tokens, {stats.generation_tps:.1f} tokens-per-sec")
+    return BatchResponse(texts=texts, stats=stats, image_sizes=sizes or None)

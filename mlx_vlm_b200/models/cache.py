@@ -170,3 +170,210 @@ def make_prompt_cache(model: Any, max_kv_size: Optional[int] = None) -> List[Any
     if hasattr(model, "make_cache"):
         return model.make_cache()
     return [KVCache() for _ in range(len(model.layers))]
+
+
+def create_causal_mask(N: int, offset: int = 0, window_size: Optional[int] = None,
+                       left_padding=None) -> torch.Tensor:
+    """Boolean (…, N, offset+N) mask, True = attend (reference cache.py:24-42): query i (absolute
+    position offset+i) sees key j iff j <= offset+i, within `window_size` if given, and, per
+    row, j >= left_padding[row]."""
+    rinds = torch.arange(offset + N)
+    linds = torch.arange(offset, offset + N) if offset else rinds
+    linds, rinds = linds[:, None], rinds[None]
+    mask = linds >= rinds
+    if window_size is not None:
+        mask = mask & (linds < rinds + window_size)
+    if left_padding is not None:
+        lp = torch.as_tensor(left_padding).reshape(-1, 1, 1, 1)
+        mask = mask & (rinds >= lp)
+    return mask
+
+
+class BatchKVCache(_BaseCache):
+    """Left-padded batch of KV rows (reference cache.py:972-1201): rows of different lengths are
+    right-aligned at the shared write index `_idx`; `left_padding[b]` positions at the front of
+    row b are dead, `offset[b] = _idx - left_padding[b]` is the row's real length.
+
+    Host-side container with the reference's observable behaviour (merge / extract / filter /
+    extend / trim / state); the B200 engine decodes each row from its own `KVCache` pool
+    (`generate_batch.BatchGenerator`), this class is the interchange format."""
+    step = 256
+
+    def __init__(self, left_padding: List[int]):
+        self.keys: Optional[torch.Tensor] = None
+        self.values: Optional[torch.Tensor] = None
+        self.left_padding = torch.as_tensor(list(left_padding), dtype=torch.int64)
+        self.offset = -self.left_padding.clone()
+        self._idx = 0
+        self._right_padding: Optional[torch.Tensor] = None
+
+    # -- append ----------------------------------------------------------------
+    def update_and_fetch(self, keys: torch.Tensor, values: torch.Tensor):
+        L = keys.shape[2]
+        start, end = self._idx, self._idx + L
+        cap = 0 if self.keys is None else self.keys.shape[2]
+        if end > cap:
+            grow = ((L + self.step - 1) // self.step) * self.step
+            B, H, _, Dk = keys.shape
+            extra_k = torch.zeros((B, H, grow, Dk), dtype=keys.dtype, device=keys.device)
+            extra_v = torch.zeros((B, H, grow, values.shape[3]), dtype=values.dtype, device=values.device)
+            if self.keys is None:
+                self.keys, self.values = extra_k, extra_v
+            else:
+                live_k = self.keys if start % self.step == 0 else self.keys[..., :start, :]
+                live_v = self.values if start % self.step == 0 else self.values[..., :start, :]
+                self.keys = torch.cat([live_k, extra_k], dim=2)
+                self.values = torch.cat([live_v, extra_v], dim=2)
+        self.keys[..., start:end, :] = keys
+        self.values[..., start:end, :] = values
+        self.offset = self.offset + L
+        self._idx = end
+        return self.keys[..., :end, :], self.values[..., :end, :]
+
+    def prepare(self, *, left_padding=None, lengths=None, right_padding=None):
+        if left_padding is not None:
+            if self.keys is not None:
+                raise ValueError("Left padding can only be added to an empty BatchKVCache")
+            lp = torch.as_tensor(list(left_padding), dtype=torch.int64)
+            self.left_padding = self.left_padding + lp
+            self.offset = self.offset - lp
+        if right_padding is not None and max(right_padding) > 0:
+            self._right_padding = torch.as_tensor(list(right_padding), dtype=torch.int64)
+
+    def finalize(self):
+        """Turn right padding (rows shorter than the processed chunk) into left padding by
+        rotating each row to the right by its padding."""
+        if self._right_padding is None:
+            return
+        pad = self._right_padding
+        n = self.keys.shape[2]
+        idx = (torch.arange(n)[None, :] - pad[:, None]) % n           # (B, n)
+        gather = idx[:, None, :, None]
+        self.keys = torch.take_along_dim(self.keys, gather.to(self.keys.device), dim=2)
+        self.values = torch.take_along_dim(self.values, gather.to(self.values.device), dim=2)
+        self.offset = self.offset - pad
+        self.left_padding = self.left_padding + pad
+        self._right_padding = None
+
+    # -- reference attribute surface ----------------------------------------------
+    @property
+    def state(self):
+        k, v = self.keys, self.values
+        if k is not None and self._idx < k.shape[2]:
+            k, v = k[..., :self._idx, :], v[..., :self._idx, :]
+        return k, v, self.offset, self.left_padding
+
+    @state.setter
+    def state(self, v):
+        self.keys, self.values, self.offset, self.left_padding = v
+        self._idx = self.keys.shape[2]
+
+    def is_trimmable(self):
+        return True
+
+    def trim(self, n):
+        n = min(self._idx, n)
+        self._idx -= n
+        self.offset = self.offset - n
+        return n
+
+    def make_mask(self, N: int, return_array: bool = False, **kwargs):
+        return create_causal_mask(N, offset=self._idx, left_padding=self.left_padding, **kwargs)
+
+    def filter(self, batch_indices):
+        """Keep the given rows (in place); drop the padding no remaining row needs."""
+        sel = torch.as_tensor(batch_indices, dtype=torch.int64).reshape(-1)
+        if self.keys is not None:
+            self.keys = self.keys[sel.to(self.keys.device)]
+            self.values = self.values[sel.to(self.values.device)]
+        self.offset = self.offset[sel]
+        self.left_padding = self.left_padding[sel]
+        if self._right_padding is not None:
+            self._right_padding = self._right_padding[sel]
+        shift = int(self.left_padding.min()) if self.left_padding.numel() else 0
+        if shift > 0:
+            if self.keys is not None:
+                self.keys = self.keys[..., shift:, :]
+                self.values = self.values[..., shift:, :]
+            self._idx -= shift
+            self.left_padding = self.left_padding - shift
+
+    def extend(self, other: "BatchKVCache"):
+        """Append the rows of `other` (in place): both are right-aligned at the larger write index."""
+        if self.keys is None and other.keys is None:
+            self.left_padding = torch.cat([self.left_padding, other.left_padding])
+            self.offset = torch.cat([self.offset, other.offset])
+            return
+        ref = self.keys if self.keys is not None else other.keys
+        refv = self.values if self.values is not None else other.values
+        H, Dk, Dv = ref.shape[1], ref.shape[3], refv.shape[3]
+        new_idx = max(self._idx, other._idx)
+        size = max(0 if c.keys is None else c.keys.shape[2] for c in (self, other))
+
+        def aligned(c):
+            rows = int(c.offset.shape[0])
+            k = c.keys if c.keys is not None else torch.zeros((rows, H, 0, Dk), dtype=ref.dtype, device=ref.device)
+            v = c.values if c.values is not None else torch.zeros((rows, H, 0, Dv), dtype=refv.dtype, device=refv.device)
+            left = new_idx - c._idx
+            right = size - k.shape[2] - left
+            if right < 0:
+                k, v = k[..., :right, :], v[..., :right, :]
+                right = 0
+            if left or right:
+                k = torch.nn.functional.pad(k, (0, 0, left, right))
+                v = torch.nn.functional.pad(v, (0, 0, left, right))
+            return k, v, c.offset, c.left_padding + left
+
+        ka, va, oa, la = aligned(self)
+        kb, vb, ob, lb = aligned(other)
+        self.keys, self.values = torch.cat([ka, kb]), torch.cat([va, vb])
+        self.offset, self.left_padding = torch.cat([oa, ob]), torch.cat([la, lb])
+        self._idx = new_idx
+
+    def extract(self, idx: int) -> "KVCache":
+        pad = int(self.left_padding[idx])
+        out = KVCache()
+        out.update_and_fetch(self.keys[idx:idx + 1, :, pad:self._idx].contiguous(),
+                             self.values[idx:idx + 1, :, pad:self._idx].contiguous())
+        return out
+
+    @classmethod
+    def merge(cls, caches: List["KVCache"]) -> "BatchKVCache":
+        lengths = [int(c.size()) for c in caches]
+        longest = max(lengths)
+        if longest == 0:
+            return cls([0] * len(caches))
+        padding = [longest - n for n in lengths]
+        src = next(c for c in caches if c.keys is not None)
+        H, Dk, Dv = src.keys.shape[1], src.keys.shape[3], src.values.shape[3]
+        keys = torch.zeros((len(caches), H, longest, Dk), dtype=src.keys.dtype, device=src.keys.device)
+        values = torch.zeros((len(caches), H, longest, Dv), dtype=src.values.dtype, device=src.values.device)
+        for b, (pad, c, n) in enumerate(zip(padding, caches, lengths)):
+            if c.keys is None or n == 0:
+                continue
+            keys[b, :, pad:pad + n] = c.keys[0, :, :n]
+            values[b, :, pad:pad + n] = c.values[0, :, :n]
+        out = cls(padding)
+        out.keys, out.values = keys, values
+        out.offset = out.offset + longest
+        out._idx = longest
+        return out
+
+    def size(self):
+        return self._idx
+
+    def empty(self):
+        return self.keys is None
+
+    @property
+    def batch_size(self) -> int:
+        return int(self.keys.shape[0]) if self.keys is not None else int(self.left_padding.shape[0])
+
+    def is_single_row(self) -> bool:
+        return self.batch_size == 1
+
+    @property
+    def nbytes(self):
+        if self.keys is None:
+            return 0
+        return self.keys.numel() * self.keys.element_size() + self.values.numel() * self.values.element_size()

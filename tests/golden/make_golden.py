@@ -40,6 +40,24 @@ def make_mx():
     mx.int32, mx.int64, mx.float32, mx.bool_ = np.int32, np.int64, np.float32, np.bool_
     mx.eval = lambda *a, **k: None
     mx.contiguous = np.ascontiguousarray
+    # ops used by the samplers / BatchKVCache (still pure numpy, nothing re-implemented)
+    for name in ("argsort", "take_along_axis", "exp", "abs", "argpartition", "std", "log"):
+        setattr(mx, name, getattr(np, name))
+    mx.max = lambda a, axis=None, keepdims=False: np.max(a, axis=axis, keepdims=keepdims)
+    mx.sum = lambda a, axis=None, keepdims=False: np.sum(a, axis=axis, keepdims=keepdims)
+    mx.std = lambda a, axis=None, keepdims=False: np.std(a, axis=axis, keepdims=keepdims)
+    mx.inf = np.inf
+
+    def put_along_axis(a, idx, vals, axis):  # mlx returns a new array
+        out = np.array(a, copy=True)
+        np.put_along_axis(out, idx, vals, axis=axis)
+        return out
+    mx.put_along_axis = put_along_axis
+
+    def softmax(x, axis=-1):
+        z = np.exp(x - np.max(x, axis=axis, keepdims=True))
+        return z / np.sum(z, axis=axis, keepdims=True)
+    mx.softmax = softmax
 
     def compile_(fn=None, **kw):
         return fn if fn is not None else (lambda f: f)
@@ -217,6 +235,79 @@ def main():
     trace.append({"trim": 7, "trimmed": int(n), "offset": int(c.offset),
                   "state_len": int(c.state[0].shape[2])})
     golden["KVCache_trace"] = trace
+
+    # ---------------- BatchKVCache bookkeeping (cache.py:972-1201) + prompt padding (ar.py:548-560)
+    ns["List"] = list
+    code, w = extract("models/cache.py", "dynamic_roll")
+    exec(compile(code, "<ref dynamic_roll>", "exec"), ns)
+    ns["_BaseCache"] = object
+    code, w = extract("models/cache.py", "BatchKVCache")
+    exec(compile(code, "<ref BatchKVCache>", "exec"), ns)
+    provenance["BatchKVCache"] = w
+    KV, BKV = ns["KVCache"], ns["BatchKVCache"]
+
+    def filled(n, base):  # a KVCache holding n positions with recognisable values
+        c = KV()
+        if n:
+            kk = (base + np.arange(n, dtype=np.float32)).reshape(1, 1, n, 1) * np.ones((1, 2, 1, 2), np.float32)
+            c.update_and_fetch(mx.array(kk), mx.array(-kk))
+        return c
+
+    def snap(c, tag):
+        k = None if c.keys is None else tolist(np.asarray(c.keys)[..., : c._idx, :])
+        v = None if c.values is None else tolist(np.asarray(c.values)[..., : c._idx, :])
+        return {"op": tag, "left_padding": tolist(c.left_padding), "offset": tolist(c.offset),
+                "idx": int(c._idx), "keys": k, "values": v}
+
+    btrace = []
+    b1 = BKV.merge([filled(5, 100), filled(2, 200), filled(7, 300)])
+    btrace.append(snap(b1, "merge lengths 5,2,7"))
+    step = (900 + np.arange(3, dtype=np.float32)).reshape(3, 1, 1, 1) * np.ones((1, 2, 1, 2), np.float32)
+    b1.update_and_fetch(mx.array(step), mx.array(-step))
+    btrace.append(snap(b1, "append one position"))
+    ex = b1.extract(1)
+    btrace.append({"op": "extract row 1", "offset": int(ex.offset), "keys": tolist(np.asarray(ex.keys)[..., : ex.offset, :])})
+    b1.filter(mx.array([0, 1]))
+    btrace.append(snap(b1, "filter keep rows 0,1 (drops the longest: shifts left)"))
+    b2 = BKV.merge([filled(3, 400)])
+    b1.extend(b2)
+    btrace.append(snap(b1, "extend with a 1-row cache of length 3"))
+    n = b1.trim(2)
+    btrace.append(snap(b1, f"trim 2 (trimmed {int(n)})"))
+    b3 = BKV([1, 3, 0])
+    btrace.append(snap(b3, "constructor left_padding [1,3,0]"))
+    golden["BatchKVCache_trace"] = btrace
+    golden["causal_mask_left_padding"] = [
+        {"N": n_, "offset": o, "left_padding": lp,
+         "mask": tolist(ccm(n_, o, left_padding=mx.array(lp)).astype(np.int32))}
+        for n_, o, lp in ((3, 0, [0, 2]), (1, 4, [1, 0, 3]))]
+    lp_fn, w = load(ns, "generate/ar.py", "_left_pad_prompts")
+    rp_fn, _ = load(ns, "generate/ar.py", "_right_pad_prompts")
+    provenance["_left_pad_prompts"] = w
+    prompts = [[1, 3, 5], [7], [2, 6, 8, 9]]
+    golden["pad_prompts"] = {"prompts": prompts, "left": tolist(lp_fn(prompts)), "right": tolist(rp_fn(prompts)),
+                             "left_max6": tolist(lp_fn(prompts, 6))}
+
+    # ---------------- sampler masks (sample_utils.py:149-345), fp32 on seeded logprobs
+    ns["math"] = __import__("math")
+    samp = {}
+    lg = rng.standard_normal((2, 12)).astype(np.float32) * 2.0
+    lp_ = lg - np.log(np.sum(np.exp(lg), axis=-1, keepdims=True))
+    samp["logits"], samp["logprobs"] = tolist(lg), tolist(lp_)
+    f, w = load(ns, "sample_utils.py", "_apply_top_k"); provenance["_apply_top_k"] = w
+    samp["top_k_3"] = tolist(f(mx.array(lp_), 3))
+    f, w = load(ns, "sample_utils.py", "apply_top_p"); provenance["apply_top_p"] = w
+    samp["top_p_0.7"] = tolist(f(mx.array(lp_), 0.7))
+    f, w = load(ns, "sample_utils.py", "_apply_min_p"); provenance["_apply_min_p"] = w
+    samp["min_p_0.2"] = tolist(f(mx.array(lp_), 0.2, 1))
+    samp["min_p_0.6_keep3"] = tolist(f(mx.array(lp_), 0.6, 3))
+    f, w = load(ns, "sample_utils.py", "_top_n_sigma"); provenance["_top_n_sigma"] = w
+    samp["top_n_sigma_1.0"] = tolist(f(mx.array(lg), 1.0))
+    f, w = load(ns, "sample_utils.py", "apply_p_less"); provenance["apply_p_less"] = w
+    samp["p_less_t0.8"] = tolist(f(mx.array(lg), 0.8))
+    f, w = load(ns, "sample_utils.py", "_typical_p"); provenance["_typical_p"] = w
+    samp["typical_p_0.6"] = tolist(f(mx.array(lp_), 0.6))
+    golden["sampler_masks"] = json.loads(json.dumps(samp).replace("-Infinity", '"-inf"'))
 
     with open(OUT, "w") as f:
         json.dump(golden, f)

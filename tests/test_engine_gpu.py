@@ -259,6 +259,41 @@ def test_tensor_core_megakernel_parity(kind, mode):
     cmp_bf16(got[mode][2], got[1][2], f"{kind} appended V rows, layer 0", rel_l2=1e-3, max_mismatch=0.02)
 
 
+def test_batch_generator_rows_equal_single_requests():
+    """Continuous batching on the real engine: three requests (two with an
+    image, different lengths / max_tokens) time-multiplexed through BatchGenerator produce
+    exactly the tokens each produces alone through generate_step."""
+    import types
+    from mlx_vlm_b200.generate import generate_step
+    from mlx_vlm_b200.generate_batch import BatchGenerator
+    c, W, model, req = _build("tiny", 10, (56, 56))
+    ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
+    pvd = torch.from_numpy(pv).cuda()
+    rng = np.random.default_rng(3)
+    text_ids = rng.integers(0, 900, size=(1, 23))
+    rows = [(ids, {"pixel_values": pvd, "image_grid_thw": grid}, 9),
+            (text_ids, {}, 14),
+            (ids[:, :ids.shape[1]], {"pixel_values": pvd, "image_grid_thw": grid}, 5)]
+    want = []
+    for r_ids, kw, m in rows:
+        toks = [t for t, _ in generate_step(r_ids, model, kw.get("pixel_values"), None, max_tokens=m,
+                                            image_grid_thw=kw.get("image_grid_thw"))]
+        want.append(toks)
+    model.config.eos_token_id = []
+    proc = types.SimpleNamespace(tokenizer=types.SimpleNamespace(stopping_criteria=None))
+    for slice_ in (1, 4):
+        g = BatchGenerator(model, proc, completion_batch_size=2, prefill_batch_size=2, decode_slice=slice_)
+        uids = g.insert([r[0] for r in rows], [r[2] for r in rows], [r[1] for r in rows])
+        got = {u: [] for u in uids}
+        while g.has_work:
+            _, rs = g.next()
+            for r in rs:
+                got[r.uid].append(r.token)
+        assert model.engine.device_error() == 0
+        for u, w in zip(uids, want):
+            assert got[u] == w, (slice_, u, got[u], w)
+
+
 def test_text_only_and_cache_reuse():
     """text-only request (qwen2_vl.py:34-42) + chunked prefill == one-shot prefill
     (reference tests/cache_invariants.py:47-115)."""
