@@ -60,7 +60,6 @@ struct MegaP {
   unsigned long long* bar;  // monotonic grid-barrier counter
   int advance;
   int l2_prefetch;
-  int kv_keep;        // K/V cache loads carry an L2 evict_last policy
   int max_inflight;   // k_mega: weight tiles requested but not landed per SM (0: no limit)
   float* att_part;  // [groups][8 units][4*hd] fp32 partial attention outputs
   unsigned long long* att_cnt;  // [groups] monotonic arrival counters

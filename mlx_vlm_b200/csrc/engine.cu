@@ -85,7 +85,7 @@ struct b200_engine {
   long tc_acc_rows = 0;
   int tc_alias = 1;
   int tc_inflight = 2;
-  int kv_keep = 0, fma_inflight = 0, l2_prefetch = 0;
+  int fma_inflight = 0, l2_prefetch = 0;
   float* att_part = nullptr;
   float* att_stats = nullptr;
   unsigned long long* att_cnt = nullptr;
@@ -206,7 +206,6 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
   p.force = e->force; p.inv_freq = e->lm_inv_freq; p.bar = e->bar; p.advance = 1;
   p.dbg = e->dbg;
   // tuning aids (defaults chosen from the sweeps recorded in profiles/)
-  p.kv_keep = e->kv_keep;
   p.max_inflight = e->fma_inflight;
   p.l2_prefetch = e->l2_prefetch;
   int rc;
@@ -735,7 +734,6 @@ int b200_engine_set_mega(b200_engine* e, int enabled) {
   e->use_mega = enabled == 3 ? 2 : enabled;
   e->tc_alias = enabled == 3 ? 0 : 1;
   if (const char* v = getenv("B200_TC_INFLIGHT")) e->tc_inflight = atoi(v) > 0 ? atoi(v) : 2;  // tuning aids
-  if (const char* v = getenv("B200_KV_KEEP")) e->kv_keep = atoi(v);
   if (const char* v = getenv("B200_FMA_INFLIGHT")) e->fma_inflight = atoi(v);
   if (const char* v = getenv("B200_L2_PREFETCH")) e->l2_prefetch = atoi(v);
   invalidate_graph(e);

@@ -59,33 +59,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 __device__ __forceinline__ uint4 ldcg16(const void* p) {
   return __ldcg(reinterpret_cast<const uint4*>(p));
 }
-// K/V cache rows: keep them L2-resident across steps (the weight stream is evict_first, so
-// ~15 MB of cache can survive 3 GB of weights per token); kvpol == 0: plain ld.cg
-__device__ __forceinline__ uint64_t policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint4 ldkv16(const void* p, uint64_t pol) {
-  if (pol == 0) return __ldcg(reinterpret_cast<const uint4*>(p));
-  uint4 r;
-  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p), "l"(pol));
-  return r;
-}
-__device__ __forceinline__ uint2 ldkv8(const void* p, uint64_t pol) {
-  if (pol == 0) return __ldcg(reinterpret_cast<const uint2*>(p));
-  uint2 r;
-  asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
-  return r;
-}
-__device__ __forceinline__ uint32_t ldkv4(const void* p, uint64_t pol) {
-  if (pol == 0) return __ldcg(reinterpret_cast<const uint32_t*>(p));
-  uint32_t r;
-  asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
-  return r;
-}
 __device__ __forceinline__ float ldcg_bf(const bf16* p) {
   return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p)) << 16);
 }
@@ -224,7 +197,6 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
   float* kn = qs + (long)AG * HD;                          //        [HD] new key
   float* vn = kn + HD;                                     //        [HD] new value
   const int seg = lane & 7, ksub = lane >> 3;
-  const uint64_t kvpol = p.kv_keep ? policy_evict_last() : 0ull;
   // ---- all global requests of the phase are issued before the first use: q, the first
   // 2 x 4 keys of this warp, and the V rows of its first VPRE keys (one round trip) ----
   constexpr int VPRE = 8;
@@ -245,7 +217,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
       const int j = j0 + 32 * q + ksub;
 #pragma unroll
       for (int v = 0; v < NV; ++v)
-        kvn[q][v] = (j < u1g) ? ldkv16(kb + (long)j * HD + seg * SEG + v * 8, kvpol) : make_uint4(0, 0, 0, 0);
+        kvn[q][v] = (j < u1g) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8) : make_uint4(0, 0, 0, 0);
     }
   }
   uint2 vraw[VPRE];
@@ -255,8 +227,8 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
     vraw[q] = make_uint2(0, 0);
     if (j < u1g) {
       const bf16* vr = vb + (long)j * HD + lane * EPL;
-      if (EPL == 4) vraw[q] = ldkv8(vr, kvpol);
-      else vraw[q].x = ldkv4(vr, kvpol);
+      if (EPL == 4) vraw[q] = __ldcg(reinterpret_cast<const uint2*>(vr));
+      else vraw[q].x = __ldcg(reinterpret_cast<const uint32_t*>(vr));
     }
   }
   float qr[AG][SEG];
@@ -328,7 +300,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
         const int j = j0 + 32 * UNR + 32 * q + ksub;
 #pragma unroll
         for (int v = 0; v < NV; ++v)
-          kvn[q][v] = (j < u1g) ? ldkv16(kb + (long)j * HD + seg * SEG + v * 8, kvpol)
+          kvn[q][v] = (j < u1g) ? ldcg16(kb + (long)j * HD + seg * SEG + v * 8)
                                 : make_uint4(0, 0, 0, 0);
       }
     }
@@ -504,11 +476,11 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
         const bf16* vr = vb + (long)j * HD + lane * EPL;
         if (EPL == 4) {
           float t4[4];
-          unpack4(ldkv8(vr, kvpol), t4);
+          unpack4(__ldcg(reinterpret_cast<const uint2*>(vr)), t4);
 #pragma unroll
           for (int e = 0; e < EPL; ++e) vf[q][e] = t4[e];
         } else {
-          const uint32_t w = ldkv4(vr, kvpol);
+          const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(vr));
           vf[q][0] = __uint_as_float(w << 16);
           vf[q][EPL - 1] = __uint_as_float(w & 0xffff0000u);
         }
