@@ -63,7 +63,7 @@ struct MegaP {
   int max_inflight;   // k_mega: weight tiles requested but not landed per SM (0: no limit)
   float* att_part;  // [groups][8 units][4*hd] fp32 partial attention outputs
   unsigned long long* att_cnt;  // [groups] monotonic arrival counters
-  float* att_stats; // [groups][8 units][4] (max, sum exp) pairs
+  float* att_stats; // [groups][8 units][4 heads] x 2 words {float bits << 32 | epoch}: (max, sum exp)
   long long* dbg;  // optional [2][1024][2] globaltimer stamps (arrive, release) per barrier
 };
 int mega_fill(MegaP& p, int sm_count);

@@ -186,7 +186,8 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
     B200_CUDA(cudaMalloc(&e->att_part, part));
     B200_CUDA(cudaMalloc(&e->att_cnt, 64 * sizeof(unsigned long long)));
     B200_CUDA(cudaMemset(e->att_cnt, 0, 64 * sizeof(unsigned long long)));
-    B200_CUDA(cudaMalloc(&e->att_stats, (size_t)64 * 8 * 4 * sizeof(float2)));
+    B200_CUDA(cudaMalloc(&e->att_stats, (size_t)64 * 8 * 4 * 16));  // {value, epoch} word pairs
+    B200_CUDA(cudaMemset(e->att_stats, 0, (size_t)64 * 8 * 4 * 16));
   }
   MegaP& p = e->mp;
   memset(&p, 0, sizeof(p));

@@ -386,46 +386,53 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
   }
   cbar();
   ATT_STAMP();  // local stats done
-  // ---- 2. publish the local statistics, group barrier ----
-  float2* gstats = reinterpret_cast<float2*>(p.att_stats) + (long)grp * ATT_UN * AG;
-  if (threadIdx.x < AG) {
-    float l = 0.f;
+  // ---- 2 + 3. exchange the softmax statistics inside the group WITHOUT a counter: every
+  // (unit, head) pair is published as two self-validating 8-byte words {float bits, epoch}
+  // (8-byte accesses are single-copy atomic; the epoch changes every attention phase), and
+  // ONE warp (lane = u*AG + g) polls the 32 pairs directly.  This replaces
+  // store + atomic arrive + counter poll + stats load (3 dependent L2 round trips) by
+  // store + poll (round 1: 750 -> 897 tok/s came from shortening this chain).
+  {
+    static_assert(ATT_UN * MEGA_ATT_G == 32, "one lane per (unit, head)");
+    unsigned long long* gw = reinterpret_cast<unsigned long long*>(p.att_stats) + (long)grp * ATT_UN * AG * 2;
+    const uint32_t epoch = (uint32_t)(sh->att_base + (unsigned long long)layer + 1ull);
+    if (warp == 0) {
+      if (lane < AG) {
+        float l = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) l += sh->s_l[w][threadIdx.x];
-    gstats[unit * AG + threadIdx.x] = make_float2(ml[threadIdx.x], (u1 > u0) ? l : 0.f);
-  }
-  cbar();
-  if (threadIdx.x == 0) {
-    const unsigned long long target = (sh->att_base + (unsigned long long)layer + 1ull) * ATT_UN;
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&p.att_cnt[grp]), "l"(1ull)
-                 : "memory");
-    unsigned spins = 0;
-    while (ld_acquire_u64(&p.att_cnt[grp]) < target) {
-      if (++spins > (1u << 22)) {
-        sh->err = 3;
-        break;
+        for (int w = 0; w < 8; ++w) l += sh->s_l[w][lane];
+        const float lv = (u1 > u0) ? l : 0.f;
+        const unsigned long long wm = ((unsigned long long)__float_as_uint(ml[lane]) << 32) | epoch;
+        const unsigned long long wl = ((unsigned long long)__float_as_uint(lv) << 32) | epoch;
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(gw + (long)(unit * AG + lane) * 2),
+                     "l"(wm), "l"(wl)
+                     : "memory");
+      }
+      unsigned long long a, b;
+      unsigned spins = 0;
+      do {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(gw + (long)lane * 2) : "memory");
+        if (++spins > (1u << 22)) {
+          sh->err = 3;
+          break;
+        }
+      } while ((uint32_t)a != epoch || (uint32_t)b != epoch);
+      const float sx = __uint_as_float((uint32_t)(a >> 32)), sy = __uint_as_float((uint32_t)(b >> 32));
+      // max / rescaled sum over the units of head g = lane % AG: butterfly over the unit bits
+      float m = sx;
+#pragma unroll
+      for (int o = AG; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float l = (sy > 0.f) ? sy * expf(sx - m) : 0.f;
+#pragma unroll
+      for (int o = AG; o < 32; o <<= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      if (lane < AG) {
+        sh->s_m[0][lane] = m;
+        sh->s_l[0][lane] = l;
       }
     }
   }
   cbar();
-  ATT_STAMP();  // group barrier passed
-  // ---- 3. global statistics: ONE warp reads the ATT_UN x AG pairs (lane = u*AG + g) ----
-  if (warp == 0) {
-    static_assert(ATT_UN * MEGA_ATT_G == 32, "one lane per (unit, head)");
-    const float2 stv = __ldcg(&gstats[lane]);
-    // max / rescaled sum over the units of head g = lane % AG: butterfly over the unit bits
-    float m = stv.x;
-#pragma unroll
-    for (int o = AG; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float l = (stv.y > 0.f) ? stv.y * expf(stv.x - m) : 0.f;
-#pragma unroll
-    for (int o = AG; o < 32; o <<= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-    if (lane < AG) {
-      sh->s_m[0][lane] = m;
-      sh->s_l[0][lane] = l;
-    }
-  }
-  cbar();
+  ATT_STAMP();  // statistics exchanged
   float M[AG], L[AG];
 #pragma unroll
   for (int g = 0; g < AG; ++g) {
