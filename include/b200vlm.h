@@ -190,7 +190,9 @@ int b200_engine_set_graph(b200_engine* e, int enabled);
  * 1: ONE persistent kernel, CUDA-core GEMV consumers (k_mega: weight ring + software grid
  * barrier); 2: the same step with tcgen05 GEMV consumers on pre-packed tile images of
  * the weights (k_mega_tc; the engine allocates the packed copy on first use);
- * 3: as 2 with a full 16-row activation operand (debugging). */
+ * 3: as 2 with a full 16-row activation operand (debugging);
+ * 4: k_mega in dataflow mode (three of the five per-layer grid barriers replaced by polling
+ *    self-validating activation words; measured slower than 1, kept for A/B). */
 int b200_engine_set_mega(b200_engine* e, int enabled);
 /* debugging / test aid: device pointer and size of an internal buffer.  names: "h", "act",
  * "tc_acc" (k_mega_tc fixed-point split-K accumulators, 3 x rows int64). */

@@ -61,6 +61,10 @@ struct MegaP {
   int advance;
   int l2_prefetch;
   int max_inflight;   // k_mega: weight tiles requested but not landed per SM (0: no limit)
+  int flow;           // k_mega dataflow mode: 3 of the 5 per-layer grid barriers become polled words
+  int scratch_bytes;  // attention scratch / activation vector region after the ring
+  unsigned long long *hmid_w, *hout_w;  // residual stream after o_proj / after down, one word per element
+  unsigned long long* qkv_w;            // finished q/k/v pairs [head slot][hd/2]
   float* att_part;  // [groups][8 units][4*hd] fp32 partial attention outputs
   unsigned long long* att_cnt;  // [groups] monotonic arrival counters
   float* att_stats; // [groups][8 units][4 heads] x 2 words {float bits << 32 | epoch}: (max, sum exp)

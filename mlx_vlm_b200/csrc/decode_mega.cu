@@ -91,9 +91,15 @@ struct PhaseIO {
   bf16 *kc, *vc;     // QKV
   float2* partials;  // HEAD
   const float* xpart;  // ORES: partial attention outputs to be summed (instead of x)
+  // dataflow mode: activations cross CTAs as self-validating words (mega_common.cuh::st_word)
+  const unsigned long long* xw;  // input vector, one word per element (nullptr: plain io.x)
+  unsigned long long* outw;      // ORES / DRES: output h, one word per element
+  unsigned long long* qkvw;      // QKV: finished (dim j, dim j + hd/2) pairs [head slot][hd/2]
+  uint16_t* hraw;                // shared-memory copy of the un-normalised residual stream
+  uint32_t epoch, epoch_in;      // tag written by this phase / tag of the words it reads
 };
 
-template <int MODE, int CHX>
+template <int MODE, int CHX, bool FLOW>
 __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g, const PhaseIO& io,
                                               uint8_t* ring, uint8_t* xs_raw, MegaShared* sh,
                                               Ring& rg, int ctx, int pos,
@@ -115,7 +121,7 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
     float ss = 0.f;
     for (int c = threadIdx.x; c < nvec; c += 256) {
       uint4 v;
-      if (MODE == PH_ORES && io.xpart) {
+      if ((MODE == PH_ORES || MODE == PH_DRES) && io.xpart) {
         // x = bf16( sum over the ATT_UN key ranges of the partial attention outputs )
         const DecodeDims& d = p.d;
         const int d0 = c * 8, h = d0 / d.hd, Gall = d.n_heads / d.n_kv, G = Gall / p.hsplit;
@@ -137,10 +143,13 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
         v.y = pack2(sa.z, sa.w);
         v.z = pack2(sb.x, sb.y);
         v.w = pack2(sb.z, sb.w);
+      } else if (FLOW && io.xw) {
+        v = poll8(io.xw + (long)c * 8, io.epoch_in, &sh->err);
       } else {
         v = ldcg16(io.x + (long)c * 8);
       }
       xs[c] = v;
+      if (FLOW && T::NORM && MODE != PH_HEAD) reinterpret_cast<uint4*>(io.hraw)[c] = v;
       if (T::NORM) {
         float f[8];
         unpack8(v, f);
@@ -182,7 +191,7 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
   float run_m = -INFINITY, run_l = 0.f;
   // epilogue operands fetched BEFORE the tiles are waited for (off the critical path)
   float hpre = 0.f;  // ORES/DRES: lane i holds the residual value of this warp's i-th tile
-  if ((MODE == PH_ORES || MODE == PH_DRES) && sub == 0) {
+  if (!FLOW && (MODE == PH_ORES || MODE == PH_DRES) && sub == 0) {
     const int t = blockIdx.x + lane * gridDim.x;
     const int r = t * g.R + rloc;
     if (t < g.tiles && r < g.N) hpre = ldcg_bf(io.out + r);
@@ -216,16 +225,20 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
           bf16* dst = io.vc + ((long)(slot - p.d.n_heads - p.d.n_kv) * p.d.cap + ctx) * hd;
           dst[j] = f2bf(y1);
           dst[j + half] = f2bf(y2);
+          if (FLOW) st_word(io.qkvw + (long)slot * half + j, bf_bits(y1) | (bf_bits(y2) << 16), io.epoch);
         } else {
           const float ang = (float)pos * (ti == 0 ? pc : p.inv_freq[j]);
           const float c = rbf(cosf(ang)), sn = rbf(sinf(ang));
           const float o1 = rbf(rbf(y1 * c) + rbf((-y2) * sn));
           const float o2 = rbf(rbf(y2 * c) + rbf(y1 * sn));
-          bf16* dst = (slot < p.d.n_heads)
-                          ? io.out + (long)slot * hd
-                          : io.kc + ((long)(slot - p.d.n_heads) * p.d.cap + ctx) * hd;
-          dst[j] = f2bf(o1);
-          dst[j + half] = f2bf(o2);
+          if (FLOW) st_word(io.qkvw + (long)slot * half + j, bf_bits(o1) | (bf_bits(o2) << 16), io.epoch);
+          if (!FLOW || slot >= p.d.n_heads) {  // dataflow mode: q travels in the words only
+            bf16* dst = (slot < p.d.n_heads)
+                            ? io.out + (long)slot * hd
+                            : io.kc + ((long)(slot - p.d.n_heads) * p.d.cap + ctx) * hd;
+            dst[j] = f2bf(o1);
+            dst[j + half] = f2bf(o2);
+          }
         }
       }
     } else if (MODE == PH_GATEUP) {
@@ -233,8 +246,13 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
     } else if (MODE == PH_ORES || MODE == PH_DRES) {
       if (mine) {
         const int r = t * g.R + rloc;
-        const float hv = (it0 == 0) ? hpre : ldcg_bf(io.out + r);  // lane i prefetched tile i
-        io.out[r] = f2bf(rbf(hv + rbf(keep0)));
+        if (FLOW) {  // residual from the CTA's own copy of the stream; result as a tagged word
+          const float hv = __uint_as_float((uint32_t)io.hraw[r] << 16);
+          st_word(io.outw + r, bf_bits(rbf(hv + rbf(keep0))), io.epoch);
+        } else {
+          const float hv = (it0 == 0) ? hpre : ldcg_bf(io.out + r);  // lane i prefetched tile i
+          io.out[r] = f2bf(rbf(hv + rbf(keep0)));
+        }
       }
     } else {  // HEAD: logits + running logsumexp (warp-parallel over the 32 tiles)
       const float a = mine ? rbf(keep0) : -INFINITY;
@@ -343,13 +361,20 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
 
 }  // namespace
 
-template <int CHH, int CHI>
+// FLOW: dataflow mode — the grid barriers after qkv, o_proj and down are replaced by polling
+// self-validating words (q/k/v pairs, the residual stream); the barriers after attention (its
+// fp32 partial outputs) and after gate/up (the 18 KB activation vector) remain.  Safe without
+// them because every later phase needs data from ALL CTAs of the phase before it (transitively
+// nobody can overwrite a word that a slower CTA still has to read), and the tag of a word is
+// unique per (step, layer).
+template <int CHH, int CHI, bool FLOW>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ MegaShared sh;
   uint8_t* ring = sm;
   uint8_t* xs = sm + (long)p.n_stages * MEGA_STAGE;  // activation vector (GEMV phases) /
   float* scratch = reinterpret_cast<float*>(xs);     // attention scratch (attention phase)
+  uint16_t* hraw = reinterpret_cast<uint16_t*>(xs + p.scratch_bytes);  // FLOW: raw residual stream
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.st->error) return;  // a previous step gave up: do not spin again
   if (threadIdx.x == 0) {
@@ -409,41 +434,49 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     bf16* kc = p.kv + (long)l * p.kv_layer_stride;
     bf16* vc = kc + p.kv_v_offset;
     (void)plane;
+    const uint32_t ep = (uint32_t)(sh.att_base + (unsigned long long)l + 1ull);  // tag of this layer
     {
-      PhaseIO io = {p.h, lw.ln1, lw.bqkv, p.qbuf, kc, vc, nullptr};
-      consume_phase<PH_QKV, CHH>(p, p.ph[PH_QKV], io, ring, xs, &sh, rg, ctx, pos);
+      PhaseIO io = {p.h, lw.ln1, lw.bqkv, p.qbuf, kc, vc, nullptr, nullptr,
+                    (FLOW && l > 0) ? p.hout_w : nullptr, nullptr, p.qkv_w, hraw, ep, ep - 1u};
+      consume_phase<PH_QKV, CHH, FLOW>(p, p.ph[PH_QKV], io, ring, xs, &sh, rg, ctx, pos);
     }
-    grid_barrier(p, &sh, bidx);
+    if (!FLOW) grid_barrier(p, &sh, bidx);
     if ((int)blockIdx.x < p.attn_ctas) {
-      const AttnParts ap = {nullptr, nullptr, 0};
-      if (d.hd == 128) attn_phase<128, false>(p, kc, vc, scratch, &sh, ctx + 1, l, ap,
-                                       (p.dbg && l == 5 && blockIdx.x < 2) ? p.dbg + 4096 + 128 + 32 * blockIdx.x : nullptr);
-      else attn_phase<64, false>(p, kc, vc, scratch, &sh, ctx + 1, l, ap);
+      const AttnParts ap = {nullptr, nullptr, 0, p.qkv_w, ep};
+      constexpr int AM = FLOW ? ATT_FLOW : ATT_PLAIN;
+      if (d.hd == 128) attn_phase<128, AM>(p, kc, vc, scratch, &sh, ctx + 1, l, ap,
+                                           (p.dbg && l == 5 && blockIdx.x < 2) ? p.dbg + 4096 + 128 + 32 * blockIdx.x : nullptr);
+      else attn_phase<64, AM>(p, kc, vc, scratch, &sh, ctx + 1, l, ap);
     }
     grid_barrier(p, &sh, bidx);
     {
-      PhaseIO io = {p.attn, nullptr, nullptr, p.h, nullptr, nullptr, nullptr, p.att_part};
-      if (p.ph[PH_ORES].S == 1) consume_phase<PH_ORES, CHH>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
-      else consume_phase<PH_DRES, CHH>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
+      PhaseIO io = {p.attn, nullptr, nullptr, p.h, nullptr, nullptr, nullptr, p.att_part,
+                    nullptr, p.hmid_w, nullptr, hraw, ep, 0u};
+      if (p.ph[PH_ORES].S == 1) consume_phase<PH_ORES, CHH, FLOW>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
+      else consume_phase<PH_DRES, CHH, FLOW>(p, p.ph[PH_ORES], io, ring, xs, &sh, rg, 0, 0);
     }
-    grid_barrier(p, &sh, bidx);
+    if (!FLOW) grid_barrier(p, &sh, bidx);
     {
-      PhaseIO io = {p.h, lw.ln2, nullptr, p.act, nullptr, nullptr, nullptr};
+      PhaseIO io = {p.h, lw.ln2, nullptr, p.act, nullptr, nullptr, nullptr, nullptr,
+                    FLOW ? p.hmid_w : nullptr, nullptr, nullptr, hraw, ep, ep};
       long long* td = (p.dbg && l == 5 && (blockIdx.x == 0 || blockIdx.x == 77))
                           ? p.dbg + 4096 + (blockIdx.x ? 32 : 0) : nullptr;
-      consume_phase<PH_GATEUP, CHH>(p, p.ph[PH_GATEUP], io, ring, xs, &sh, rg, 0, 0, td);
+      consume_phase<PH_GATEUP, CHH, FLOW>(p, p.ph[PH_GATEUP], io, ring, xs, &sh, rg, 0, 0, td);
     }
     grid_barrier(p, &sh, bidx);
     {
-      PhaseIO io = {p.act, nullptr, nullptr, p.h, nullptr, nullptr, nullptr};
+      PhaseIO io = {p.act, nullptr, nullptr, p.h, nullptr, nullptr, nullptr, nullptr,
+                    nullptr, p.hout_w, nullptr, hraw, ep, 0u};
       long long* td = (p.dbg && l == 5 && blockIdx.x == 0) ? p.dbg + 4096 + 64 : nullptr;
-      consume_phase<PH_DRES, CHI>(p, p.ph[PH_DRES], io, ring, xs, &sh, rg, 0, 0, td);
+      consume_phase<PH_DRES, CHI, FLOW>(p, p.ph[PH_DRES], io, ring, xs, &sh, rg, 0, 0, td);
     }
-    grid_barrier(p, &sh, bidx);
+    if (!FLOW) grid_barrier(p, &sh, bidx);
   }
   {
-    PhaseIO io = {p.h, p.final_norm, nullptr, p.logits, nullptr, nullptr, p.partials};
-    consume_phase<PH_HEAD, CHH>(p, p.ph[PH_HEAD], io, ring, xs, &sh, rg, 0, 0);
+    const uint32_t ep_last = (uint32_t)(sh.att_base + (unsigned long long)p.n_layers);
+    PhaseIO io = {p.h, p.final_norm, nullptr, p.logits, nullptr, nullptr, p.partials, nullptr,
+                  (FLOW && p.n_layers > 0) ? p.hout_w : nullptr, nullptr, nullptr, hraw, 0u, ep_last};
+    consume_phase<PH_HEAD, CHH, FLOW>(p, p.ph[PH_HEAD], io, ring, xs, &sh, rg, 0, 0);
   }
   grid_barrier(p, &sh, bidx);
   mega_sample_finalize(p, sh, bidx);
@@ -466,7 +499,8 @@ static int mega_geometry(MegaPhase& g, int K, int N, bool pair, int units) {
 
 // region after the ring: attention scratch, or the activation vector of a GEMV phase
 static size_t mega_attn_scratch(const DecodeDims& d) {
-  const size_t att = ((size_t)MEGA_ATT_G * cdiv(d.cap, ATT_UN) + (size_t)8 * MEGA_ATT_G * d.hd) * 4;
+  const size_t att = ((size_t)MEGA_ATT_G * cdiv(d.cap, ATT_UN) + (size_t)8 * MEGA_ATT_G * d.hd +
+                      (size_t)(MEGA_ATT_G + 2) * d.hd /* dataflow mode: q, new k, new v */) * 4;
   const size_t xs = (size_t)max(max(d.inter, d.hidden), d.n_heads * d.hd) * 2;
   return ((att > xs ? att : xs) + 127) & ~(size_t)127;
 }
@@ -495,7 +529,9 @@ int mega_fill(MegaP& p, int sm_count) {
   B200_REQUIRE(p.attn_ctas <= sm_count, "mega: %d attention CTAs > %d SMs", p.attn_ctas, sm_count);
   B200_REQUIRE(d.hd == 64 || d.hd == 128, "mega: head_dim %d (64|128)", d.hd);
   const size_t scratch = mega_attn_scratch(d);
-  const long budget = 227 * 1024 - 2048 - (long)scratch;
+  p.scratch_bytes = (int)scratch;
+  const size_t hraw = ((size_t)d.hidden * 2 + 127) & ~(size_t)127;  // dataflow mode: raw residual stream
+  const long budget = 227 * 1024 - 2048 - (long)scratch - (long)hraw;
   int ns = (int)(budget / MEGA_STAGE);
   B200_REQUIRE(ns >= 2, "mega: cache capacity %d leaves no room for the weight ring", d.cap);
   p.n_stages = ns > 8 ? 8 : ns;
@@ -505,23 +541,29 @@ int mega_fill(MegaP& p, int sm_count) {
 
 static int mega_chx(const MegaPhase& g) { return cdiv(cdiv(g.K >> 3, g.S), 32); }
 
-template <int CHH, int CHI>
-static int mega_launch_t(const MegaP& p, int grid, size_t smem, cudaStream_t s) {
+template <int CHH, int CHI, bool FLOW>
+static int mega_launch_f(const MegaP& p, int grid, size_t smem, cudaStream_t s) {
   static bool set = false;
   if (!set) {
-    B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024 - 2048));
-    B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI, FLOW>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
     set = true;
   }
-  k_mega<CHH, CHI><<<grid, MEGA_THREADS, smem, s>>>(p);
+  k_mega<CHH, CHI, FLOW><<<grid, MEGA_THREADS, smem, s>>>(p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
+template <int CHH, int CHI>
+static int mega_launch_t(const MegaP& p, int grid, size_t smem, cudaStream_t s) {
+  return p.flow ? mega_launch_f<CHH, CHI, true>(p, grid, smem, s)
+                : mega_launch_f<CHH, CHI, false>(p, grid, smem, s);
+}
 
 int mega_launch(const MegaP& p, int sm_count, cudaStream_t s) {
-  const size_t smem = (size_t)p.n_stages * MEGA_STAGE + mega_attn_scratch(p.d);
+  const size_t smem = (size_t)p.n_stages * MEGA_STAGE + mega_attn_scratch(p.d) +
+                      (((size_t)p.d.hidden * 2 + 127) & ~(size_t)127);
   int chh = mega_chx(p.ph[PH_QKV]);
   chh = max(chh, mega_chx(p.ph[PH_ORES]));
   chh = max(chh, mega_chx(p.ph[PH_GATEUP]));

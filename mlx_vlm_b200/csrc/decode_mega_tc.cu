@@ -508,9 +508,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega_tc(const __grid_consta
     grid_barrier(p, &sh.m, bidx);
     // ---- attention (finishes q/k/v from the partials) ----
     if ((int)blockIdx.x < p.attn_ctas) {
-      const AttnParts ap = {P.qkv_acc, lw.bqkv, pos};
-      if (d.hd == 128) attn_phase<128, true>(p, kc, vc, scratch, &sh.m, ctx + 1, l, ap);
-      else attn_phase<64, true>(p, kc, vc, scratch, &sh.m, ctx + 1, l, ap);
+      const AttnParts ap = {P.qkv_acc, lw.bqkv, pos, nullptr, 0u};
+      if (d.hd == 128) attn_phase<128, ATT_PARTS>(p, kc, vc, scratch, &sh.m, ctx + 1, l, ap);
+      else attn_phase<64, ATT_PARTS>(p, kc, vc, scratch, &sh.m, ctx + 1, l, ap);
     }
     grid_barrier(p, &sh.m, bidx);
     // ---- o_proj: split-K partials ----

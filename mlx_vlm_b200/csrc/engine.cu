@@ -86,6 +86,8 @@ struct b200_engine {
   int tc_alias = 1;
   int tc_inflight = 2;
   int fma_inflight = 0, l2_prefetch = 0;
+  int flow = 0;  // k_mega dataflow mode (set_mega(4) / B200_MEGA_FLOW=1): measured slower, see DESIGN.md
+  unsigned long long* flow_words = nullptr;
   float* att_part = nullptr;
   float* att_stats = nullptr;
   unsigned long long* att_cnt = nullptr;
@@ -208,6 +210,17 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
   p.dbg = e->dbg;
   // tuning aids (defaults chosen from the sweeps recorded in profiles/)
   p.max_inflight = e->fma_inflight;
+  p.flow = e->flow;
+  {
+    const size_t nh = (size_t)c.hidden, nq = (size_t)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim / 2;
+    if (!e->flow_words) {
+      B200_CUDA(cudaMalloc(&e->flow_words, (2 * nh + nq) * sizeof(unsigned long long)));
+      B200_CUDA(cudaMemset(e->flow_words, 0, (2 * nh + nq) * sizeof(unsigned long long)));
+    }
+    p.hmid_w = e->flow_words;
+    p.hout_w = e->flow_words + nh;
+    p.qkv_w = e->flow_words + 2 * nh;
+  }
   p.l2_prefetch = e->l2_prefetch;
   int rc;
   if (e->use_mega == 2) {
@@ -335,6 +348,7 @@ int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine**
   e->device = device;
   e->sm_count = sm;
   decode_set_sm_count(sm);
+  if (const char* v = getenv("B200_MEGA_FLOW")) e->flow = atoi(v) != 0;  // tuning aid (A/B)
   const auto& c = e->cfg;
   B200_CUDA(cudaMalloc(&e->st, sizeof(DecState)));
   B200_CUDA(cudaMemset(e->st, 0, sizeof(DecState)));
@@ -731,11 +745,15 @@ int b200_engine_set_graph(b200_engine* e, int enabled) {
 }
 int b200_engine_set_mega(b200_engine* e, int enabled) {
   B200_REQUIRE(e, "set_mega: null engine");
-  B200_REQUIRE(enabled >= 0 && enabled <= 3, "set_mega: mode %d (0 off, 1 k_mega, 2 k_mega_tc, 3 k_mega_tc with a 16-row operand)", enabled);
-  e->use_mega = enabled == 3 ? 2 : enabled;
+  B200_REQUIRE(enabled >= 0 && enabled <= 4,
+               "set_mega: mode %d (0 off, 1 k_mega, 2 k_mega_tc, 3 k_mega_tc with a 16-row operand, 4 k_mega dataflow)",
+               enabled);
+  e->use_mega = enabled == 3 ? 2 : (enabled == 4 ? 1 : enabled);
   e->tc_alias = enabled == 3 ? 0 : 1;
+  e->flow = enabled == 4 ? 1 : 0;
   if (const char* v = getenv("B200_TC_INFLIGHT")) e->tc_inflight = atoi(v) > 0 ? atoi(v) : 2;  // tuning aids
   if (const char* v = getenv("B200_FMA_INFLIGHT")) e->fma_inflight = atoi(v);
+
   if (const char* v = getenv("B200_L2_PREFETCH")) e->l2_prefetch = atoi(v);
   invalidate_graph(e);
   return B200_OK;

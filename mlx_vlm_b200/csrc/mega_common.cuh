@@ -59,6 +59,48 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 __device__ __forceinline__ uint4 ldcg16(const void* p) {
   return __ldcg(reinterpret_cast<const uint4*>(p));
 }
+// ---- self-validating activation words (dataflow mode of k_mega) -------------------------
+// A value that crosses CTAs inside a layer is published as an 8-byte word {payload << 32 |
+// epoch}; 8-byte accesses are single-copy atomic, the epoch is unique per (step, layer), so a
+// reader simply re-loads until the tag matches: barrier + load (3 dependent L2 round trips)
+// become one polled load.
+__device__ __forceinline__ void st_word(unsigned long long* p, uint32_t payload, uint32_t epoch) {
+  const unsigned long long w = ((unsigned long long)payload << 32) | epoch;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ld_word2(const unsigned long long* p, unsigned long long& a,
+                                         unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// 8 consecutive per-element words (payload = bf16 bits) -> one 16-byte vector of 8 bf16
+__device__ __forceinline__ uint4 poll8(const unsigned long long* w, uint32_t epoch, int* err) {
+  unsigned long long a[8];
+  unsigned spins = 0;
+  bool ok;
+  do {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld_word2(w + 2 * i, a[2 * i], a[2 * i + 1]);
+    ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ok = ok && ((uint32_t)a[i] == epoch);
+    if (!ok) {
+      __nanosleep(200);  // back off: ~28k threads poll the same few KB of L2
+      if (++spins > (1u << 20)) {
+        *err = 4;
+        break;
+      }
+    }
+  } while (!ok);
+  uint4 v;
+  v.x = ((uint32_t)(a[0] >> 32) & 0xffffu) | ((uint32_t)(a[1] >> 32) << 16);
+  v.y = ((uint32_t)(a[2] >> 32) & 0xffffu) | ((uint32_t)(a[3] >> 32) << 16);
+  v.z = ((uint32_t)(a[4] >> 32) & 0xffffu) | ((uint32_t)(a[5] >> 32) << 16);
+  v.w = ((uint32_t)(a[6] >> 32) & 0xffffu) | ((uint32_t)(a[7] >> 32) << 16);
+  return v;
+}
+__device__ __forceinline__ uint32_t bf_bits(float x) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
 __device__ __forceinline__ float ldcg_bf(const bf16* p) {
   return __uint_as_float((uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p)) << 16);
 }
@@ -164,12 +206,17 @@ namespace {
 // memory, the unit that owns the new key scores it from there and one CTA per kv head
 // appends it to the cache.
 struct AttnParts {
-  const long long* acc;  // [qkv rows]
+  const long long* acc;  // PARTS: [qkv rows] fixed-point sums
   const bf16* bias;
   int pos;
+  // FLOW (k_mega dataflow mode): q / k / v of this step as finished, rotated bf16 PAIRS (dims j and
+  // j + hd/2 of a head) in self-validating words [head slot][hd/2]
+  const unsigned long long* qkvw;
+  uint32_t epoch;
 };
 
-template <int HD, bool PARTS>
+enum { ATT_PLAIN = 0, ATT_PARTS = 1, ATT_FLOW = 2 };
+template <int HD, int AMODE>
 __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const bf16* vc,
                                            float* scratch, MegaShared* sh, int nkeys, int layer,
                                            const AttnParts& ap, long long* tdbg = nullptr) {
@@ -191,6 +238,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
   const bf16* vb = vc + (long)kvh * d.cap * HD;
   const int per = (nkeys + ATT_UN - 1) / ATT_UN;
   const int u0 = min(nkeys, unit * per), u1 = min(nkeys, u0 + per);
+  constexpr bool PARTS = (AMODE != ATT_PLAIN);  // q / new k / new v come through shared memory
   const bool owner = PARTS && (u1 == nkeys) && (u1 > u0);  // holds the new key (index nkeys-1)
   const int u1g = u1 - (owner ? 1 : 0);                    // keys that are read from the cache
   float* qs = red + (long)8 * AG * HD;                     // PARTS: [AG][HD] q * scale
@@ -232,7 +280,42 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
     }
   }
   float qr[AG][SEG];
-  if (PARTS) {
+  if (AMODE == ATT_FLOW) {
+    // poll the finished q (x scale) / new k / new v pairs published by the qkv phase
+    const int half = HD / 2;
+    const int nslot = G + (owner ? 2 : 0);
+    for (int i = threadIdx.x; i < nslot * half; i += 256) {
+      const int slot = i / half, j = i % half;
+      const int hs = (slot < G) ? (h0 + slot) : (slot == G ? d.n_heads + kvh : d.n_heads + d.n_kv + kvh);
+      const unsigned long long* wp = ap.qkvw + (long)hs * half + j;
+      unsigned long long w;
+      unsigned spins = 0;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(wp) : "memory");
+        if ((uint32_t)w != ap.epoch) {
+          __nanosleep(200);
+          if (++spins > (1u << 20)) {
+            sh->err = 4;
+            break;
+          }
+        }
+      } while ((uint32_t)w != ap.epoch);
+      const uint32_t pr = (uint32_t)(w >> 32);
+      float lo = __uint_as_float(pr << 16), hi = __uint_as_float(pr & 0xffff0000u);
+      float* dst = (slot < G) ? qs + (long)slot * HD : (slot == G ? kn : vn);
+      if (slot < G) {
+        lo = rbf(lo * d.scale_bf);
+        hi = rbf(hi * d.scale_bf);
+      }
+      dst[j] = lo;
+      dst[j + half] = hi;
+    }
+    cbar();
+#pragma unroll
+    for (int g = 0; g < AG; ++g)
+#pragma unroll
+      for (int i = 0; i < SEG; ++i) qr[g][i] = (g < G) ? qs[(long)g * HD + seg * SEG + i] : 0.f;
+  } else if (PARTS) {
     const int half = HD / 2;
     const int nslot = G + (owner ? 2 : 0);
     for (int i = threadIdx.x; i < nslot * HD; i += 256) {

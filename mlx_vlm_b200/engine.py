@@ -176,7 +176,8 @@ class Engine:
 
     def set_mega(self, enabled):
         """0/False: one kernel per phase; 1/True: k_mega (CUDA-core consumers); 2: k_mega_tc
-        (tcgen05 consumers); 3: k_mega_tc with a full 16-row activation operand."""
+        (tcgen05 consumers); 3: k_mega_tc with a full 16-row activation operand; 4: k_mega in
+        dataflow mode (polled self-validating activation words instead of 3 of the 5 barriers)."""
         N.check(self.lib.b200_engine_set_mega(self.h, int(enabled)), "set_mega")
 
     def debug_buffer(self, name: str, dtype=torch.float32) -> torch.Tensor:

@@ -212,10 +212,11 @@ def test_multi_kernel_decode_equals_megakernel():
         assert rl2(a, b) <= 1e-3
 
 
-@pytest.mark.parametrize("kind,mode", [("tiny", 2), ("wide2", 2), ("wide2", 3)])
+@pytest.mark.parametrize("kind,mode", [("tiny", 2), ("wide2", 2), ("wide2", 3), ("tiny", 4), ("wide2", 4)])
 def test_tensor_core_megakernel_parity(kind, mode):
-    """k_mega_tc (decode_mega_tc.cu: tcgen05 GEMV phases on pre-packed weight tile images,
-    exact fixed-point split-K accumulation) against the oracle, teacher-forced, and against
+    """Alternative decode-step kernels — k_mega_tc (modes 2/3; decode_mega_tc.cu: tcgen05 GEMV
+    phases on pre-packed weight tile images, exact fixed-point split-K accumulation) and k_mega
+    in dataflow mode (mode 4: polled self-validating activation words) — against the oracle, teacher-forced, and against
     k_mega on the same cache; the appended K/V rows of layer 0 must be bit-identical (same
     inputs, one Linear + rotary, fp32 accumulation differences stay below one bf16 ulp almost
     everywhere)."""

@@ -26,22 +26,28 @@ raw = np.zeros(2 * 1024 * 2 + 256, dtype=np.int64)
 buf = raw[:4096].reshape(2, 1024, 2)
 N.check(eng.lib.b200_engine_mega_timeline(eng.h, raw.ctypes.data))
 L = 28
-names = ["qkv", "attn", "ores", "gateup", "dres"]
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+flow = mode == 1 and os.environ.get("B200_MEGA_FLOW", "1") != "0"
+if flow:
+    # dataflow mode: two grid barriers per layer (after attention, after gate/up)
+    names, per = ["down(l-1) + qkv + attention", "o_proj + gate/up"], 2
+else:
+    names, per = ["qkv", "attn", "ores", "gateup", "dres"], 5
 for cta in (0, 1):
     a = buf[cta]
-    nb = 5 * L + 2
+    nb = per * L + 2
     arrive, release = a[:nb, 0], a[:nb, 1]
-    t0 = release[0]
     comp = np.empty(nb); comp[0] = np.nan
     comp[1:] = arrive[1:] - release[:-1]
     wait = release - arrive
-    print(f"--- CTA {'0' if cta == 0 else 'last'}: step span {(release[nb-1]-arrive[0])/1e3:.1f} us (first arrive -> last release)")
+    print(f"--- CTA {'0' if cta == 0 else 'last'}: step span {(release[nb-1]-arrive[0])/1e3:.1f} us (first arrive -> last release)"
+          + (" [dataflow mode]" if flow else ""))
     for k, nm in enumerate(names):
-        idx = np.arange(L) * 5 + k
+        idx = np.arange(L) * per + k
         c = comp[idx[1:] if k == 0 else idx]
-        print(f"  {nm:7s} compute {np.nanmean(c)/1e3:7.2f} us  barrier wait {wait[idx].mean()/1e3:7.2f} us")
-    print(f"  head    compute {comp[5*L]/1e3:7.2f} us  wait {wait[5*L]/1e3:7.2f} us; sample compute {comp[5*L+1]/1e3:7.2f} wait {wait[5*L+1]/1e3:7.2f}")
-    print("  layer 5 raw (compute, wait) us:", [(round(comp[25+k]/1e3,2), round(wait[25+k]/1e3,2)) for k in range(5)])
+        print(f"  {nm:28s} compute {np.nanmean(c)/1e3:7.2f} us  barrier wait {wait[idx].mean()/1e3:7.2f} us")
+    print(f"  head (+ last down)           compute {comp[per*L]/1e3:7.2f} us  wait {wait[per*L]/1e3:7.2f} us; sample compute {comp[per*L+1]/1e3:7.2f} wait {wait[per*L+1]/1e3:7.2f}")
+    print("  layer 5 raw (compute, wait) us:", [(round(float(comp[per*5+k])/1e3,2), round(float(wait[per*5+k])/1e3,2)) for k in range(per)])
 
 for name, off in (("gateup CTA0", 4096), ("gateup CTA77", 4096 + 32), ("dres CTA0", 4096 + 64)):
     t = raw[off:off + 28]
@@ -53,9 +59,9 @@ for name, off in (("gateup CTA0", 4096), ("gateup CTA77", 4096 + 32), ("dres CTA
 t = raw[4096 + 96:4096 + 126]; t = t[t > 0]
 c = raw[4096:4096 + 30]; c = c[c > 0]
 b = buf[0]
-print("layer-5 CTA0 absolute us (relative to QKV-barrier release of layer 5):")
-t0 = b[25, 1]
-print("  barrier releases qkv/attn/ores/gateup/dres:", [round((b[25 + k, 1] - t0) / 1e3, 2) for k in range(5)])
+print("layer-5 CTA0 absolute us (relative to the first barrier release of layer 5):")
+t0 = b[per * 5, 1]
+print("  barrier releases:", [round(float(b[per * 5 + k, 1] - t0) / 1e3, 2) for k in range(per)])
 print("  producer issue times of gate/up tiles:", [round((x - t0) / 1e3, 2) for x in t])
 print("  consumer gate/up stamps (start, prologue end, then wait-done/compute-done):", [round((x - t0) / 1e3, 2) for x in c])
 
