@@ -192,9 +192,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       umma_commit(tmem_full);  // accumulator complete
     }
-  } else if (warp >= 4) {
+  }
+  __syncwarp();
+  {
     // ===== epilogue: TMEM -> registers -> bias/activation/residual -> global =====
-    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    // ALL 8 warps take part once their main-loop role is done (the producer / MMA threads have
+    // issued everything by now): warp w reads TMEM lane quarter w % 4 and column half w / 4, so
+    // the non-overlapped tail of a CTA (bias, GELU, residual, 16-byte stores) is half as long
+    // (ncu, round 1: a 128x128 tile's epilogue is 3-5 us of a 13-24 us CTA).
+    const int q = warp & 3;  // TMEM lane quarter == warp % 4
+    const int chalf = warp >> 2;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int row = m_blk * BM + q * 32 + lane;
@@ -202,7 +209,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool vec_ok = ((p.ldc & 7) == 0) && (!p.residual || (p.ldr & 7) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
       const int n0 = n_blk * BN + c0;
