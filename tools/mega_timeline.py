@@ -10,7 +10,7 @@ model, proc = load_synthetic("qwen2-vl-2b", seed=0, device="cuda:0", n_text_toke
 eng = model.engine
 eng.set_graph(False)
 if len(sys.argv) > 1:
-    eng.set_mega(int(sys.argv[1]))  # 1: k_mega, 2: k_mega_tc
+    eng.set_mega(int(sys.argv[1]))  # 1: k_mega, 2: k_mega_tc, 4: k_mega dataflow mode
 N.check(eng.lib.b200_engine_mega_timeline(eng.h, 0))
 img = np.random.default_rng(0).integers(0, 256, size=(336, 336, 3), dtype=np.uint8)
 inp = prepare_inputs(proc, images=[img], prompts="x", device=eng.device, stream=eng.stream)
@@ -27,7 +27,7 @@ buf = raw[:4096].reshape(2, 1024, 2)
 N.check(eng.lib.b200_engine_mega_timeline(eng.h, raw.ctypes.data))
 L = 28
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-flow = mode == 1 and os.environ.get("B200_MEGA_FLOW", "1") != "0"
+flow = mode == 4 or (mode == 1 and os.environ.get("B200_MEGA_FLOW", "0") == "1")
 if flow:
     # dataflow mode: two grid barriers per layer (after attention, after gate/up)
     names, per = ["down(l-1) + qkv + attention", "o_proj + gate/up"], 2
