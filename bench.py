@@ -140,8 +140,9 @@ def cpu_reference_run(W, n_decode, threads=None):
     import numpy as np
     import torch
     from oracle import qwen2vl as O
-    if threads:
-        torch.set_num_threads(threads)
+    # all host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU
+    # arm runs on rank 0 alone, so it takes the whole host)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     c = O.qwen2_vl_2b()
     req = O.synthetic_request(c, N_TEXT, image_hw=IMG_HW, seed=0)
     ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
