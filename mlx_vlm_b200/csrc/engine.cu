@@ -406,6 +406,9 @@ int b200_engine_destroy(b200_engine* e) {
   if (e->att_stats) cudaFree(e->att_stats);
   if (e->bar) cudaFree(e->bar);
   if (e->dbg) cudaFree(e->dbg);
+  if (e->packed) cudaFree(e->packed);
+  if (e->tc_acc) cudaFree(e->tc_acc);
+  if (e->flow_words) cudaFree(e->flow_words);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
