@@ -288,6 +288,32 @@ def main():
     golden["pad_prompts"] = {"prompts": prompts, "left": tolist(lp_fn(prompts)), "right": tolist(rp_fn(prompts)),
                              "left_max6": tolist(lp_fn(prompts, 6))}
 
+    # ---------------- LLaVA merge (models/llava/llava.py:90-116): positional assignment, batch 1
+    lmerge, w = load(ns, "models/llava/llava.py", "_merge_input_ids_with_image_features", "Model")
+    provenance["llava._merge_input_ids_with_image_features"] = w
+    lstub = types.SimpleNamespace(config=types.SimpleNamespace(image_token_index=100))
+    lcases = []
+
+    def run_lmerge(ids, n_feats, tag):
+        ids = np.asarray(ids)
+        H = 4
+        feats = (1000 + np.arange(n_feats * H, dtype=np.float32)).reshape(1, n_feats, H)
+        emb = -(np.arange(ids.size * H, dtype=np.float32) + 1).reshape(1, ids.shape[1], H)
+        try:
+            out = tolist(lmerge(lstub, mx.array(feats), mx.array(emb), mx.array(ids)))
+            err = None
+        except Exception as e:  # ValueError (too many features) or numpy's shape error (too few)
+            out, err = None, f"{type(e).__name__}: {e}"
+        lcases.append({"tag": tag, "input_ids": ids.tolist(), "n_feats": n_feats, "hidden": H,
+                       "positions": np.where(ids == 100)[1].tolist(), "output": out, "error": err})
+
+    run_lmerge([[5, 100, 100, 100, 6, 7]], 3, "one image, three positions")
+    run_lmerge([[100, 5, 100, 6, 100, 100]], 4, "scattered positions")
+    run_lmerge([[5, 6, 7]], 0, "no image tokens, no features")
+    run_lmerge([[5, 100, 100, 6]], 3, "more features than positions -> ValueError")
+    run_lmerge([[5, 100, 100, 100, 6]], 2, "fewer features than positions -> shape error")
+    golden["llava_merge"] = lcases
+
     # ---------------- sampler masks (sample_utils.py:149-345), fp32 on seeded logprobs
     ns["math"] = __import__("math")
     samp = {}
