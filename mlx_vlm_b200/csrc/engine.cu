@@ -77,6 +77,8 @@ struct b200_engine {
   int prepared_cap = -1, prepared_cluster = -1;
   // megakernel
   int use_mega = 1;  // 0: one kernel per phase, 1: k_mega (CUDA cores), 2: k_mega_tc (tcgen05)
+  bool mega_fits = true;  // false: this shape / cache capacity does not fit the persistent kernel
+  int active_mega() const { return mega_fits ? use_mega : 0; }
   MegaTcP tp;
   uint8_t* packed = nullptr;  // tile images of the LM weights (k_mega_tc)
   size_t packed_bytes = 0;
@@ -172,6 +174,7 @@ static int resolve(b200_engine* e) {
 
 static void invalidate_graph(b200_engine* e) {
   e->mega_ready = false;
+  e->mega_fits = true;
   if (e->gexec) {
     cudaGraphExecDestroy(e->gexec);
     e->gexec = nullptr;
@@ -293,8 +296,8 @@ static int enqueue_step(b200_engine* e, cudaStream_t s) {
   const DecodeDims d = e->dims();
   const auto& c = e->cfg;
   int rc;
-  if (e->use_mega == 2) return mega_tc_launch(e->tp, e->sm_count, s);
-  if (e->use_mega) return mega_launch(e->mp, e->sm_count, s);
+  if (e->active_mega() == 2) return mega_tc_launch(e->tp, e->sm_count, s);
+  if (e->active_mega()) return mega_launch(e->mp, e->sm_count, s);
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerW& lw = e->layers[l];
     bf16* kc = e->kptr(l, 0);
@@ -313,7 +316,7 @@ static int enqueue_step(b200_engine* e, cudaStream_t s) {
 }
 
 static int kernels_per_step(const b200_engine* e) {
-  return e->use_mega ? 1 : e->cfg.n_layers * 5 + 2;
+  return e->active_mega() ? 1 : e->cfg.n_layers * 5 + 2;
 }
 
 extern "C" {
@@ -699,8 +702,14 @@ int b200_engine_decode(b200_engine* e, int n_steps, const int* force_tokens_host
     e->prepared_cap = e->kv_cap;
     e->prepared_cluster = e->attn_cluster;
   }
-  if (e->use_mega && !e->mega_ready) {
-    if ((rc = mega_prepare(e, s))) return rc;
+  if (e->use_mega && e->mega_fits && !e->mega_ready) {
+    if ((rc = mega_prepare(e, s))) {
+      // a geometry the persistent kernel cannot hold (very long cache: the attention scratch
+      // leaves no room for the weight ring; > 148 attention CTAs; ...): same step, one kernel per
+      // phase — still this library's CUDA path.  b200_last_error() keeps the reason.
+      if (rc != B200_ERR_INVALID) return rc;
+      e->mega_fits = false;
+    }
   }
   if (e->use_graph && !e->gexec) {
     // capture one step on the engine's own stream (capture does not execute)

@@ -44,6 +44,14 @@ def _mk_cfg(kind):
         c.text.num_hidden_layers = 2
         c.vision.depth = 2
         return c
+    if kind == "mha32":  # 32 kv heads (Llama-7B-like MHA): more attention CTAs than SMs -> the
+        c = O.tiny_cfg()  # persistent kernel does not fit and the engine falls back per phase
+        c.text.hidden_size, c.text.num_attention_heads, c.text.num_key_value_heads = 2048, 32, 32
+        c.text.intermediate_size, c.text.num_hidden_layers = 512, 1
+        c.text.mrope_section = (8, 12, 12)
+        c.vision.hidden_size = 2048
+        c.vision.depth = 1
+        return c
     if kind == "full":
         return O.qwen2_vl_2b()
     raise ValueError(kind)
@@ -293,6 +301,76 @@ def test_batch_generator_rows_equal_single_requests():
         assert model.engine.device_error() == 0
         for u, w in zip(uids, want):
             assert got[u] == w, (slice_, u, got[u], w)
+
+
+def test_two_images_of_different_size_in_one_prompt():
+    """Multi-image request (the case of the reference's TestMultiImageMRoPE, test_models.py:11866):
+    two images with different grids -> per-image (block-diagonal) vision attention, features
+    concatenated, merge by cumsum(mask)-1, position ids / delta bit-exact, prefill logits in noise."""
+    from mlx_vlm_b200.models.cache import make_prompt_cache
+    from oracle import qwen2vl as O
+    c, W, model, _ = _build("tiny", 8, (56, 56))
+    eng = model.engine
+    rng = np.random.default_rng(7)
+    imgs = [rng.integers(0, 256, size=(3, 56, 84), dtype=np.uint8),
+            rng.integers(0, 256, size=(3, 84, 56), dtype=np.uint8)]
+    pvs, grids = zip(*[O.preprocess_image(im, c.vision) for im in imgs])
+    pv = np.concatenate(pvs, axis=0)
+    grid = np.asarray(grids, dtype=np.int64)
+    text = rng.integers(0, 900, size=12).tolist()
+    ids = text[:3] + [c.vision_start_token_id, c.image_token_id, c.vision_end_token_id] + text[3:7] + \
+        [c.vision_start_token_id, c.image_token_id, c.vision_end_token_id] + text[7:]
+    ids = np.asarray([O.expand_image_tokens(ids, grids, c)], dtype=np.int64)
+    ref = O.greedy_generate(c, W, ids, pv, grid, 2)
+    ex = O.greedy_generate(c, W, ids, pv, grid, 2, dtype="f32", force_tokens=ref["tokens"][0].tolist())
+    pre, pre32 = ref["prefill"], ex["prefill"]
+    pvd = torch.from_numpy(pv).cuda()
+    feats = model.vision_tower(pvd, grid)
+    eng.stream.synchronize()
+    assert feats.shape[0] == int(sum(np.prod(g) for g in grids)) // 4
+    cmp_noise(feats, pre.image_features, pre32.image_features, "two-image vision features")
+    emb = model.get_input_embeddings(ids, pvd, image_grid_thw=grid)
+    eng.stream.synchronize()
+    assert np.array_equal(np.asarray(emb.position_ids), pre.position_ids)
+    assert np.array_equal(np.asarray(emb.rope_deltas), pre.rope_deltas)
+    src = O.merge_indices(c, ids)[0]
+    img_rows = np.where(src >= 0)[0]
+    e = emb.inputs_embeds[0].float().cpu()
+    assert torch.equal(e[img_rows], feats.float().cpu()[torch.from_numpy(src[img_rows])])
+    cache = make_prompt_cache(model.language_model)
+    out = model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache,
+                               position_ids=emb.position_ids, rope_deltas=emb.rope_deltas)
+    eng.stream.synchronize()
+    cmp_noise(out.logits[0, -1], pre.logits_last[0], pre32.logits_last[0], "two-image prefill logits")
+
+
+def test_geometry_that_does_not_fit_the_persistent_kernel_falls_back_per_phase():
+    """32 kv heads x 8 key ranges > 148 SMs: k_mega cannot hold the step; the engine must run the
+    same step as per-phase kernels (still the CUDA path) and stay in parity with the oracle."""
+    from mlx_vlm_b200.models.cache import make_prompt_cache
+    from oracle import qwen2vl as O
+    c, W, model, req = _build("mha32", 10, (56, 56))
+    ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
+    eng = model.engine
+    n_dec = 4
+    ref = O.greedy_generate(c, W, ids, pv, grid, n_dec)
+    toks = ref["tokens"][0].tolist()
+    ex = O.greedy_generate(c, W, ids, pv, grid, n_dec, dtype="f32", force_tokens=toks[:])
+    pvd = torch.from_numpy(pv).cuda()
+    cache = make_prompt_cache(model.language_model)
+    emb = model.get_input_embeddings(ids, pvd, image_grid_thw=grid)
+    model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache,
+                         position_ids=emb.position_ids, rope_deltas=emb.rope_deltas)
+    T = ids.shape[1]
+    eng.set_next(toks[0], T, T + int(ref["prefill"].rope_deltas[0, 0]))
+    launches0 = eng.launch_count
+    for n in range(1, n_dec):
+        eng.decode(1, force_tokens=np.asarray([toks[n]], dtype=np.int32))
+        eng.stream.synchronize()
+        cmp_noise(eng.logits_view(), ref["logits"][n][0], ex["logits"][n][0], f"mha32 decode step {n}")
+    assert eng.device_error() == 0
+    per_step = (eng.launch_count - launches0) / (n_dec - 1)
+    assert per_step > 2, f"expected the per-phase path (several launches per step), got {per_step}"
 
 
 def test_text_only_and_cache_reuse():
