@@ -314,6 +314,86 @@ def main():
     run_lmerge([[5, 100, 100, 100, 6]], 2, "fewer features than positions -> shape error")
     golden["llava_merge"] = lcases
 
+    # ---------------- Idefics2 integer logic (models/idefics2/vision.py:123-173, idefics2.py:15-33,185-280)
+    mx.flatten = lambda a, start_axis=0, end_axis=-1: np.reshape(
+        a, a.shape[:start_axis] + (-1,) + (a.shape[end_axis + 1:] if end_axis != -1 and end_axis + 1 < a.ndim else ()))
+    mx.reshape = np.reshape
+    mx.uint32 = np.uint32
+    code, w = extract("models/idefics2/vision.py", "VisionEmbeddings")
+    ns["VisionConfig"] = object
+    exec(compile(code, "<ref idefics2 VisionEmbeddings>", "exec"), ns)
+    provenance["idefics2.VisionEmbeddings.__call__"] = w
+    seen = {}
+
+    def make_embed_stub(num_side, patch):
+        st = types.SimpleNamespace(patch_size=patch, num_patches=num_side)
+        st.patch_embedding = lambda x: np.zeros((x.shape[0], x.shape[1] // patch, x.shape[2] // patch, 2), np.float32)
+
+        def pos_emb(ids):
+            seen["ids"] = np.asarray(ids).copy()
+            return np.zeros(ids.shape + (2,), np.float32)
+        st.position_embedding = pos_emb
+        return st
+
+    icases = []
+    for num_side, patch, H_, W_, masks in (
+            (5, 14, 70, 70, [np.ones((5, 5), bool)]),
+            (7, 14, 70, 56, [np.ones((5, 4), bool), np.pad(np.ones((3, 2), bool), ((0, 2), (0, 2)))]),
+            (70, 14, 98, 98, [np.pad(np.ones((7, 4), bool), ((0, 0), (0, 3))), np.ones((7, 7), bool)])):
+        st = make_embed_stub(num_side, patch)
+        x = np.zeros((len(masks), H_, W_, 3), np.float32)
+        ns["VisionEmbeddings"].__call__(st, x, mask=[m for m in masks])
+        icases.append({"num_patches_per_side": num_side, "patch_size": patch,
+                       "patch_mask": [m.astype(int).tolist() for m in masks],
+                       "position_ids": seen["ids"].tolist()})
+    golden["idefics2_position_ids"] = icases
+
+    ns["InputEmbeddingsFeatures"] = lambda inputs_embeds=None, **k: types.SimpleNamespace(inputs_embeds=inputs_embeds)
+    load(ns, "models/idefics2/idefics2.py", "masked_scatter")
+    gie, w = load(ns, "models/idefics2/idefics2.py", "get_input_embeddings", "Model")
+    prep, w2 = load(ns, "models/idefics2/idefics2.py", "_prepare_inputs_for_multimodal", "Model")
+    provenance["idefics2.get_input_embeddings"] = w
+    provenance["idefics2._prepare_inputs_for_multimodal"] = w2
+    cap = {}
+
+    def vision_stub(x, patch_attention_mask=None, output_hidden_states=None):
+        cap["n_images"] = int(x.shape[0])
+        cap["patch_mask"] = np.asarray(patch_attention_mask).astype(int).tolist()
+        cap["pixel_sum"] = [float(v) for v in np.asarray(x).reshape(x.shape[0], -1).sum(1)]
+        return np.zeros((x.shape[0], 3, 2), np.float32), None, None
+
+    mstub = types.SimpleNamespace(
+        config=types.SimpleNamespace(vision_config=types.SimpleNamespace(patch_size=14), image_token_index=100),
+        language_model=types.SimpleNamespace(embed_tokens=lambda ids: np.zeros(ids.shape + (2,), np.float32)),
+        vision_model=vision_stub, connector=lambda f: f)
+    mstub._prepare_inputs_for_multimodal = lambda feats, emb, ids: emb
+    pvv = rng.standard_normal((1, 3, 3, 42, 56)).astype(np.float32)
+    pvv[0, 1] = 0.0  # a padding image
+    pam = np.zeros((1, 3, 42, 56), bool)
+    pam[0, 0] = True
+    pam[0, 2, :30, :20] = True
+    gie(mstub, mx.array(np.zeros((1, 4), np.int64)), mx.array(pvv), pixel_attention_mask=mx.array(pam))
+    golden["idefics2_get_input_embeddings"] = {"pixel_values_shape": list(pvv.shape), "zero_image": 1,
+                                               "pixel_attention_valid": [[42, 56], [0, 0], [30, 20]],
+                                               "n_images_kept": cap["n_images"], "patch_mask": cap["patch_mask"],
+                                               "pixel_sum": cap["pixel_sum"],
+                                               "pixel_sum_expected": [float(pvv[0, i].sum()) for i in (0, 2)]}
+    pcases = []
+    for ids_, nfeat, tag in (([[5, 100, 100, 6, 100]], 3, "three image rows"),
+                             ([[5, 100, 6]], 2, "count mismatch -> ValueError")):
+        ids_ = np.asarray(ids_)
+        Hd = 3
+        feats = (1000 + np.arange(nfeat * Hd, dtype=np.float32)).reshape(1, nfeat, Hd)
+        emb = -(np.arange(ids_.size * Hd, dtype=np.float32) + 1).reshape(1, ids_.shape[1], Hd)
+        try:
+            out = tolist(prep(mstub, mx.array(feats), mx.array(emb), mx.array(ids_)))
+            err = None
+        except ValueError as e:
+            out, err = None, str(e)
+        pcases.append({"tag": tag, "input_ids": ids_.tolist(), "n_feats": nfeat, "hidden": Hd,
+                       "output": out, "error": err})
+    golden["idefics2_merge"] = pcases
+
     # ---------------- sampler masks (sample_utils.py:149-345), fp32 on seeded logprobs
     ns["math"] = __import__("math")
     samp = {}
