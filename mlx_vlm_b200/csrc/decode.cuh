@@ -66,7 +66,6 @@ struct MegaP {
   unsigned long long *hmid_w, *hout_w;  // residual stream after o_proj / after down, one word per element
   unsigned long long* qkv_w;            // finished q/k/v pairs [head slot][hd/2]
   float* att_part;  // [groups][8 units][4*hd] fp32 partial attention outputs
-  unsigned long long* att_cnt;  // [groups] monotonic arrival counters
   float* att_stats; // [groups][8 units][4 heads] x 2 words {float bits << 32 | epoch}: (max, sum exp)
   long long* dbg;  // optional [2][1024][2] globaltimer stamps (arrive, release) per barrier
 };

@@ -92,7 +92,6 @@ struct b200_engine {
   unsigned long long* flow_words = nullptr;
   float* att_part = nullptr;
   float* att_stats = nullptr;
-  unsigned long long* att_cnt = nullptr;
   unsigned long long* bar = nullptr;
   bool mega_ready = false;
   MegaP mp;
@@ -189,8 +188,6 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
     B200_CUDA(cudaMemset(e->bar, 0, sizeof(unsigned long long)));
     const size_t part = (size_t)64 * 8 * 4 * c.head_dim * sizeof(float);
     B200_CUDA(cudaMalloc(&e->att_part, part));
-    B200_CUDA(cudaMalloc(&e->att_cnt, 64 * sizeof(unsigned long long)));
-    B200_CUDA(cudaMemset(e->att_cnt, 0, 64 * sizeof(unsigned long long)));
     B200_CUDA(cudaMalloc(&e->att_stats, (size_t)64 * 8 * 4 * 16));  // {value, epoch} word pairs
     B200_CUDA(cudaMemset(e->att_stats, 0, (size_t)64 * 8 * 4 * 16));
   }
@@ -200,7 +197,6 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
   p.n_layers = c.n_layers;
   for (int l = 0; l < c.n_layers; ++l) p.layers[l] = e->layers[l];
   p.att_part = e->att_part;
-  p.att_cnt = e->att_cnt;
   p.att_stats = e->att_stats;
   p.final_norm = e->norm; p.head = e->head; p.embed = e->embed;
   p.h = e->h; p.qbuf = e->qbuf; p.attn = e->attn; p.act = e->act;
@@ -405,7 +401,6 @@ int b200_engine_destroy(b200_engine* e) {
   cudaFree(e->force); cudaFree(e->lm_inv_freq); cudaFree(e->axis_sel); cudaFree(e->v_inv_freq);
   if (e->pos_hw) cudaFree(e->pos_hw);
   if (e->att_part) cudaFree(e->att_part);
-  if (e->att_cnt) cudaFree(e->att_cnt);
   if (e->att_stats) cudaFree(e->att_stats);
   if (e->bar) cudaFree(e->bar);
   if (e->dbg) cudaFree(e->dbg);

@@ -191,16 +191,17 @@ namespace {
 // Under the weight stream every dependent global round trip costs ~1 us, so the phase
 // is built around the NUMBER of such trips.  CTA (grp, unit): grp = (kv head, q-head
 // group), unit = one of ATT_UN key ranges.
-//   1. scores of the OWN key range (coalesced: 8 lanes per key, 4 keys per warp
-//      instruction, all K loads of the range in flight at once), local (max, sum exp)
-//      per head -> global stats;
-//   2. group barrier among the ATT_UN CTAs of the group (atomic counter);
-//   3. global (M, L) from the ATT_UN stats, p = bf16(exp(s - M) / L), partial P.V
-//      (V rows were requested before the barrier);
-//   4. the last CTA of the group to finish sums the partial outputs in a fixed order.
-// Measured alternatives (tools/mega_timeline.py, ctx ~470): one CTA per (kv head,
-// group) 15.9 us; one CTA per q head 17.1 us; every unit recomputing all scores
-// 11.1 us; this 10.6 us.
+//   1. all q / K / V requests of the CTA are issued up front; scores of the OWN key range
+//      (coalesced: 8 lanes per key, 4 keys per warp instruction, software-pipelined trips),
+//      local (max, sum exp) per head;
+//   2. the ATT_UN x heads statistics are exchanged as self-validating {value, epoch} words
+//      polled by one warp (no counter, no separate load): global (M, L) by a butterfly;
+//   3. p = bf16(exp(s - M) / L) precomputed cooperatively, partial P.V -> global fp32;
+//   4. the partial outputs are summed, in a fixed order, by the o_proj prologue.
+// Measured history of this phase (tools/mega_timeline.py, ctx ~470): one CTA per (kv head,
+// group) 15.9 us; one CTA per q head 17.1 us; every unit recomputing all scores 11.1 us;
+// counter barrier + last-arriver combine 10.6 us; one-warp statistics read, no combine 5.4 us;
+// polled statistics words 4.7 us.
 // PARTS (k_mega_tc): q / k / v of this step arrive as fixed-point split-K sums of the qkv
 // GEMV; the phase prologue finishes them (+ bias, round, rotary, q * scale) in shared
 // memory, the unit that owns the new key scores it from there and one CTA per kv head
