@@ -140,9 +140,21 @@ def cpu_reference_run(W, n_decode, threads=None):
     import numpy as np
     import torch
     from oracle import qwen2vl as O
-    # all host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU
-    # arm runs on rank 0 alone, so it takes the whole host)
-    torch.set_num_threads(threads or os.cpu_count() or 1)
+    # one thread per PHYSICAL core (torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm
+    # runs on rank 0 alone, so it takes the whole host.  Measured: 64 threads 3.5-4.7 tok/s, the
+    # 128 logical CPUs 0.13 tok/s — hyper-thread oversubscription)
+    if not threads:
+        try:
+            import psutil
+            threads = psutil.cpu_count(logical=False)
+        except Exception:
+            threads = None
+        threads = threads or max(1, (os.cpu_count() or 2) // 2)
+        try:
+            threads = min(threads, len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
+    torch.set_num_threads(threads)
     c = O.qwen2_vl_2b()
     req = O.synthetic_request(c, N_TEXT, image_hw=IMG_HW, seed=0)
     ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
