@@ -73,17 +73,19 @@ class Model:
 
     # ------------------------------------------------------------ weights
     def sanitize(self, weights):
-        """qwen2_vl.py:179-190 key renames (HF -> reference names)."""
-        def transform_key(key):
-            if "vision_tower" not in key:
-                key = key.replace("visual", "vision_tower")
-            if "language_model" not in key:
-                if "model" in key:
-                    key = key.replace("model", "language_model.model")
-                elif "lm_head" in key:
-                    key = key.replace("lm_head", "language_model.lm_head")
-            return key
-        return {transform_key(k): v for k, v in weights.items()}
+        """HF checkpoint names -> the reference's names (behaviour of qwen2_vl.py:179-190, pinned by
+        tests/golden `sanitize_keys`): `visual.*` becomes `vision_tower.*`; tensors not yet under
+        `language_model` get the `language_model.` prefix on their `model` / `lm_head` component."""
+        renamed = {}
+        for key, value in weights.items():
+            name = key if "vision_tower" in key else key.replace("visual", "vision_tower")
+            if "language_model" not in name:
+                for part in ("model", "lm_head"):       # first match wins, like the reference's if/elif
+                    if part in name:
+                        name = name.replace(part, "language_model." + part)
+                        break
+            renamed[name] = value
+        return renamed
 
     def load_weights(self, weights: Dict[str, torch.Tensor], strict: bool = True):
         """Pack reference-named tensors into the engine layout (bf16, device):

@@ -394,6 +394,51 @@ def main():
                        "output": out, "error": err})
     golden["idefics2_merge"] = pcases
 
+    # ---------------- load path: key renames + conv layout rule (qwen2_vl.py:179-190, vision.py:9-25,292-310)
+    msan, w = load(ns, "models/qwen2_vl/qwen2_vl.py", "sanitize", "Model")
+    provenance["qwen2_vl.Model.sanitize"] = w
+    hf_keys = ["visual.patch_embed.proj.weight", "visual.blocks.0.attn.qkv.weight", "visual.merger.mlp.0.bias",
+               "model.embed_tokens.weight", "model.layers.3.self_attn.q_proj.bias", "model.norm.weight",
+               "lm_head.weight", "vision_tower.blocks.1.norm1.weight",
+               "language_model.model.layers.0.mlp.up_proj.weight", "language_model.lm_head.weight"]
+    golden["sanitize_keys"] = {k: list(msan(None, {k: 0}).keys())[0] for k in hf_keys}
+    load(ns, "models/qwen2_vl/vision.py", "check_array_shape")
+    vsan, w = load(ns, "models/qwen2_vl/vision.py", "sanitize", "VisionModel")
+    provenance["qwen2_vl.VisionModel.sanitize"] = w
+    hfw = np.arange(8 * 3 * 2 * 4 * 4, dtype=np.float32).reshape(8, 3, 2, 4, 4)   # HF [O, C, T, H, W]
+    vout = vsan(None, {"vision_tower.patch_embed.proj.weight": hfw, "vision_tower.blocks.0.attn.position_ids": 1,
+                       "vision_tower.blocks.0.attn.qkv.weight": np.zeros((2, 2), np.float32)})
+    mlxw = vout["vision_tower.patch_embed.proj.weight"]
+    again = vsan(None, {"vision_tower.patch_embed.proj.weight": mlxw})["vision_tower.patch_embed.proj.weight"]
+    golden["vision_sanitize"] = {"hf_shape": list(hfw.shape), "kept_keys": sorted(vout.keys()),
+                                 "mlx_layout_shape": list(mlxw.shape), "mlx_layout": tolist(mlxw),
+                                 "idempotent": bool(np.array_equal(again, mlxw))}
+
+    # ---------------- image processor (qwen3_vl/processing_qwen3_vl.py:164-354): PIL bicubic resize,
+    # rescale / normalise, temporal duplication, merge-group-major patch rows
+    import hashlib
+    ns["math"] = __import__("math")
+    ns["Tuple"], ns["List"] = tuple, list
+    ns["Image"] = __import__("PIL.Image", fromlist=["Image"])
+    load(ns, "models/qwen3_vl/processing_qwen3_vl.py", "_smart_resize_image")
+    load(ns, "models/qwen3_vl/processing_qwen3_vl.py", "_resize_video_frames")
+    ns["ImageProcessingMixin"] = object
+    code, w = extract("models/qwen3_vl/processing_qwen3_vl.py", "Qwen3VLImageProcessor")
+    exec(compile(code, "<ref Qwen3VLImageProcessor>", "exec"), ns)
+    provenance["Qwen3VLImageProcessor._process_one"] = w
+    IP = ns["Qwen3VLImageProcessor"]
+    ip = IP(patch_size=14, temporal_patch_size=2, merge_size=2,
+            image_mean=[0.48145466, 0.4578275, 0.40821073], image_std=[0.26862954, 0.26130258, 0.27577711])
+    pcases = []
+    for hw_ in ((336, 336), (56, 84), (200, 310), (28, 1000), (30, 45)):
+        img = np.random.default_rng(hw_[0] * 1000 + hw_[1]).integers(0, 256, size=(3, hw_[0], hw_[1]), dtype=np.uint8)
+        pvv_, grid_ = ip._process_one(img)
+        pvv_ = np.ascontiguousarray(pvv_.astype(np.float32))
+        pcases.append({"hw": list(hw_), "seed": hw_[0] * 1000 + hw_[1], "grid": [int(x) for x in grid_],
+                       "shape": list(pvv_.shape), "sha256": hashlib.sha256(pvv_.tobytes()).hexdigest(),
+                       "first": tolist(pvv_[0, :4]), "last": tolist(pvv_[-1, -4:])})
+    golden["image_processor"] = pcases
+
     # ---------------- sampler masks (sample_utils.py:149-345), fp32 on seeded logprobs
     ns["math"] = __import__("math")
     samp = {}

@@ -193,3 +193,45 @@ def test_greedy_sampler_semantics():
     assert int(S.argmax_lowest(x)[0]) == 1
     from mlx_vlm_b200.sample_utils import greedy_sampler
     assert int(greedy_sampler(x)[0]) == 1
+
+
+def test_load_path_key_renames_and_conv_layout_match_reference_source():
+    """`Model.sanitize` (qwen2_vl.py:179-190) and the patch-embed layout rule
+    (vision.py:9-25, 292-310).  The reference normalises the conv weight to MLX [O,T,H,W,C]; the
+    engine wants HF [O,C,T,H,W] (same linear map on (C,T,H,W)-ordered pixel rows): both layouts
+    must come out as the HF tensor."""
+    from mlx_vlm_b200.models.qwen2_vl import Model
+    from mlx_vlm_b200.models.qwen2_vl.vision import VisionModel
+    m = Model.__new__(Model)
+    for k, want in GOLD["sanitize_keys"].items():
+        assert list(m.sanitize({k: 0}).keys()) == [want], k
+    g = GOLD["vision_sanitize"]
+    hf = torch.arange(int(np.prod(g["hf_shape"])), dtype=torch.float32).reshape(g["hf_shape"])
+    mlx_layout = torch.tensor(g["mlx_layout"], dtype=torch.float32)
+    assert list(mlx_layout.shape) == g["mlx_layout_shape"] and g["idempotent"]
+    assert torch.equal(mlx_layout, hf.permute(0, 2, 3, 4, 1))          # what the reference stores
+    vm = VisionModel.__new__(VisionModel)
+    key = "vision_tower.patch_embed.proj.weight"
+    for src in (hf, mlx_layout):
+        out = vm.sanitize({key: src, "vision_tower.blocks.0.attn.position_ids": 1,
+                           "vision_tower.blocks.0.attn.qkv.weight": torch.zeros(2, 2)})
+        assert sorted(out.keys()) == g["kept_keys"]
+        assert torch.equal(out[key].contiguous(), hf)
+
+
+def test_image_processor_matches_reference_source_bit_exactly():
+    """`Qwen3VLImageProcessor._process_one` (processing_qwen3_vl.py:302-354) executed
+    from the reference's source: smart_resize, PIL bicubic, rescale/normalise, temporal duplication,
+    merge-group-major patch order.  Oracle and product must give the same bytes."""
+    import hashlib
+    from mlx_vlm_b200.models.qwen2_vl.processing_qwen2_vl import Qwen2VLImageProcessor
+    ip = Qwen2VLImageProcessor(image_mean=O.OPENAI_CLIP_MEAN, image_std=O.OPENAI_CLIP_STD)
+    for c in GOLD["image_processor"]:
+        img = np.random.default_rng(c["seed"]).integers(0, 256, size=(3, c["hw"][0], c["hw"][1]), dtype=np.uint8)
+        pv, grid = O.preprocess_image(img, O.VisionCfg())
+        assert list(grid) == c["grid"] and list(pv.shape) == c["shape"], c["hw"]
+        assert hashlib.sha256(np.ascontiguousarray(pv.astype(np.float32)).tobytes()).hexdigest() == c["sha256"], c["hw"]
+        out = ip([img.transpose(1, 2, 0)])
+        assert out["image_grid_thw"].tolist() == [c["grid"]]
+        got = np.ascontiguousarray(np.asarray(out["pixel_values"], dtype=np.float32))
+        assert hashlib.sha256(got.tobytes()).hexdigest() == c["sha256"], c["hw"]
