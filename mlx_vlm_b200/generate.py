@@ -340,7 +340,13 @@ def generate(model, processor, prompt: str, image=None, audio=None, video=None,
 
 # --------------------------------------------------------------------------
 class _NaiveDetokenizer:
-    """tokenizer_utils.py:71-118 NaiveStreamingDetokenizer semantics."""
+    """Streaming detokenizer with the reference's observable behaviour (tokenizer_utils.py:48-118,
+    `StreamingDetokenizer.last_segment` + `NaiveStreamingDetokenizer`; pinned by the golden trace
+    `detokenizer_trace`): the pending tokens are re-decoded on every read and folded into the
+    settled text at a newline; a segment is only released when the text does not end in an
+    incomplete UTF-8 sequence (U+FFFD)."""
+
+    _REPLACEMENT = "\ufffd"
 
     def __init__(self, tokenizer):
         self._tok = tokenizer
@@ -348,37 +354,41 @@ class _NaiveDetokenizer:
 
     def reset(self):
         self.offset = 0
-        self._tokens: List[int] = []
-        self._text = ""
-        self._current: List[int] = []
-        self._current_text = ""
+        self._settled_tokens: List[int] = []
+        self._settled_text = ""
+        self._pending: List[int] = []
+        self._pending_text = ""
 
     def add_token(self, token, skip_special_token_ids=()):
-        if token in skip_special_token_ids:
-            return
-        self._current.append(token)
-        self._tokens.append(token)
+        if token not in skip_special_token_ids:
+            self._pending.append(token)
+
+    def _settle(self, text: str):
+        self._settled_tokens.extend(self._pending)
+        self._settled_text += text
+        self._pending = []
+        self._pending_text = ""
 
     def finalize(self):
-        self._text += self._tok.decode(self._current)
-        self._current = []
-        self._current_text = ""
+        self._settle(self._tok.decode(self._pending))
 
     @property
-    def text(self):
-        if self._current:
-            self._current_text = self._tok.decode(self._current)
-            if self._current_text.endswith("�"):
-                self._current_text = self._current_text[:-1]
-            if self._current_text and self._current_text[-1] == "\n":
-                self._text += self._current_text
-                self._current = []
-                self._current_text = ""
-        return self._text + self._current_text
+    def text(self) -> str:
+        if self._pending:
+            self._pending_text = self._tok.decode(self._pending)
+        if self._pending_text.endswith("\n"):
+            self._settle(self._pending_text)
+        return self._settled_text + self._pending_text
 
     @property
-    def last_segment(self):
+    def tokens(self) -> List[int]:
+        return self._settled_tokens
+
+    @property
+    def last_segment(self) -> str:
         text = self.text
+        if not text or text.endswith(self._REPLACEMENT):
+            return ""
         seg = text[self.offset:]
         self.offset = len(text)
         return seg

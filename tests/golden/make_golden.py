@@ -439,6 +439,30 @@ def main():
                        "first": tolist(pvv_[0, :4]), "last": tolist(pvv_[-1, -4:])})
     golden["image_processor"] = pcases
 
+    # ---------------- streaming detokenizer (tokenizer_utils.py:14-118)
+    ns["REPLACEMENT_CHAR"] = "\ufffd"
+    code, w = extract("tokenizer_utils.py", "StreamingDetokenizer")
+    exec(compile(code, "<ref StreamingDetokenizer>", "exec"), ns)
+    code, w = extract("tokenizer_utils.py", "NaiveStreamingDetokenizer")
+    exec(compile(code, "<ref NaiveStreamingDetokenizer>", "exec"), ns)
+    provenance["NaiveStreamingDetokenizer"] = w
+    pieces = {0: b"", 1: b"Hel", 2: b"lo", 3: b" w", 4: "\u00e9".encode()[:1], 5: "\u00e9".encode()[1:], 6: b"\n",
+              7: b"next", 8: "\U0001f600".encode()[:2], 9: "\U0001f600".encode()[2:], 10: b"!", 11: b"<eos>"}
+
+    class FakeTok:
+        def decode(self, ids):
+            return b"".join(pieces[i] for i in ids).decode("utf-8", errors="replace")
+    det = ns["NaiveStreamingDetokenizer"](FakeTok())
+    seq = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 6, 1]
+    dtrace = []
+    for tk in seq:
+        det.add_token(tk, skip_special_token_ids=[11])
+        dtrace.append({"token": tk, "segment": det.last_segment, "settled_tokens": list(det.tokens)})
+    det.finalize()
+    golden["detokenizer_trace"] = {"pieces_hex": {str(k): v.hex() for k, v in pieces.items()}, "skip": [11],
+                                   "steps": dtrace, "final_segment": det.last_segment, "final_text": det.text,
+                                   "final_tokens": list(det.tokens)}
+
     # ---------------- sampler masks (sample_utils.py:149-345), fp32 on seeded logprobs
     ns["math"] = __import__("math")
     samp = {}
