@@ -154,29 +154,8 @@ class LanguageModel:
         B, L = ids_host.shape
         if B != 1:
             raise NotImplementedError("batched LanguageModel calls arrive with BatchKVCache (next round)")
-        position_ids = _np(position_ids)
-        if position_ids is not None and position_ids.shape[-1] > L:
-            position_ids = position_ids[..., cache_offset:cache_offset + L]
-        rope_mask = mask
-        if mask is not None and _np(mask).shape[-1] != L:
-            rope_mask = None
-        if position_ids is None and (rope_mask is None or _np(rope_mask).ndim == 2):
-            if cache_offset == 0 or self._rope_deltas is None:
-                if self._position_ids is not None:
-                    position_ids = self._position_ids[..., cache_offset:cache_offset + L]
-                else:
-                    position_ids, deltas = self.get_rope_index(ids_host, image_grid_thw,
-                                                               video_grid_thw, rope_mask)
-                    self._rope_deltas = deltas
-                    self._position_ids = position_ids
-            else:
-                src = _np(rope_deltas_kw) if rope_deltas_kw is not None else self._rope_deltas
-                delta = cache_offset + np.asarray(src).reshape(-1)[:B]
-                position_ids = np.arange(L)[None, :] + delta[:, None]  # (B, L)
-                position_ids = np.broadcast_to(position_ids[None], (3, B, L))
-        if position_ids.ndim == 2:  # text-only: the same scalar position on every axis
-            position_ids = np.broadcast_to(position_ids[None], (3,) + position_ids.shape)
-        delta0 = int(np.asarray(self._rope_deltas).reshape(-1)[0]) if self._rope_deltas is not None else 0
+        position_ids, delta0 = self.resolve_position_ids(ids_host, cache_offset, position_ids, mask,
+                                                         image_grid_thw, video_grid_thw, rope_deltas_kw)
 
         need = max(cache_offset + L, reserve_tokens)
         self._bind(cache, need)
@@ -204,6 +183,42 @@ class LanguageModel:
         for c in cache:
             c.offset += L
         return LanguageModelOutput(logits=logits)
+
+    def resolve_position_ids(self, ids_host: np.ndarray, cache_offset: int, position_ids=None, mask=None,
+                             image_grid_thw=None, video_grid_thw=None, rope_deltas_kw=None):
+        """Position bookkeeping of `LanguageModel.__call__` (reference language.py:404-518), pure host
+        logic: returns ((3, B, L) int positions, M-RoPE delta of row 0) and records `_rope_deltas` /
+        `_position_ids` like the reference.
+          * explicit `position_ids` longer than the chunk are sliced at the cache offset;
+          * first call of a request (cache empty or no delta yet): the stored ids of the request
+            (chunked prefill) or `get_rope_index`;
+          * afterwards (decode / later chunks): arange(L) + cache_offset + rope_delta on all three axes;
+          * 2-D (text-only) positions are broadcast to the three M-RoPE axes."""
+        B, L = ids_host.shape
+        position_ids = _np(position_ids)
+        if position_ids is not None and position_ids.shape[-1] > L:
+            position_ids = position_ids[..., cache_offset:cache_offset + L]
+        rope_mask = mask
+        if mask is not None and _np(mask).shape[-1] != L:
+            rope_mask = None
+        if position_ids is None and (rope_mask is None or _np(rope_mask).ndim == 2):
+            if cache_offset == 0 or self._rope_deltas is None:
+                if self._position_ids is not None:
+                    position_ids = self._position_ids[..., cache_offset:cache_offset + L]
+                else:
+                    position_ids, deltas = self.get_rope_index(ids_host, image_grid_thw,
+                                                               video_grid_thw, rope_mask)
+                    self._rope_deltas = deltas
+                    self._position_ids = position_ids
+            else:
+                src = _np(rope_deltas_kw) if rope_deltas_kw is not None else self._rope_deltas
+                delta = cache_offset + np.asarray(src).reshape(-1)[:B]
+                position_ids = np.arange(L)[None, :] + delta[:, None]  # (B, L)
+                position_ids = np.broadcast_to(position_ids[None], (3, B, L))
+        if position_ids.ndim == 2:  # text-only: the same scalar position on every axis
+            position_ids = np.broadcast_to(position_ids[None], (3,) + position_ids.shape)
+        delta0 = int(np.asarray(self._rope_deltas).reshape(-1)[0]) if self._rope_deltas is not None else 0
+        return position_ids, delta0
 
     # -------------------------------------------------- fused greedy decoding
     def fused_greedy_decode(self, n_steps: int, cache, reserve_tokens: int = 0):

@@ -235,3 +235,37 @@ def test_image_processor_matches_reference_source_bit_exactly():
         assert out["image_grid_thw"].tolist() == [c["grid"]]
         got = np.ascontiguousarray(np.asarray(out["pixel_values"], dtype=np.float32))
         assert hashlib.sha256(got.tobytes()).hexdigest() == c["sha256"], c["hw"]
+
+
+def test_language_model_position_bookkeeping():
+    """SURVEY §8 a7 (language.py:404-518): prefill uses get_rope_index, chunks slice the stored ids,
+    decode steps use cache_offset + rope_delta on all three axes (== oracle.decode_position_ids),
+    explicit position ids longer than the chunk are sliced at the cache offset."""
+    lm = _product_lm()
+    ids = np.asarray([_INPUT_IDS])
+    grid = _GRID
+    L = ids.shape[1]
+    # one-shot prefill
+    pos, d0 = lm.resolve_position_ids(ids, 0, image_grid_thw=grid)
+    assert pos.shape == (3, 1, L) and pos[0, 0].tolist() == _EXPECTED_T and d0 == _EXPECTED_DELTA
+    # decode steps: offset + delta, identical on the three axes, same as the oracle
+    for off in (L, L + 1, L + 7):
+        p, d = lm.resolve_position_ids(np.asarray([[5]]), off)
+        want = O.decode_position_ids(off, np.asarray([[_EXPECTED_DELTA]]), 1)
+        assert np.array_equal(np.asarray(p), np.asarray(want)) and d == _EXPECTED_DELTA
+    # an explicit per-row delta (continuous batching passes rope_deltas per call)
+    p, _ = lm.resolve_position_ids(np.asarray([[5]]), 40, rope_deltas_kw=np.asarray([[-3]]))
+    assert np.asarray(p).reshape(3).tolist() == [37, 37, 37]
+    # chunked prefill: second chunk slices the ids stored by the first call of the request
+    lm2 = _product_lm()
+    full, _ = lm2.resolve_position_ids(ids, 0, image_grid_thw=grid)
+    lm2._rope_deltas = None  # state at the time the reference takes this branch (chunk before decode)
+    p2, _ = lm2.resolve_position_ids(ids[:, 6:], 6)
+    assert np.array_equal(np.asarray(p2), np.asarray(full)[..., 6:])
+    # explicit position ids for the whole prompt, chunk of 4 at offset 3
+    p3, _ = lm2.resolve_position_ids(ids[:, 3:7], 3, position_ids=np.asarray(full))
+    assert np.array_equal(np.asarray(p3), np.asarray(full)[..., 3:7])
+    # text-only 2-D positions are broadcast to three axes
+    lm3 = _product_lm()
+    p4, d4 = lm3.resolve_position_ids(np.asarray([[1, 2, 3, 4]]), 0)
+    assert np.asarray(p4).shape == (3, 1, 4) and np.asarray(p4)[1, 0].tolist() == [0, 1, 2, 3] and d4 == 0
