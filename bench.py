@@ -374,8 +374,8 @@ def main():
                          "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_step,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one k_mega launch,
-                         # ncu --set full, profiles/r1_k_mega_ncu_full.txt (ctx ~275)
-                         "traffic": 3_095_564_000 + 4_551_936},
+                         # ncu --set full, profiles/r1_k_mega_ncu_full.txt (ctx ~280)
+                         "traffic": 3_095_604_000 + 4_354_816},
         }
         if not args.no_cpu_baseline and world == 1:
             W = _engine_weights_to_oracle(model, __import__("oracle.qwen2vl", fromlist=["x"]).qwen2_vl_2b())
