@@ -463,6 +463,40 @@ def main():
                                    "steps": dtrace, "final_segment": det.last_segment, "final_text": det.text,
                                    "final_tokens": list(det.tokens)}
 
+    # ---------------- logits processors (sample_utils.py:390-475): repetition / presence / frequency
+    class _At:
+        def __init__(self, arr):
+            self.arr = arr
+
+        def __getitem__(self, idx):
+            arr = self.arr
+
+            class _Op:
+                def subtract(self_, v):   # mlx `.at[idx].subtract(v)`: duplicates accumulate
+                    out = np.array(arr, copy=True)
+                    np.subtract.at(out, idx, v)
+                    return out.view(AtArray)
+            return _Op()
+
+    class AtArray(np.ndarray):
+        @property
+        def at(self):
+            return _At(self)
+
+    pen = {}
+    plog = (rng.standard_normal((1, 16)).astype(np.float32) * 3.0)
+    hist = [3, 7, 7, 1, 12, 3, 3, 9, 15, 0, 7]
+    pen["logits"], pen["tokens"] = tolist(plog), hist
+    for nm, arg, ctx in (("make_repetition_penalty", 1.3, 20), ("make_repetition_penalty", 1.3, 4),
+                         ("make_presence_penalty", 0.7, 20), ("make_presence_penalty", 0.7, 3),
+                         ("make_frequency_penalty", 0.4, 20), ("make_frequency_penalty", 0.4, 6)):
+        mk, w = load(ns, "sample_utils.py", nm)
+        provenance[nm] = w
+        out = mk(arg, ctx)(list(hist), np.array(plog, copy=True).view(AtArray))
+        pen[f"{nm}({arg},{ctx})"] = tolist(np.asarray(out))
+        pen[f"{nm}({arg},{ctx}) empty history"] = tolist(np.asarray(mk(arg, ctx)([], np.array(plog, copy=True).view(AtArray))))
+    golden["logits_processors"] = pen
+
     # ---------------- sampler masks (sample_utils.py:149-345), fp32 on seeded logprobs
     ns["math"] = __import__("math")
     samp = {}
