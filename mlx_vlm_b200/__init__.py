@@ -14,8 +14,9 @@ from .generate_batch import (BatchGenerator, BatchResponse, BatchStats, Generati
                              PromptProgress, batch_generate)
 from .utils import load, load_synthetic, prepare_inputs, process_image
 from .version import __version__
+from .vision_cache import VisionFeatureCache
 
 __all__ = ["BatchGenerator", "BatchResponse", "BatchStats", "GenerationBatch", "PromptProgress",
            "batch_generate", "GenerationResult", "PromptCacheState", "generate", "generate_step",
-           "stream_generate", "load", "load_synthetic", "prepare_inputs", "process_image",
+           "stream_generate", "VisionFeatureCache", "load", "load_synthetic", "prepare_inputs", "process_image",
            "__version__"]

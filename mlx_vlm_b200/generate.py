@@ -216,7 +216,7 @@ def stream_generate(model, processor, prompt: str, image: Union[str, List[str], 
     skip_special_token_ids = (set(getattr(tokenizer, "all_special_ids", []))
                               if kwargs.pop("skip_special_tokens", False) else set())
     prompt_cache_state: Optional[PromptCacheState] = kwargs.pop("prompt_cache_state", None)
-    kwargs.pop("vision_cache", None)
+    vision_cache = kwargs.pop("vision_cache", None)
     eos_tokens = kwargs.pop("eos_tokens", None)
     if not hasattr(tokenizer, "stopping_criteria") or tokenizer.stopping_criteria is None:
         eos = getattr(model.config, "eos_token_id", None)
@@ -239,6 +239,18 @@ def stream_generate(model, processor, prompt: str, image: Union[str, List[str], 
         kwargs.update({k: v for k, v in inputs.items() if v is not None})
     ids_list = np.asarray(input_ids.cpu() if isinstance(input_ids, torch.Tensor) else input_ids
                           ).reshape(-1).tolist()
+
+    # vision feature reuse across turns (dispatch.py:800-809): a hit is handed to the model as
+    # `cached_image_features`; a miss is filled only by models that expose `encode_image`
+    # (Qwen2-VL does not, in the reference either)
+    if vision_cache is not None and image is not None and pixel_values is not None:
+        cached = vision_cache.get(image)
+        if cached is not None:
+            kwargs["cached_image_features"] = cached
+        elif hasattr(model, "encode_image"):
+            features = model.encode_image(pixel_values)
+            vision_cache.put(image, features)
+            kwargs["cached_image_features"] = features
 
     # prefix reuse across turns (dispatch.py:861-882): trim the cached KV to the
     # common prefix and only prefill the new suffix (text-only suffixes).
