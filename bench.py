@@ -244,7 +244,6 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from mlx_vlm_b200 import generate as api_generate
-    from mlx_vlm_b200.generate import generate_step
     from mlx_vlm_b200.models.cache import make_prompt_cache
     from mlx_vlm_b200.utils import load_synthetic, prepare_inputs
 

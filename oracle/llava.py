@@ -30,7 +30,7 @@ step are those of that file (unpinned at the mlx boundary, stated there).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch

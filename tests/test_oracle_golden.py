@@ -10,7 +10,6 @@ Integer outputs must be bit-exact; fp32 formulas within 1e-6.
 """
 import json
 import os
-import types
 
 import numpy as np
 import pytest
