@@ -126,14 +126,24 @@ def gelu_exact(R: Rounder, x):
 # out = scores @ v.
 #   q,k,v: (B, H, L, D) / (B, Hkv, S, D) -> (B, H, L, D)
 # ---------------------------------------------------------------------------
-def sdpa(R: Rounder, q, k, v, scale: float, causal: bool):
+def sdpa(R: Rounder, q, k, v, scale: float, causal: bool, mask=None):
+    """`mask` (bool, broadcastable to (B, 1, L, S), True = attend) is the array-mask form used by the
+    batched path (left-padded rows, models/cache.py:24-42 with `left_padding`): the fallback graph
+    replaces masked scores by the most negative FINITE value of the score dtype, so a fully masked
+    (padding) query row yields a uniform, finite distribution instead of NaN."""
     B, H, L, D = q.shape
     Hkv, S = k.shape[1], k.shape[2]
     rep = H // Hkv
     qs = R.r(q * R.scalar(scale))
     qs = qs.reshape(B, Hkv, rep, L, D)
     scores = R.r(qs @ k[:, :, None].transpose(-1, -2))  # (B,Hkv,rep,L,S)
-    if causal and L > 1:
+    if mask is not None:
+        m = torch.as_tensor(mask, dtype=torch.bool)
+        while m.ndim < 4:
+            m = m[None]
+        m = m[:, :, None]  # (B|1, 1, 1, L, S)
+        scores = torch.where(m, scores, torch.tensor(float(torch.finfo(R.dtype).min)))
+    elif causal and L > 1:
         qi = torch.arange(S - L, S)[:, None]
         ki = torch.arange(S)[None, :]
         scores = torch.where(qi >= ki, scores, torch.tensor(float("-inf")))

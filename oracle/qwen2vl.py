@@ -547,7 +547,7 @@ class OracleKVCache:
 # Language model (language.py)
 # ---------------------------------------------------------------------------
 def lm_layers_forward(cfg: Cfg, W, h, position_ids, cache: List[OracleKVCache], R: Rounder,
-                      collect: Optional[list] = None):
+                      collect: Optional[list] = None, mask=None):
     """Qwen2Model.__call__ without the embedding: h (B,L,H) -> final-normed (B,L,H)."""
     t = cfg.text
     B, L, H = h.shape
@@ -566,7 +566,7 @@ def lm_layers_forward(cfg: Cfg, W, h, position_ids, cache: List[OracleKVCache], 
         v = v.reshape(B, L, nkv, hd).transpose(1, 2)
         q, k = apply_mrope(R, q, k, cos, sin)
         keys, values = cache[i].update_and_fetch(k, v)
-        o = S.sdpa(R, q, keys, values, scale, causal=(L > 1))
+        o = S.sdpa(R, q, keys, values, scale, causal=(L > 1), mask=mask)
         o = o.transpose(1, 2).reshape(B, L, H)
         r = S.linear(R, o, W[p + "self_attn.o_proj.weight"])
         h = R.r(h + r)
