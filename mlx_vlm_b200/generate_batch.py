@@ -91,8 +91,26 @@ class PromptProgress:
     cached_tokens: int = 0
 
 
+@dataclass
+class _Row:
+    uid: int
+    ids: List[int]
+    max_tokens: int
+    kwargs: Dict[str, Any]
+    cache: Optional[list] = None
+    delta: Optional[int] = 0   # M-RoPE delta of the row (None: the model has no M-RoPE state)
+    n_tokens: int = 0          # tokens surfaced so far
+    n_decoded: int = 0         # tokens computed so far (>= n_tokens: the slice buffer)
+    last_token: int = -1       # last computed token (input of the next decode step)
+    buffer: List[Tuple[int, float]] = field(default_factory=list)
+    reserve: int = 0
+
+
 class GenerationBatch:
-    """Namespace parity: the reference nests the response type in GenerationBatch."""
+    """The set of rows that are decoding (reference ar.py:929-1390).  Observable bookkeeping of the
+    reference object — `uids`, `max_tokens`, `_num_tokens`, per-row `_rope_deltas` (B, 1), `filter`,
+    `extend`, `empty` — over rows that each own their KV pool (so `filter` / `extend` move no cache
+    memory here; the reference's versions also re-pack a `BatchKVCache`)."""
 
     @dataclass
     class Response:
@@ -102,20 +120,42 @@ class GenerationBatch:
         finish_reason: Optional[str]
         top_logprobs: Optional[List[Tuple[int, float]]] = None
 
+    def __init__(self, rows: Optional[List[_Row]] = None):
+        self.rows: List[_Row] = list(rows or [])
 
-@dataclass
-class _Row:
-    uid: int
-    ids: List[int]
-    max_tokens: int
-    kwargs: Dict[str, Any]
-    cache: Optional[list] = None
-    delta: int = 0
-    n_tokens: int = 0          # tokens surfaced so far
-    n_decoded: int = 0         # tokens computed so far (>= n_tokens: the slice buffer)
-    last_token: int = -1       # last computed token (input of the next decode step)
-    buffer: List[Tuple[int, float]] = field(default_factory=list)
-    reserve: int = 0
+    @classmethod
+    def empty(cls, *_, **__) -> "GenerationBatch":
+        return cls([])
+
+    def __len__(self) -> int:
+        return len(self.rows)
+
+    @property
+    def uids(self) -> List[int]:
+        return [r.uid for r in self.rows]
+
+    @property
+    def max_tokens(self) -> List[int]:
+        return [r.max_tokens for r in self.rows]
+
+    @property
+    def _num_tokens(self) -> List[int]:
+        return [r.n_tokens for r in self.rows]
+
+    @property
+    def _rope_deltas(self) -> Optional[np.ndarray]:
+        if not self.rows or self.rows[0].delta is None:
+            return None
+        return np.asarray([[r.delta] for r in self.rows], dtype=np.int32)
+
+    def filter(self, keep: List[int]) -> None:
+        self.rows = [self.rows[i] for i in keep]
+
+    def extend(self, other: "GenerationBatch") -> None:
+        if self.rows and other.rows and (self.rows[0].delta is None) != (other.rows[0].delta is None):
+            raise RuntimeError("extend() mixes MRoPE and non-MRoPE batches; both sides must carry "
+                               "rope_deltas or neither side may.")
+        self.rows.extend(other.rows)
 
 
 class BatchGenerator:
@@ -157,7 +197,7 @@ class BatchGenerator:
             self.tokenizer.stopping_criteria.add_eos_token_ids(list(stop_tokens))
         self.uid_count = 0
         self._unprocessed_sequences: List[_Row] = []
-        self._active: List[_Row] = []
+        self._generation_batch = GenerationBatch.empty()
         self._prompt_tokens_counter = 0
         self._prompt_time_counter = 0.0
         self._gen_tokens_counter = 0
@@ -181,12 +221,19 @@ class BatchGenerator:
         self._unprocessed_sequences.sort(key=lambda r: len(r.ids))  # shortest first (ar.py:2620-2623)
         return uids
 
+    @property
+    def _active(self) -> List[_Row]:
+        return self._generation_batch.rows
+
     def remove(self, uid) -> bool:
-        for lst in (self._unprocessed_sequences, self._active):
-            for i, r in enumerate(lst):
-                if r.uid == uid:
-                    lst.pop(i)
-                    return True
+        for i, r in enumerate(self._unprocessed_sequences):   # waiting in the queue
+            if r.uid == uid:
+                self._unprocessed_sequences.pop(i)
+                return True
+        if uid in self._generation_batch.uids:                 # already decoding
+            idx = self._generation_batch.uids.index(uid)
+            self._generation_batch.filter([i for i in range(len(self._generation_batch)) if i != idx])
+            return True
         return False
 
     @property
@@ -219,7 +266,7 @@ class BatchGenerator:
         return s
 
     def close(self):
-        self._active.clear()
+        self._generation_batch.filter([])
         self._unprocessed_sequences.clear()
 
     # ------------------------------------------------------------------ device work
@@ -315,7 +362,7 @@ class BatchGenerator:
         if self._active:
             tic = time.perf_counter()
             keep = []
-            for row in self._active:
+            for i, row in enumerate(self._active):
                 if not row.buffer:
                     self._decode_slice(row)
                 tok, lp = row.buffer.pop(0)
@@ -328,17 +375,21 @@ class BatchGenerator:
                 generation_responses.append(GenerationBatch.Response(
                     uid=row.uid, token=tok, token_logprob=lp, finish_reason=finish))
                 if finish is None:
-                    keep.append(row)
+                    keep.append(i)
             self._gen_tokens_counter += len(self._active)
             self._gen_time_counter += time.perf_counter() - tic
-            self._active = keep
+            if len(keep) < len(self._generation_batch):
+                self._generation_batch.filter(keep)
         # 2. admit waiting prompts while there is room (shortest first)
         room = self.completion_batch_size - len(self._active)
         n_admit = min(room, self.prefill_batch_size, len(self._unprocessed_sequences))
+        admitted = []
         for _ in range(max(0, n_admit)):
             row = self._unprocessed_sequences.pop(0)
             prompt_responses.append(self._prefill(row))
-            self._active.append(row)
+            admitted.append(row)
+        if admitted:
+            self._generation_batch.extend(GenerationBatch(admitted))
         return prompt_responses, generation_responses
 
 
