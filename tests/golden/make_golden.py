@@ -497,6 +497,19 @@ def main():
         pen[f"{nm}({arg},{ctx}) empty history"] = tolist(np.asarray(mk(arg, ctx)([], np.array(plog, copy=True).view(AtArray))))
     golden["logits_processors"] = pen
 
+    # ---------------- config schema (models/qwen2_vl/config.py): field names, order, literal defaults
+    csrc = open(os.path.join(REF, "models/qwen2_vl/config.py")).read()
+    schema = {}
+    for node in ast.parse(csrc).body:
+        if isinstance(node, ast.ClassDef):
+            rows = []
+            for st in node.body:
+                if isinstance(st, ast.AnnAssign):
+                    rows.append([st.target.id, None if st.value is None else ast.literal_eval(st.value)])
+            schema[node.name] = rows
+    golden["qwen2_vl_config_schema"] = schema
+    provenance["qwen2_vl config schema"] = "models/qwen2_vl/config.py (AnnAssign nodes)"
+
     # ---------------- sampler masks (sample_utils.py:149-345), fp32 on seeded logprobs
     ns["math"] = __import__("math")
     samp = {}
