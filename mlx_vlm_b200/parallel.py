@@ -6,7 +6,7 @@ and NO per-step collective.  Timing results are max-reduced over ranks.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Any, Callable, Dict, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -41,3 +41,33 @@ def max_over_ranks(values: Sequence[float], device=None, group=None) -> List[flo
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return t.tolist()
+
+
+def generate_sharded(make_generator: Callable[[], Any], prompts: Sequence[Sequence[int]],
+                     max_tokens, prompt_kwargs: Optional[List[dict]] = None, group=None) -> List[List[int]]:
+    """Config C5 on N replicas: request i runs on rank i % world (round-robin router), every rank drives
+    its own `BatchGenerator` (`make_generator()` builds it around the rank's replica) to completion,
+    and the generated token ids come back on EVERY rank in request order.  The only communication is
+    the final gather of python lists — nothing per step."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    mine = shard_requests(len(prompts), world, rank)
+    if isinstance(max_tokens, int):
+        max_tokens = [max_tokens] * len(prompts)
+    out: Dict[int, List[int]] = {}
+    if mine:
+        gen = make_generator()
+        kws = [dict((prompt_kwargs or [{}] * len(prompts))[i]) for i in mine]
+        uids = gen.insert([list(prompts[i]) for i in mine], [max_tokens[i] for i in mine], kws)
+        by_uid = {u: i for u, i in zip(uids, mine)}
+        for i in mine:
+            out[i] = []
+        while gen.has_work:
+            _, responses = gen.next()
+            for r in responses:
+                out[by_uid[r.uid]].append(r.token)
+    if world > 1:
+        parts: List[Optional[Dict[int, List[int]]]] = [None] * world
+        dist.all_gather_object(parts, out, group=group)
+        out = {k: v for part in parts for k, v in part.items()}
+    return [out[i] for i in range(len(prompts))]

@@ -33,6 +33,21 @@ def _worker(rank, world, port, ret):
     ok = ok and flat == list(range(11))
     mx = max_over_ranks([1.0 + rank, 5.0 - rank])
     ok = ok and mx == [float(world), 5.0]
+    # C5 host logic: 5 requests over 2 replicas, each rank drives its own BatchGenerator; the tokens
+    # every rank sees must equal the requests run alone (deterministic stand-in engine)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_batch_host import _alone, _fake_model
+    from mlx_vlm_b200.generate_batch import BatchGenerator
+    from mlx_vlm_b200.parallel import generate_sharded
+    prompts = [[5, 6, 7, 8, 9], [1, 2], [3, 3, 3], [11] * 9, [4, 2]]
+    maxes = [7, 12, 1, 9, 3]
+
+    def make():
+        model, proc = _fake_model()
+        return BatchGenerator(model, proc, completion_batch_size=2, prefill_batch_size=2, decode_slice=4)
+    got = generate_sharded(make, prompts, maxes)
+    ok = ok and got == [_alone(p, m)[0] for p, m in zip(prompts, maxes)]
     ret[rank] = ok
     dist.destroy_process_group()
 
