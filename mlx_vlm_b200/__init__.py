@@ -12,11 +12,12 @@ from .generate import (GenerationResult, PromptCacheState, generate, generate_st
                        stream_generate)
 from .generate_batch import (BatchGenerator, BatchResponse, BatchStats, GenerationBatch,
                              PromptProgress, batch_generate)
+from .prompt_utils import apply_chat_template, get_message_json
 from .utils import load, load_synthetic, prepare_inputs, process_image
 from .version import __version__
 from .vision_cache import VisionFeatureCache
 
 __all__ = ["BatchGenerator", "BatchResponse", "BatchStats", "GenerationBatch", "PromptProgress",
            "batch_generate", "GenerationResult", "PromptCacheState", "generate", "generate_step",
-           "stream_generate", "VisionFeatureCache", "load", "load_synthetic", "prepare_inputs", "process_image",
+           "stream_generate", "VisionFeatureCache", "apply_chat_template", "get_message_json", "load", "load_synthetic", "prepare_inputs", "process_image",
            "__version__"]

@@ -124,7 +124,7 @@ __device__ __forceinline__ void consume_phase(const MegaP& p, const MegaPhase& g
       if ((MODE == PH_ORES || MODE == PH_DRES) && io.xpart) {
         // x = bf16( sum over the ATT_UN key ranges of the partial attention outputs )
         const DecodeDims& d = p.d;
-        const int d0 = c * 8, h = d0 / d.hd, Gall = d.n_heads / d.n_kv, G = Gall / p.hsplit;
+        const int d0 = c * 8, h = d0 / d.hd, Gall = d.n_heads / d.n_kv, G = (Gall + p.hsplit - 1) / p.hsplit;
         const int grp = (h / Gall) * p.hsplit + (h % Gall) / G, gi = (h % Gall) % G;
         const float* src = io.xpart + (long)grp * ATT_UN * MEGA_ATT_G * d.hd + (long)gi * d.hd + (d0 % d.hd);
         float4 a[ATT_UN], b[ATT_UN];
@@ -521,8 +521,7 @@ int mega_fill(MegaP& p, int sm_count) {
   if ((rc = mega_geometry(p.ph[PH_HEAD], d.hidden, d.vocab, false, d.vocab))) return rc;
   p.ph[PH_HEAD].tiles = cdiv(d.vocab, p.ph[PH_HEAD].R);
   const int G = d.n_heads / d.n_kv;
-  int hs = 1;
-  while (G / hs > MEGA_ATT_G || (G % hs) != 0) ++hs;
+  int hs = (G + MEGA_ATT_G - 1) / MEGA_ATT_G;  // <= MEGA_ATT_G q heads per CTA, uneven split allowed
   if (hs == 1 && G % 2 == 0 && G >= 4) hs = 2;
   p.hsplit = hs;
   p.attn_ctas = d.n_kv * hs * ATT_UN;
@@ -543,16 +542,32 @@ static int mega_chx(const MegaPhase& g) { return cdiv(cdiv(g.K >> 3, g.S), 32); 
 
 template <int CHH, int CHI, bool FLOW>
 static int mega_launch_f(const MegaP& p, int grid, size_t smem, cudaStream_t s) {
-  static bool set = false;
-  if (!set) {
+  // the function attributes are per device (a second engine on another GPU of the same process
+  // must opt in again)
+  static unsigned long long set_mask = 0ull;
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!(set_mask >> (dev & 63) & 1ull)) {
     B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024 - 2048));
     B200_CUDA(cudaFuncSetAttribute(k_mega<CHH, CHI, FLOW>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
-    set = true;
+    set_mask |= 1ull << (dev & 63);
   }
-  k_mega<CHH, CHI, FLOW><<<grid, MEGA_THREADS, smem, s>>>(p);
-  B200_CHECK_LAUNCH();
+  // COOPERATIVE launch: the software grid barrier needs every CTA resident at once; the driver
+  // refuses the launch (instead of letting it deadlock) if the grid cannot be co-resident, and
+  // never schedules it partially next to another kernel.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(MEGA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, k_mega<CHH, CHI, FLOW>, p));
   return B200_OK;
 }
 template <int CHH, int CHI>
@@ -573,6 +588,7 @@ int mega_launch(const MegaP& p, int sm_count, cudaStream_t s) {
   const int grid = sm_count;
   if (chh <= 2 && chi <= 2) return mega_launch_t<2, 2>(p, grid, smem, s);
   if (chh <= 6 && chi <= 10) return mega_launch_t<6, 10>(p, grid, smem, s);
+  if (chh <= 8 && chi <= 10) return mega_launch_t<8, 10>(p, grid, smem, s);  // Qwen2-VL-7B widths
   if (chh <= 10 && chi <= 10) return mega_launch_t<10, 10>(p, grid, smem, s);
   set_error("mega: unsupported widths (hidden chunks %d, inter chunks %d per lane)", chh, chi);
   return B200_ERR_INVALID;

@@ -308,7 +308,7 @@ __device__ __forceinline__ void pro_attn_slice(const MegaTcP& P, uint8_t* xop, c
     xop_zero_rows(xop, P.x_kstride, t.kb1 - t.kb0);
     const int c0 = t.kb0 * 8, c1 = min(t.kb1 * 8, g.K >> 3);
     for (int c = c0 + threadIdx.x; c < c1; c += 256) {
-      const int d0 = c * 8, h = d0 / d.hd, Gall = d.n_heads / d.n_kv, G = Gall / p.hsplit;
+      const int d0 = c * 8, h = d0 / d.hd, Gall = d.n_heads / d.n_kv, G = (Gall + p.hsplit - 1) / p.hsplit;
       const int grp = (h / Gall) * p.hsplit + (h % Gall) / G, gi = (h % Gall) % G;
       const float* src = p.att_part + (long)grp * ATT_UN * MEGA_ATT_G * d.hd + (long)gi * d.hd + (d0 % d.hd);
       const float4 sa = sum_parts4(src, (long)MEGA_ATT_G * d.hd, ATT_UN);
@@ -640,8 +640,7 @@ int mega_tc_fill(MegaTcP& P, int sm_count) {
                "mega_tc: dims must be multiples of 8");
   // attention geometry (same rules as k_mega)
   const int G = d.n_heads / d.n_kv;
-  int hs = 1;
-  while (G / hs > MEGA_ATT_G || (G % hs) != 0) ++hs;
+  int hs = (G + MEGA_ATT_G - 1) / MEGA_ATT_G;  // <= MEGA_ATT_G q heads per CTA, uneven split allowed
   if (hs == 1 && G % 2 == 0 && G >= 4) hs = 2;
   p.hsplit = hs;
   p.attn_ctas = d.n_kv * hs * ATT_UN;
@@ -671,16 +670,28 @@ int mega_tc_fill(MegaTcP& P, int sm_count) {
 }
 
 int mega_tc_launch(const MegaTcP& P, int sm_count, cudaStream_t s) {
-  static bool set = false;
-  if (!set) {
+  static unsigned long long set_mask = 0ull;  // per device
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!(set_mask >> (dev & 63) & 1ull)) {
     B200_CUDA(cudaFuncSetAttribute(k_mega_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    227 * 1024 - 2048));
     B200_CUDA(cudaFuncSetAttribute(k_mega_tc, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
-    set = true;
+    set_mask |= 1ull << (dev & 63);
   }
-  k_mega_tc<<<sm_count, MEGA_THREADS, P.smem_bytes, s>>>(P);
-  B200_CHECK_LAUNCH();
+  // cooperative launch: see decode_mega.cu::mega_launch_f
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(sm_count);
+  cfg.blockDim = dim3(MEGA_THREADS);
+  cfg.dynamicSmemBytes = P.smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, k_mega_tc, P));
   return B200_OK;
 }
 

@@ -227,14 +227,17 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
   constexpr int EPL = HD / 32, SEG = HD / 8, AG = MEGA_ATT_G, NV = SEG / 8, UNR = 2;
   const DecodeDims& d = p.d;
   const int Gall = d.n_heads / d.n_kv;
-  const int G = Gall / p.hsplit;
+  // q heads of a kv head are split over p.hsplit CTAs, Gc per CTA; the last part may hold fewer
+  // (Qwen2-VL-7B: 7 q heads per kv head -> 4 + 3)
+  const int Gc = (Gall + p.hsplit - 1) / p.hsplit;
   const int ucap = (d.cap + ATT_UN - 1) / ATT_UN;
   float* sc = scratch;                       // [AG][ucap]
   float* red = sc + (long)AG * ucap;         // [8][AG*HD]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = blockIdx.x / ATT_UN, unit = blockIdx.x % ATT_UN;
-  const int kvh = grp / p.hsplit;
-  const int h0 = kvh * Gall + (grp % p.hsplit) * G;
+  const int kvh = grp / p.hsplit, part = grp % p.hsplit;
+  const int G = min(Gc, Gall - part * Gc);
+  const int h0 = kvh * Gall + part * Gc;
   const bf16* kb = kc + (long)kvh * d.cap * HD;
   const bf16* vb = vc + (long)kvh * d.cap * HD;
   const int per = (nkeys + ATT_UN - 1) / ATT_UN;
@@ -344,7 +347,7 @@ __device__ __forceinline__ void attn_phase(const MegaP& p, const bf16* kc, const
       v[j + half] = o2;
     }
     cbar();
-    if (owner && (grp % p.hsplit) == 0) {  // append the new position to the cache (one CTA per kv head)
+    if (owner && part == 0) {  // append the new position to the cache (one CTA per kv head)
       bf16* kw = const_cast<bf16*>(kb) + (long)(nkeys - 1) * HD;
       bf16* vw = const_cast<bf16*>(vb) + (long)(nkeys - 1) * HD;
       for (int i = threadIdx.x; i < HD; i += 256) {

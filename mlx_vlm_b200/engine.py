@@ -89,11 +89,14 @@ class Engine:
 
     # -- kv ------------------------------------------------------------------
     def bind_pool(self, pool: KVPool):
-        key = (id(pool), pool.generation)
+        # keyed on the device buffer itself (not id(pool): CPython reuses ids of collected pools);
+        # the engine keeps a strong reference to the bound buffer so its address cannot be recycled
+        key = (pool.buf.data_ptr(), pool.batch, pool.capacity)
         if key != self._bound:
             N.check(self.lib.b200_engine_bind_kv(self.h, pool.buf.data_ptr(), pool.batch,
                                                  pool.capacity), "bind_kv")
             self._bound = key
+            self._bound_buf = pool.buf
 
     # -- calls ---------------------------------------------------------------
     def vision(self, pixel_values: torch.Tensor, grid_thw: np.ndarray) -> torch.Tensor:

@@ -157,25 +157,35 @@ def generate_step(
         yield from _greedy_device_loop(eng, lm, prompt_cache, max_tokens, reserve, return_logprobs)
         return
 
-    # ---- general path: host-visible logits, torch samplers ----
-    tokens: List[int] = []
-    logits = outputs.logits[:, -1, :]
-    n = 0
-    while True:
-        if processors:
+    # ---- general path: torch samplers / logits processors on the ENGINE's stream ----
+    # The engine enqueues its kernels and the logits copy on `eng.stream` (non-blocking); every
+    # torch op that touches those logits runs inside `torch.cuda.stream(eng.stream)` so it is
+    # stream-ordered after the step that produced them, and `.item()` synchronises that stream.
+    # The stream context never spans a `yield`.
+    # Token history of the processors (ar.py:357-361): the reference concatenates the ids fed to
+    # EVERY `_step`, so it starts with the prompt (its last chunk) and then holds each fed token.
+    tokens: List[int] = [int(t) for t in np.asarray(ids_host).reshape(-1)] if processors else []
+
+    def _sample(logits):
+        with torch.cuda.stream(eng.stream):
             for p in processors:
                 logits = p(tokens, logits)
-        lf = logits.float()
-        logprobs = (logits - torch.logsumexp(lf, dim=-1, keepdim=True).to(logits.dtype))
-        y = sampler(logprobs)
-        if n == max_tokens:
-            break
-        tok = int(y.reshape(-1)[0].item())
-        tokens.append(tok)
+            lf = logits.float()
+            logprobs = (logits - torch.logsumexp(lf, dim=-1, keepdim=True).to(logits.dtype))
+            y = sampler(logprobs)
+            tok = int(y.reshape(-1)[0].item())   # synchronises eng.stream
+        return tok, logprobs
+
+    logits = outputs.logits[:, -1, :]
+    n = 0
+    while n < max_tokens:
+        tok, logprobs = _sample(logits)
         yield tok, logprobs.squeeze(0)
         n += 1
         if n == max_tokens:
             break
+        if processors:
+            tokens.append(tok)
         outputs = lm(np.asarray([[tok]]), cache=prompt_cache, reserve_tokens=reserve)
         logits = outputs.logits[:, -1, :]
 

@@ -271,8 +271,10 @@ class BatchGenerator:
 
     # ------------------------------------------------------------------ device work
     def _logprob_of(self, tok: int) -> float:
-        lp = self.model.engine.snapshot("logprobs")
-        return float(lp.view(-1)[tok].float().item())
+        eng = self.model.engine
+        lp = eng.snapshot("logprobs")
+        with torch.cuda.stream(eng.stream):   # ordered after the snapshot copy; .item() syncs it
+            return float(lp.view(-1)[tok].float().item())
 
     def _prefill(self, row: _Row) -> PromptProgress:
         """Embeddings + prefill for one row; the fused head + sampler leave the first token in
@@ -315,11 +317,13 @@ class BatchGenerator:
                               prompt_tps=len(row.ids) / dt if dt > 0 else 0.0)
 
     def _sample(self, logits: torch.Tensor) -> Tuple[int, float]:
-        lf = logits.float()
-        logprobs = logits - torch.logsumexp(lf, dim=-1, keepdim=True).to(logits.dtype)
-        y = self.sampler(logprobs)
-        tok = int(y.reshape(-1)[0].item())
-        return tok, float(logprobs.reshape(-1)[tok].float().item())
+        # torch ops on the engine's stream: ordered after the step that wrote `logits`
+        with torch.cuda.stream(self.model.engine.stream):
+            lf = logits.float()
+            logprobs = logits - torch.logsumexp(lf, dim=-1, keepdim=True).to(logits.dtype)
+            y = self.sampler(logprobs)
+            tok = int(y.reshape(-1)[0].item())
+            return tok, float(logprobs.reshape(-1)[tok].float().item())
 
     def _decode_slice(self, row: _Row):
         """Refill the row's token buffer: hand the engine to this row for up to `decode_slice`
@@ -345,9 +349,9 @@ class BatchGenerator:
                      rope_deltas=np.asarray([[row.delta]]), reserve_tokens=row.reserve)
             if self.greedy_sampling:
                 lp = eng.snapshot("logprobs").view(-1)
-                eng.stream.synchronize()
-                tok = int(torch.argmax(lp.float()).item())
-                lpv = float(lp[tok].float().item())
+                with torch.cuda.stream(eng.stream):
+                    tok = int(torch.argmax(lp.float()).item())
+                    lpv = float(lp[tok].float().item())
             else:
                 tok, lpv = self._sample(out.logits[:, -1, :])
             row.buffer.append((tok, lpv))
