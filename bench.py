@@ -33,6 +33,10 @@ W_BYTES_2B = 3_087_428_608      # decode weight bytes / token (bf
 KV_BYTES_PER_POS = 28_672       # 2 (k,v) * 2 kv heads * 128 * 2 B * 28 layers
 
 
+# ViT + merge + LM prefill FLOPs of one C2 request (2*M*N*K per GEMM, 4*N^2*D attention)
+VIT_GFLOP, PREFILL_GFLOP_T272 = 790.7, 720.0
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -40,6 +44,41 @@ def _peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _tensor_peak():
+    """bf16 tensor peak for a kernel timed INSIDE a long step: the sustained cuBLAS figure."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+
+
+def _ncu_traffic():
+    """dram bytes (read + write) of ONE decode-kernel launch from the committed ncu capture
+    (profiles/decode_traffic.json: written by tools/ncu_traffic.py from an `ncu --set full` run)."""
+    p = os.path.join(ROOT, "profiles", "decode_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("dram_bytes"), d.get("source", "profiles/decode_traffic.json")
+    return None, "no ncu capture committed"
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    name = ln.split(":", 1)[1].strip()
+                    break
+            else:
+                name = "unknown"
+        return f"{name} ({os.cpu_count()} logical CPUs)"
+    except Exception:
+        return "unknown"
 
 
 class ClockSampler:
@@ -228,7 +267,7 @@ def main():
                 "data": "synthetic", "config": config,
                 "prefill_img_tokens_per_sec": len(vals) * 144 / sum(v["prefill_s"] for v in vals),
                 "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": vals[0]["cores"],
-                                 "kind": "port",
+                                 "kind": "port", "cpu": _cpu_model(),
                                  "sample": f"per step: C2 prompt ViT+prefill once, {n_dec} decode "
                                            "steps (oracle = CPU restatement of the reference's "
                                            "MLX-CPU path; mlx is not installable offline)"},
@@ -288,7 +327,7 @@ def main():
                              position_ids=emb.position_ids, rope_deltas=emb.rope_deltas,
                              logits_to_keep=1, reserve_tokens=T + N_OUT + 1)
         ev[1].record(eng.stream)
-        model.language_model.fused_greedy_decode(N_OUT, cache, reserve_tokens=T + N_OUT + 1)
+        model.language_model.fused_greedy_decode_n(N_OUT, cache, reserve_tokens=T + N_OUT + 1)
         ev[2].record(eng.stream)
         eng.stream.synchronize()
         return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
@@ -345,6 +384,9 @@ def main():
         dec_tps = world * K * N_OUT / (dec_ms / 1e3)
         img_tps = world * K * 144 / (pre_ms / 1e3)
         peak, peak_src = _peaks()
+        tpeak, tpeak_src = _tensor_peak()
+        traffic, traffic_src = _ncu_traffic()
+        pre_tflops = (VIT_GFLOP + PREFILL_GFLOP_T272) / (pre_ms / K)   # GFLOP / ms = TFLOP/s
         mean_ctx = T + N_OUT / 2
         bytes_per_step = W_BYTES_2B + KV_BYTES_PER_POS * mean_ctx
         step_ms = dec_ms / (K * N_OUT)
@@ -372,15 +414,26 @@ def main():
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_step,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_mega launch,
-                         # ncu --set full, profiles/r1_k_mega_ncu_full.txt (ctx ~280)
-                         "traffic": 3_095_604_000 + 4_354_816},
+                         "traffic": traffic, "traffic_source": traffic_src},
+            # the other half of the metric: ViT + merge + LM prefill (T=272) on the tensor cores
+            "roofline_prefill": {"kernels": "ViT (32 blocks) + merge + LM prefill (28 layers, T=272): "
+                                            "tcgen05 GEMMs + tcgen05 attention + row ops",
+                                 "bound": "tensor", "achieved": pre_tflops, "peak": tpeak,
+                                 "unit": "TFLOP/s", "frac": pre_tflops / tpeak, "peak_source": tpeak_src,
+                                 "algorithmic_gflop": VIT_GFLOP + PREFILL_GFLOP_T272},
+            "parity": {"per_op": "rel-L2 <= 1e-3 vs oracle on identical inputs (tests/test_kernels_gpu.py)",
+                       "integer": "bit-exact (merge indices, rope ids, cache offsets)",
+                       "e2e": "deep bf16 chain: |cuda-oracle| <= 1.5 x |oracle_bf16 - exact fp32| "
+                              "(tests/_util.cmp_noise; C2 as benched: tests/test_gate_gpu.py)",
+                       "oracle": "CPU restatement pinned on the reference's own source + HF fp32; "
+                                 "mlx rounding points unpinned (mlx not installable offline)"},
         }
         if not args.no_cpu_baseline and world == 1:
             W = _engine_weights_to_oracle(model, __import__("oracle.qwen2vl", fromlist=["x"]).qwen2_vl_2b())
             r = cpu_reference_run(W, 6)
             line["cpu_baseline"] = {
                 "value": r["decode_tps"], "unit": "tokens/s", "cores": r["cores"], "kind": "port",
+                "cpu": _cpu_model(),
                 "prefill_img_tokens_per_sec": r["img_tps"],
                 "sample": "same weights/prompt as the GPU run: ViT+merge+prefill (T=272) once, "
                           "6 decode steps, torch-CPU fp32 matmuls with bf16 rounding points "

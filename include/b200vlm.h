@@ -47,6 +47,14 @@ int b200_device_check(int device, int* sm_count);
 int b200_cast_f32_bf16(const float* src, void* dst, long n, void* stream);
 
 /* epilogues of b200_gemm_bf16_tn */
+/* gemm_wt output modes / finish_rows normalisation kinds */
+#define B200_WT_BF16 0    /* C[t][n] = epi(bf16(acc + bias)) (+ residual), bf16            */
+#define B200_WT_PARTIAL 1 /* fp32 split-K partial tiles P[split][t][n] (finish_rows adds them) */
+#define B200_WT_SWIGLU 2  /* W = [gate rows; up rows]: C[t][i] = silu(gate) * up, bf16     */
+#define B200_NORM_NONE 0
+#define B200_NORM_RMS 1   /* mx.fast.rms_norm   (language.py:139-140)                      */
+#define B200_NORM_LN 2    /* mx.fast.layer_norm (vision.py:180-181)                        */
+
 #define B200_EPI_NONE 0
 #define B200_EPI_GELU_FAST 1  /* nn.GELU(approx="fast")  vision.py:167          */
 #define B200_EPI_GELU_EXACT 2 /* nn.GELU()               vision.py:112          */
@@ -61,6 +69,23 @@ int b200_cast_f32_bf16(const float* src, void* dst, long n, void* stream);
 int b200_gemm_bf16_tn(const void* A, long lda, const void* W, const void* bias,
                       const void* residual, long ldr, void* C, long ldc,
                       int M, int N, int K, int epilogue, void* stream);
+
+/* The same Linear, weight-major (gemm_wt.cu): weight rows on the UMMA M side, TN tokens
+ * (16..256) on the N side, optional split-K.  mode B200_WT_BF16 as b200_gemm_bf16_tn;
+ * B200_WT_PARTIAL: fp32 tiles partial[split][T][N] (bias / residual applied by
+ * b200_finish_rows); B200_WT_SWIGLU: W = [gate; up] (N == 2*inter), C[T][inter] =
+ * swiglu (mlp.py:9-15, activations.py:8-10).  cfg4 = {TN, k-blocks per stage, stages,
+ * splits} or NULL / {0} for the automatic choice.  flags: debugging aids, pass 0. */
+int b200_gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual,
+                 long ldr, void* C, long ldc, float* partial, int T, int N, int K, int epilogue,
+                 int mode, int inter, const int* cfg4, unsigned flags, void* stream);
+int b200_gemm_wt_auto_config(int T, int N, int K, int mode, int inter, int* cfg4_out);
+/* h[t] = bf16(resid[t] + bf16(sum_s partial[s][t] + bias)), and xn[t] = the RMSNorm /
+ * LayerNorm of h[t] that the next block applies (language.py:139-148, vision.py:177-194):
+ * the split-K reduction, the residual add and the norm in ONE pass over the row. */
+int b200_finish_rows(const float* partial, int splits, const void* bias, const void* resid, long ldr,
+                     void* h_out, long ldh, int norm_kind, const void* norm_w, const void* norm_b,
+                     float eps, void* xn, long ldx, int T, int N, void* stream);
 
 /* mx.fast.layer_norm (vision.py:180-181,108) / mx.fast.rms_norm (language.py:128-131) */
 int b200_layer_norm(const void* x, const void* w, const void* b, void* y,
@@ -98,6 +123,17 @@ int b200_attention(const void* q, long q_tok_stride, long q_head_stride,
                    int causal, float scale, void* stream);
 
 /* swiglu (activations.py:8-10): out[r,i] = silu(gu[r,i]) * gu[r,I+i] */
+/* Pipelined SDPA (attention_fa.cu): same arithmetic as b200_attention, operands TMA-loaded.
+ * q must be PRE-SCALED (bf16(q * bf16(scale)): b200_vision_qkv_post / the engine's M-RoPE
+ * kernel do it); vt = V transposed, element (kv head, dim, key) at vt + kvh*vt_hs + d*vt_ds + key. */
+int b200_attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
+                      const void* vt, long vt_hs, long vt_ds, void* out, long o_ts, int n_heads,
+                      int n_kv, int hd, int Lq, int S, int causal, void* stream);
+/* vision tower after the qkv GEMM: 2-D rotary on q,k in place (vision.py:35-50), q pre-scaled
+ * by bf16(scale), V^T written to vt[head][dim][t_ld] (t_ld % 8 == 0, >= n_tok) */
+int b200_vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
+                         int hd, float scale, void* vt, int t_ld, void* stream);
+
 int b200_swiglu(const void* gate_up, void* out, int rows, int inter, void* stream);
 
 /* embed_tokens + merge_input_ids_with_image_features (qwen2_vl.py:48,78-148) for

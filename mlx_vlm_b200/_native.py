@@ -40,12 +40,17 @@ SIGNATURES = {
     "b200_device_check": (_I, [_I, C.POINTER(_I)]),
     "b200_cast_f32_bf16": (_I, [_P, _P, _L, _P]),
     "b200_gemm_bf16_tn": (_I, [_P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
+    "b200_gemm_wt": (_I, [_P, _L, _P, _P, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P, C.c_uint, _P]),
+    "b200_gemm_wt_auto_config": (_I, [_I, _I, _I, _I, _I, _P]),
+    "b200_finish_rows": (_I, [_P, _I, _P, _P, _L, _P, _L, _I, _P, _P, _F, _P, _L, _I, _I, _P]),
     "b200_layer_norm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "b200_rms_norm": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "b200_vision_rope": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "b200_mrope_kv_write": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200_attention": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _I, _I, _I,
                             _F, _P]),
+    "b200_attention_fa": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "b200_vision_qkv_post": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "b200_swiglu": (_I, [_P, _P, _I, _I, _P]),
     "b200_embed_merge": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "b200_engine_create": (_I, [C.POINTER(Qwen2VLConfig), _I, C.POINTER(_P)]),

@@ -129,13 +129,32 @@ int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, 
                 int hd, cudaStream_t st);
 int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
                    void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
-                   cudaStream_t st);
+                   cudaStream_t st, float q_scale = 0.f, void* vt = nullptr, int t_ld = 0);
+int vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads, int hd,
+                    float scale, void* vt, int t_ld, cudaStream_t st);
+bool attention_fa_supported(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
+                            const void* vt, long vt_hs, long vt_ds, const void* out, long o_ts, int hd);
+int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs, const void* vt,
+                 long vt_hs, long vt_ds, void* out, long o_ts, int n_heads, int n_kv, int hd, int Lq, int S,
+                 int causal, cudaStream_t st);
 int swiglu(const void* gu, void* out, int rows, int inter, cudaStream_t st);
 int embed_merge(const int* ids, int B, int T, const void* table, int hidden, const void* feats,
                 int n_feats, int image_token, int video_token, void* out, int* src_out,
                 cudaStream_t st);
 int gemm_bf16_tn(const void* A, long lda, const void* W, const void* bias, const void* residual,
                  long ldr, void* C, long ldc, int M, int N, int K, int epilogue, cudaStream_t st);
+// weight-major tcgen05 GEMM (gemm_wt.cu) + the row op that finishes its split-K partials
+struct WtConfig {
+  int TN, KS, stages, split;
+};
+void gemm_wt_auto(int T, int row_blocks, int K, bool allow_split, WtConfig* c, int sm_count);
+int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
+            void* C, long ldc, float* partial, int T, int N, int K, int epilogue, int mode, int inter,
+            const WtConfig& cfg, unsigned flags, cudaStream_t st);
+int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
+                long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn, long ldx,
+                int T, int N, cudaStream_t st);
+void gemm_wt_set_pdl(bool on);
 int attention(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
               const void* v, long v_ts, long v_hs, void* out, long o_ts, int n_heads, int n_kv,
               int hd, int Lq, int S, int causal, float scale, cudaStream_t st);

@@ -1,0 +1,717 @@
+// gemm_wt: the Linear layers of the prefill / vision / batched-decode paths as a WEIGHT-MAJOR
+// tcgen05 GEMM:   D[n, t] = sum_k W[n, k] * X[t, k]      (C[t, n] = D[n, t])
+//
+// Why weight-major ("swap AB"): the token count of this path is small and awkward for the
+// tensor core's M = 128 side (T = 272 -> 3 tiles, one of them 88 % padding; T = 576 -> 4.5
+// tiles; batched decode T <= 16), while the weight rows are many and regular.  So the
+// weight rows take the UMMA M side (128 rows per CTA, streamed exactly once per token tile)
+// and the tokens the N side, whose width TN is any multiple of 16 up to 256 and is chosen per
+// problem (T = 272 -> 2 x 144, T = 576 -> 3 x 192, decode batch -> 16): no padded MMA rows,
+// 2-3x less weight re-streaming than 128-row token tiles.
+//
+//   * TMA (cp.async.bulk.tensor, 128B swizzle) feeds a shared-memory ring of `n_stages` stages
+//     of KS k-blocks (64 columns each); one elected thread issues tcgen05.mma (fp32 accumulators
+//     in TMEM: 128 lanes = weight rows x TN columns = tokens);
+//   * programmatic dependent launch: the weight tiles of the first stages do not depend on the
+//     previous kernel and are requested BEFORE griddepcontrol.wait, so the cold-HBM latency of a
+//     layer's weights overlaps the previous kernel's tail; shared memory is kept <= 113 KB where
+//     that does not hurt so that two CTAs (of this or the next kernel) share an SM;
+//   * split-K over gridDim.z for the GEMMs with few weight rows and long K (o_proj, down, fc2):
+//     fp32 partial tiles, summed in a FIXED order by the row-op kernel that follows
+//     (finish_rows: bias + residual + RMSNorm / LayerNorm of the next block, fused);
+//   * epilogue: TMEM -> registers (lane = weight row) -> transposed through shared memory ->
+//     coalesced 16-byte rows of C (bias / GELU / residual), or SwiGLU of interleaved gate/up
+//     row blocks (64 + 64 rows per tile, two TMA boxes), or fp32 partial tiles.
+//
+// Replaces nn.Linear of the reference (models/qwen2_vl/vision.py:83-102,108-119,132-133,168-169;
+// language.py:52-55; mlp.py:9-15; activations.py:8-10).  Rounding points follow
+// oracle/mlx_semantics.py::linear (+ activations, residual add).
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int WT_ROWS = 128;        // weight rows per CTA (UMMA M)
+constexpr int WT_BK = 64;           // one k-block: 64 bf16 = 128 B = one swizzle row
+constexpr int WT_WBLK = WT_ROWS * 128;  // bytes of one weight k-block tile
+constexpr int WT_MAX_STAGES = 16;
+constexpr int WT_EPI_TOK = 64;      // tokens staged per epilogue pass
+
+struct WtParams {
+  const bf16* bias;
+  const bf16* residual;
+  bf16* C;
+  float* partial;
+  long ldc, ldr;
+  int T, N, K;
+  int TN, KS, n_stages;
+  int kb_per_split;
+  int epilogue, mode;
+  int inter;
+  unsigned flags;  // debug: 1 = no MMA (loads only), 2 = no loads (MMA on stale smem), 4 = no epilogue stores
+};
+
+__device__ __forceinline__ uint32_t w_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void w_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(w_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void w_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(w_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void w_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(w_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void w_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t addr = w_smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void w_tma_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                         int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(w_smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(w_smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void w_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void w_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// descriptors as (lo, hi) words: walking an operand is one 32-bit add per MMA
+__device__ __forceinline__ void w_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void w_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   w_smem_u32(bar))
+               : "memory");
+}
+// K-major, 128B swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint32_t w_desc_lo(uint32_t addr) {
+  return ((addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+constexpr uint32_t W_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+
+__device__ __forceinline__ void w_tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void w_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void w_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void w_ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 2)
+gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+               const WtParams p) {
+  extern __shared__ uint8_t wt_smem_raw[];
+  __shared__ uint64_t full_bar[WT_MAX_STAGES], empty_bar[WT_MAX_STAGES];
+  __shared__ uint64_t tmem_full;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wt_smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool swiglu = (p.mode == B200_WT_SWIGLU);
+  const int rb = blockIdx.x;
+  const int n0 = rb * (swiglu ? 64 : WT_ROWS);  // first output feature (SwiGLU: channel) of the tile
+  const int t0 = blockIdx.y * p.TN;
+  const int split = blockIdx.z;
+  const int kb_total = (p.K + WT_BK - 1) / WT_BK;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+  const int n_it = (kb1 - kb0 + p.KS - 1) / p.KS;
+  const int xblk = p.TN * 128;                      // bytes of one token k-block tile
+  const int stage_bytes = p.KS * (WT_WBLK + xblk);
+  const int NS = p.n_stages;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.TN) tmem_cols <<= 1;
+
+  w_pdl_launch();  // the next kernel may start its prologue / weight prefetch as SM resources free up
+
+  auto issue_w = [&](int it, int s) {
+    uint8_t* sW = ring + (long)s * stage_bytes;
+    const int cnt = min(p.KS, kb1 - kb0 - it * p.KS);
+    if (p.flags & 2u) {  // debug: no loads at all, the MMAs run on whatever the ring holds
+      w_mbar_arrive(&full_bar[s]);
+      return;
+    }
+    w_mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (WT_WBLK + xblk));
+    for (int j = 0; j < cnt; ++j) {
+      const int kc = (kb0 + it * p.KS + j) * WT_BK;
+      if (swiglu) {
+        w_tma_2d(sW + j * WT_WBLK, &tmW, &full_bar[s], kc, n0);
+        w_tma_2d(sW + j * WT_WBLK + 64 * 128, &tmW, &full_bar[s], kc, p.inter + n0);
+      } else {
+        w_tma_2d(sW + j * WT_WBLK, &tmW, &full_bar[s], kc, n0);
+      }
+    }
+  };
+  auto issue_x = [&](int it, int s) {
+    if (p.flags & 2u) return;
+    uint8_t* sX = ring + (long)s * stage_bytes + p.KS * WT_WBLK;
+    const int cnt = min(p.KS, kb1 - kb0 - it * p.KS);
+    for (int j = 0; j < cnt; ++j)
+      w_tma_2d(sX + j * xblk, &tmX, &full_bar[s], (kb0 + it * p.KS + j) * WT_BK, t0);
+  };
+
+  const int pre = n_it < NS ? n_it : NS;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    for (int s = 0; s < NS; ++s) {
+      w_mbar_init(&full_bar[s], 1);
+      w_mbar_init(&empty_bar[s], 1);
+    }
+    w_mbar_init(&tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // weights never depend on the previous kernel: request them before waiting for it
+    for (int it = 0; it < pre; ++it) issue_w(it, it);
+  }
+  if (warp == 2) {  // whole warp: tcgen05.alloc is .sync.aligned
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     w_smem_u32(&tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  w_fence_before();
+  __syncthreads();
+  w_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  w_pdl_wait();  // everything the previous kernels wrote (X, residual) is visible from here on
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int it = 0; it < pre; ++it) issue_x(it, it);
+      for (int it = pre; it < n_it; ++it) {
+        const int s = it % NS;
+        w_mbar_wait(&empty_bar[s], ((it / NS) & 1) ^ 1);
+        issue_w(it, s);
+        issue_x(it, s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      // D = f32, A = B = bf16, both K-major; M = 128 weight rows, N = TN tokens
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.TN >> 3) << 17) |
+                             ((uint32_t)(WT_ROWS >> 4) << 24);
+      uint32_t acc = 0;
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % NS;
+        w_mbar_wait(&full_bar[s], (it / NS) & 1);
+        w_fence_after();
+        if (!(p.flags & 1u)) {
+          const uint32_t w_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes));
+          const uint32_t x_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes + p.KS * WT_WBLK));
+          const int cnt = min(p.KS, kb1 - kb0 - it * p.KS);
+          for (int j = 0; j < cnt; ++j) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              w_umma(tmem_base, w_lo + (uint32_t)(j * (WT_WBLK >> 4) + kk * 2),
+                     x_lo + (uint32_t)(j * (xblk >> 4) + kk * 2), W_DESC_HI, idesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        w_commit(&empty_bar[s]);  // frees the ring slot when these MMAs retire
+      }
+      w_commit(&tmem_full);
+    }
+  }
+  __syncwarp();
+
+  // ===== epilogue (all 8 warps): warp w reads TMEM lane quarter w % 4, token half w / 4 =====
+  w_mbar_wait(&tmem_full, 0);
+  w_fence_after();
+  const int q = warp & 3, half = warp >> 2;
+  const int row = q * 32 + lane;  // weight row of the tile == TMEM lane
+  float bias_v = 0.f;
+  if (p.mode == B200_WT_BF16 && p.bias && n0 + row < p.N) bias_v = bf2f(p.bias[n0 + row]);
+  uint8_t* stg = ring;  // every TMA load has landed and every MMA has retired: the ring is free
+  const int tid = threadIdx.x;
+  for (int c0 = 0; c0 < p.TN; c0 += WT_EPI_TOK) {
+    const int cc = c0 + half * 32;
+    if (cc < p.TN && !(p.flags & 1u)) {
+      uint32_t a[32];
+      w_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, a);
+      if (p.mode == B200_WT_PARTIAL) {
+        float* sf = reinterpret_cast<float*>(stg);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sf[(half * 32 + j) * WT_ROWS + row] = __uint_as_float(a[j]);
+      } else {
+        bf16* sb = reinterpret_cast<bf16*>(stg);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = rbf(__uint_as_float(a[j]) + bias_v);
+          if (p.epilogue == B200_EPI_GELU_FAST) v = gelu_fast_bf(v);
+          else if (p.epilogue == B200_EPI_GELU_EXACT) v = gelu_exact_bf(v);
+          sb[(half * 32 + j) * WT_ROWS + row] = f2bf(v);
+        }
+      }
+    }
+    w_ebar();
+    if (!(p.flags & 4u)) {
+      if (p.mode == B200_WT_BF16) {
+        const bool vec_ok = ((p.N & 7) == 0) && ((p.ldc & 7) == 0) && (!p.residual || (p.ldr & 7) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = tid + 256 * u;
+          const int tl = idx >> 4, ch = idx & 15;
+          const int t = t0 + c0 + tl, n = n0 + ch * 8;
+          if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
+          const uint4 sv = *reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + ch * 8) * 2);
+          if (vec_ok) {
+            uint4 o = sv;
+            if (p.residual) {
+              float r[8], v[8];
+              unpack8(*reinterpret_cast<const uint4*>(p.residual + (long)t * p.ldr + n), r);
+              unpack8(sv, v);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = rbf(r[e] + v[e]);
+              o.x = pack2(v[0], v[1]); o.y = pack2(v[2], v[3]); o.z = pack2(v[4], v[5]); o.w = pack2(v[6], v[7]);
+            }
+            *reinterpret_cast<uint4*>(p.C + (long)t * p.ldc + n) = o;
+          } else {
+            float v[8];
+            unpack8(sv, v);
+            for (int e = 0; e < 8 && n + e < p.N; ++e) {
+              float o = v[e];
+              if (p.residual) o = rbf(bf2f(p.residual[(long)t * p.ldr + n + e]) + o);
+              p.C[(long)t * p.ldc + n + e] = f2bf(o);
+            }
+          }
+        }
+      } else if (p.mode == B200_WT_SWIGLU) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int idx = tid + 256 * u;
+          const int tl = idx >> 3, ch = idx & 7;
+          const int t = t0 + c0 + tl, i = n0 + ch * 8;
+          if (c0 + tl >= p.TN || t >= p.T || i >= p.inter) continue;
+          float g[8], uu[8], o[8];
+          unpack8(*reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + ch * 8) * 2), g);
+          unpack8(*reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + 64 + ch * 8) * 2), uu);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = swiglu_bf(g[e], uu[e]);
+          uint4 ov;
+          ov.x = pack2(o[0], o[1]); ov.y = pack2(o[2], o[3]); ov.z = pack2(o[4], o[5]); ov.w = pack2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(p.C + (long)t * p.ldc + i) = ov;
+        }
+      } else {  // fp32 partial tile -> P[split][t][n]
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = tid + 256 * u;
+          const int tl = idx >> 5, ch = idx & 31;
+          const int t = t0 + c0 + tl, n = n0 + ch * 4;
+          if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
+          const float4 v = *reinterpret_cast<const float4*>(stg + (tl * WT_ROWS + ch * 4) * 4);
+          float* dst = p.partial + ((long)split * p.T + t) * p.N + n;
+          if (n + 4 <= p.N && (p.N & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = v;
+          } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            for (int e = 0; e < 4 && n + e < p.N; ++e) dst[e] = vv[e];
+          }
+        }
+      }
+    }
+    w_ebar();
+  }
+  w_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    w_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finish_rows: h[t] = r(resid[t] + r(sum_s P[s][t] + bias)) and, fused, the normalisation that
+// the NEXT block applies to h (RMSNorm / LayerNorm with the oracle's rounding points).  One CTA
+// per token row; the split-K partials are added in split order (deterministic).
+// ---------------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_MAXV = 8;  // float4 vectors per thread: N <= 256 * 4 * 8 = 8192
+
+__device__ __forceinline__ float fin_block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < FIN_THREADS / 32; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finish_rows_kernel(const float* __restrict__ P, int S, const bf16* __restrict__ bias,
+                   const bf16* __restrict__ resid, long ldr, bf16* __restrict__ h_out, long ldh,
+                   int norm_kind, const bf16* __restrict__ nw, const bf16* __restrict__ nb, float eps,
+                   bf16* __restrict__ xn, long ldx, int T, int N) {
+  __shared__ float red[FIN_THREADS / 32];
+  w_pdl_launch();
+  w_pdl_wait();
+  const int t = blockIdx.x;
+  const int nv = N >> 2;
+  float4 h[FIN_MAXV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < FIN_MAXV; ++u) {
+    const int c = threadIdx.x + FIN_THREADS * u;
+    h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nv) {
+      float4 a = __ldcg(reinterpret_cast<const float4*>(P + (long)t * N + c * 4));
+      for (int s = 1; s < S; ++s) {
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(P + ((long)s * T + t) * N + c * 4));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (bias) {
+        float bb[4];
+        unpack4(*reinterpret_cast<const uint2*>(bias + c * 4), bb);
+        a.x += bb[0]; a.y += bb[1]; a.z += bb[2]; a.w += bb[3];
+      }
+      a.x = rbf(a.x); a.y = rbf(a.y); a.z = rbf(a.z); a.w = rbf(a.w);
+      if (resid) {
+        float rr[4];
+        unpack4(*reinterpret_cast<const uint2*>(resid + (long)t * ldr + c * 4), rr);
+        a.x = rbf(rr[0] + a.x); a.y = rbf(rr[1] + a.y); a.z = rbf(rr[2] + a.z); a.w = rbf(rr[3] + a.w);
+      }
+      h[u] = a;
+      if (h_out)
+        *reinterpret_cast<uint2*>(h_out + (long)t * ldh + c * 4) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+      s1 += (a.x + a.y) + (a.z + a.w);
+      s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+    }
+  }
+  if (norm_kind == B200_NORM_NONE) return;
+  if (norm_kind == B200_NORM_RMS) {
+    const float tot = fin_block_sum(s2, red);
+    const float rs = 1.0f / sqrtf(tot / (float)N + eps);
+#pragma unroll
+    for (int u = 0; u < FIN_MAXV; ++u) {
+      const int c = threadIdx.x + FIN_THREADS * u;
+      if (c < nv) {
+        float w[4];
+        unpack4(*reinterpret_cast<const uint2*>(nw + c * 4), w);
+        const float4 a = h[u];
+        *reinterpret_cast<uint2*>(xn + (long)t * ldx + c * 4) =
+            make_uint2(pack2(rbf(rbf(a.x * rs) * w[0]), rbf(rbf(a.y * rs) * w[1])),
+                       pack2(rbf(rbf(a.z * rs) * w[2]), rbf(rbf(a.w * rs) * w[3])));
+      }
+    }
+    return;
+  }
+  // LayerNorm: fp32 mean / variance (two passes over the registers), cast, * w, + b
+  const float mu = fin_block_sum(s1, red) / (float)N;
+  float v = 0.f;
+#pragma unroll
+  for (int u = 0; u < FIN_MAXV; ++u) {
+    const int c = threadIdx.x + FIN_THREADS * u;
+    if (c < nv) {
+      const float4 a = h[u];
+      const float d0 = a.x - mu, d1 = a.y - mu, d2 = a.z - mu, d3 = a.w - mu;
+      v += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  }
+  const float var = fin_block_sum(v, red) / (float)N;
+  const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+  for (int u = 0; u < FIN_MAXV; ++u) {
+    const int c = threadIdx.x + FIN_THREADS * u;
+    if (c < nv) {
+      const float4 a = h[u];
+      float o[4] = {rbf((a.x - mu) * rstd), rbf((a.y - mu) * rstd), rbf((a.z - mu) * rstd),
+                    rbf((a.w - mu) * rstd)};
+      if (nw) {
+        float w[4];
+        unpack4(*reinterpret_cast<const uint2*>(nw + c * 4), w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rbf(o[e] * w[e]);
+      }
+      if (nb) {
+        float b[4];
+        unpack4(*reinterpret_cast<const uint2*>(nb + c * 4), b);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rbf(o[e] + b[e]);
+      }
+      *reinterpret_cast<uint2*>(xn + (long)t * ldx + c * 4) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+    }
+  }
+}
+
+// ---- host: tensor maps ------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn wt_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+struct WtKey {
+  const void* ptr;
+  long ld;
+  int rows, k, box_rows;
+  bool operator==(const WtKey& o) const {
+    return ptr == o.ptr && ld == o.ld && rows == o.rows && k == o.k && box_rows == o.box_rows;
+  }
+};
+struct WtHash {
+  size_t operator()(const WtKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1000003u ^ std::hash<long>()(k.ld);
+    h = h * 1000003u ^ (size_t)k.rows;
+    h = h * 1000003u ^ (size_t)k.k;
+    h = h * 1000003u ^ (size_t)k.box_rows;
+    return h;
+  }
+};
+// 2-D K-major bf16 operand (rows x K, row pitch ld elements), box = box_rows x 64
+int wt_tmap(const void* ptr, long ld, int rows, int k, int box_rows, CUtensorMap* out) {
+  static std::unordered_map<WtKey, CUtensorMap, WtHash> cache;
+  static std::mutex mu;
+  WtKey key{ptr, ld, rows, k, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return B200_OK;
+    }
+  }
+  EncodeTiledFn enc = wt_get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return B200_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)WT_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p ld=%ld rows=%d k=%d box_rows=%d", (int)r, ptr,
+              ld, rows, k, box_rows);
+    return B200_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 16384) cache.clear();
+    cache[key] = tm;
+  }
+  *out = tm;
+  return B200_OK;
+}
+
+static bool g_wt_pdl = true;
+
+}  // namespace
+
+void gemm_wt_set_pdl(bool on) { g_wt_pdl = on; }
+
+static int round16(int x) { return (x + 15) & ~15; }
+
+// Tile / pipeline configuration for (T, rows, K).  `rows` = weight rows (SwiGLU: 2 * channels).
+//   TN: tokens per tile, balanced over ceil(T / 256) tiles;  KS: k-blocks per stage (2: 256 B of a
+//   weight row per request burst);  split: K splits so that ~one wave of CTAs exists;
+//   stages: as many as fit the shared-memory budget (<= 110 KB when 2 CTAs per SM pay off).
+void gemm_wt_auto(int T, int row_blocks, int K, bool allow_split, WtConfig* c, int sm_count) {
+  const int nt = cdiv(T, 256);
+  c->TN = round16(cdiv(T, nt));
+  if (c->TN > 256) c->TN = 256;
+  const int tok_tiles = cdiv(T, c->TN);
+  const int kb_total = cdiv(K, WT_BK);
+  const long base = (long)row_blocks * tok_tiles;
+  int split = 1;
+  if (allow_split && base < (long)sm_count * 3 / 4) {
+    split = (int)(sm_count / base);
+    const int max_by_k = kb_total / 8 > 0 ? kb_total / 8 : 1;  // at least 8 k-blocks per split
+    if (split > max_by_k) split = max_by_k;
+    if (split < 1) split = 1;
+  }
+  split = cdiv(kb_total, cdiv(kb_total, split));  // no empty split
+  c->split = split;
+  c->KS = 2;
+  const int stage = c->KS * (WT_WBLK + c->TN * 128);
+  // two CTAs per SM when several waves exist (one CTA's epilogue under the other's main loop)
+  const long ctas = base * split;
+  const int budget = (ctas > sm_count) ? 108 * 1024 : 208 * 1024;
+  int st = budget / stage;
+  if (st < 2) {  // large token tiles: fall back to one k-block per stage / one CTA per SM
+    c->KS = 1;
+    st = (208 * 1024) / (WT_WBLK + c->TN * 128);
+  }
+  if (st > 8) st = 8;
+  c->stages = st;
+}
+
+int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
+            void* C, long ldc, float* partial, int T, int N, int K, int epilogue, int mode, int inter,
+            const WtConfig& cfg, unsigned flags, cudaStream_t st) {
+  B200_REQUIRE(T > 0 && N > 0 && K > 0, "gemm_wt: empty problem T=%d N=%d K=%d", T, N, K);
+  B200_REQUIRE((ldx % 8) == 0 && (K % 8) == 0, "gemm_wt: ldx (%ld) and K (%d) must be multiples of 8", ldx, K);
+  B200_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm_wt: X and W must be 16-byte aligned");
+  B200_REQUIRE(cfg.TN >= 16 && cfg.TN <= 256 && (cfg.TN % 16) == 0, "gemm_wt: TN=%d", cfg.TN);
+  B200_REQUIRE(cfg.KS >= 1 && cfg.stages >= 2 && cfg.stages <= WT_MAX_STAGES && cfg.split >= 1,
+               "gemm_wt: bad config KS=%d stages=%d split=%d", cfg.KS, cfg.stages, cfg.split);
+  B200_REQUIRE(mode == B200_WT_BF16 || mode == B200_WT_PARTIAL || mode == B200_WT_SWIGLU, "gemm_wt: mode %d", mode);
+  B200_REQUIRE(mode != B200_WT_PARTIAL || partial, "gemm_wt: partial buffer missing");
+  B200_REQUIRE(mode == B200_WT_PARTIAL || cfg.split == 1, "gemm_wt: split-K needs the partial mode");
+  B200_REQUIRE(mode != B200_WT_SWIGLU || (inter > 0 && (inter % 8) == 0 && N == 2 * inter),
+               "gemm_wt: SwiGLU needs N == 2 * inter (inter %% 8 == 0)");
+  const int kb_total = cdiv(K, WT_BK);
+  WtParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = (const bf16*)bias; p.residual = (const bf16*)residual; p.C = (bf16*)C; p.partial = partial;
+  p.ldc = ldc; p.ldr = ldr; p.T = T; p.N = N; p.K = K;
+  p.TN = cfg.TN; p.KS = cfg.KS; p.n_stages = cfg.stages;
+  p.kb_per_split = cdiv(kb_total, cfg.split);
+  const int splits = cdiv(kb_total, p.kb_per_split);
+  B200_REQUIRE(splits == cfg.split, "gemm_wt: split %d leaves empty splits (%d k-blocks)", cfg.split, kb_total);
+  p.epilogue = epilogue; p.mode = mode; p.inter = inter; p.flags = flags;
+  const int stage = cfg.KS * (WT_WBLK + cfg.TN * 128);
+  const size_t smem = (size_t)cfg.stages * stage + 1024;
+  B200_REQUIRE(smem <= 227 * 1024 - 1024, "gemm_wt: %zu B of shared memory", smem);
+  B200_REQUIRE((size_t)cfg.stages * stage >= (size_t)WT_EPI_TOK * WT_ROWS * 4, "gemm_wt: ring smaller than the epilogue staging tile");
+  CUtensorMap tw, tx;
+  int rc = wt_tmap(W, (long)K, N, K, mode == B200_WT_SWIGLU ? 64 : WT_ROWS, &tw);
+  if (rc) return rc;
+  if ((rc = wt_tmap(X, ldx, T, K, cfg.TN, &tx))) return rc;
+  static unsigned long long set_mask = 0ull;
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (!(set_mask >> (dev & 63) & 1ull)) {
+    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    set_mask |= 1ull << (dev & 63);
+  }
+  const int row_blocks = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, WT_ROWS);
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(row_blocks, cdiv(T, cfg.TN), splits);
+  lc.blockDim = dim3(256);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = g_wt_pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&lc, gemm_wt_kernel, tw, tx, p));
+  return B200_OK;
+}
+
+int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
+                long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn, long ldx,
+                int T, int N, cudaStream_t st) {
+  B200_REQUIRE(P && S >= 1 && T > 0 && N > 0 && (N % 4) == 0 && N <= FIN_THREADS * 4 * FIN_MAXV,
+               "finish_rows: T=%d N=%d S=%d", T, N, S);
+  B200_REQUIRE(norm_kind == B200_NORM_NONE || (xn && (norm_kind != B200_NORM_RMS || nw)),
+               "finish_rows: norm output / weight missing");
+  B200_REQUIRE((ldr % 4) == 0 && (ldh % 4) == 0 && (ldx % 4) == 0, "finish_rows: strides must be multiples of 4");
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(T);
+  lc.blockDim = dim3(FIN_THREADS);
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = g_wt_pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&lc, finish_rows_kernel, P, S, (const bf16*)bias, (const bf16*)resid, ldr,
+                               (bf16*)h_out, ldh, norm_kind, (const bf16*)nw, (const bf16*)nb, eps,
+                               (bf16*)xn, ldx, T, N));
+  return B200_OK;
+}
+
+}  // namespace b200
+
+// ---- C ABI ------------------------------------------------------------------
+using namespace b200;
+extern "C" {
+
+/* explicit-configuration entry (benchmark sweeps, tests): cfg = {TN, KS, stages, split}; a 0 in
+ * cfg[0] asks for the automatic choice.  partial: fp32 [split][T][N] (mode B200_WT_PARTIAL). */
+int b200_gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual,
+                 long ldr, void* C, long ldc, float* partial, int T, int N, int K, int epilogue,
+                 int mode, int inter, const int* cfg4, unsigned flags, void* stream) {
+  WtConfig c;
+  if (cfg4 && cfg4[0] > 0) {
+    c.TN = cfg4[0]; c.KS = cfg4[1]; c.stages = cfg4[2]; c.split = cfg4[3];
+  } else {
+    const int rbs = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, 128);
+    gemm_wt_auto(T, rbs, K, mode == B200_WT_PARTIAL, &c, 148);
+  }
+  return gemm_wt(X, ldx, W, bias, residual, ldr, C, ldc, partial, T, N, K, epilogue, mode, inter, c,
+                 flags, (cudaStream_t)stream);
+}
+
+int b200_finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
+                     long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn,
+                     long ldx, int T, int N, void* stream) {
+  return finish_rows(P, S, bias, resid, ldr, h_out, ldh, norm_kind, nw, nb, eps, xn, ldx, T, N,
+                     (cudaStream_t)stream);
+}
+
+int b200_gemm_wt_auto_config(int T, int N, int K, int mode, int inter, int* cfg4_out) {
+  WtConfig c;
+  const int rbs = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, 128);
+  gemm_wt_auto(T, rbs, K, mode == B200_WT_PARTIAL, &c, 148);
+  cfg4_out[0] = c.TN; cfg4_out[1] = c.KS; cfg4_out[2] = c.stages; cfg4_out[3] = c.split;
+  return B200_OK;
+}
+}

@@ -145,7 +145,8 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
                                       const float* __restrict__ inv_freq,
                                       const int* __restrict__ axis_sel, bf16* __restrict__ kc,
                                       bf16* __restrict__ vc, int T, int ctx0, int cap, int n_heads,
-                                      int n_kv, int hd) {
+                                      int n_kv, int hd, float q_scale, bf16* __restrict__ vt,
+                                      int t_ld) {
   const int half = hd >> 1;
   const int slots = n_heads + 2 * n_kv;
   const long total = (long)T * slots * half;
@@ -163,6 +164,10 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
       bf16* dst = vc + ((long)kvh * cap + ctx0 + t) * hd;
       dst[j] = base[j];
       dst[j + half] = base[j + half];
+      if (vt) {  // V^T [kv head][dim][token] for the pipelined attention kernel (attention_fa.cu)
+        vt[((long)kvh * hd + j) * t_ld + t] = base[j];
+        vt[((long)kvh * hd + j + half) * t_ld + t] = base[j + half];
+      }
       continue;
     }
     const float ang = (float)pos3[axis_sel[j] * T + t] * inv_freq[j];
@@ -170,8 +175,9 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
     const float o1 = rbf(rbf(x1 * c) + rbf((-x2) * s));
     const float o2 = rbf(rbf(x2 * c) + rbf(x1 * s));
     if (slot < n_heads) {
-      base[j] = f2bf(o1);
-      base[j + half] = f2bf(o2);
+      // q_scale != 0: qs = bf16(q * bf16(scale)) of the SDPA is applied here (base.py:305-373)
+      base[j] = f2bf(q_scale != 0.f ? o1 * q_scale : o1);
+      base[j + half] = f2bf(q_scale != 0.f ? o2 * q_scale : o2);
     } else {
       const int kvh = slot - n_heads;
       bf16* dst = kc + ((long)kvh * cap + ctx0 + t) * hd;
@@ -307,12 +313,79 @@ int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, 
 
 int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
                    void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
-                   cudaStream_t st) {
+                   cudaStream_t st, float q_scale, void* vt, int t_ld) {
   B200_REQUIRE(T > 0 && ctx0 >= 0 && ctx0 + T <= cap, "mrope_kv_write: T=%d ctx0=%d cap=%d", T,
                ctx0, cap);
+  B200_REQUIRE(!vt || t_ld >= T, "mrope_kv_write: V^T pitch %d < T %d", t_ld, T);
   const long total = (long)T * (n_heads + 2 * n_kv) * (hd / 2);
   mrope_kv_write_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-      (bf16*)qkv, pos3, inv_freq, axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd);
+      (bf16*)qkv, pos3, inv_freq, axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd,
+      q_scale, (bf16*)vt, t_ld);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Vision tower, after the qkv GEMM: 2-D rotary on q and k in place (same arithmetic as
+// vision_rope_kernel), q pre-scaled for the SDPA (qs = bf16(q * bf16(scale))), and V written
+// TRANSPOSED ([head][dim][token], tokens contiguous) through a shared-memory tile: the
+// pipelined attention kernel loads Q, K and V^T with TMA and touches no operand with a thread.
+// grid (ceil(T / 32), heads), 256 threads.
+__global__ void vision_qkv_post_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos_hw,
+                                       const float* __restrict__ inv_freq, int T, int n_heads, int hd,
+                                       float scale_bf, bf16* __restrict__ vt, int t_ld) {
+  __shared__ bf16 tile[32][136];
+  const int t0 = blockIdx.x * 32, h = blockIdx.y;
+  const int half = hd >> 1, quarter = hd >> 2;
+  const long row = 3L * n_heads * hd;
+  for (int idx = threadIdx.x; idx < 32 * 2 * half; idx += blockDim.x) {
+    const int j = idx % half;
+    const int r = idx / half;
+    const int which = r & 1, t = t0 + (r >> 1);
+    if (t >= T) continue;
+    const int axis = (j < quarter) ? 0 : 1;
+    const float ang = (float)pos_hw[t * 2 + axis] * inv_freq[j - axis * quarter];
+    const float c = cosf(ang), sn = sinf(ang);
+    bf16* base = qkv + (long)t * row + ((long)which * n_heads + h) * hd;
+    const float x1 = bf2f(base[j]), x2 = bf2f(base[j + half]);
+    float o1 = rbf(__fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, sn)));
+    float o2 = rbf(__fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, sn)));
+    if (which == 0) {
+      o1 *= scale_bf;
+      o2 *= scale_bf;
+    }
+    base[j] = f2bf(o1);
+    base[j + half] = f2bf(o2);
+  }
+  const int nv = hd >> 3;
+  for (int idx = threadIdx.x; idx < 32 * nv; idx += blockDim.x) {
+    const int tl = idx / nv, c = idx % nv;
+    const int t = t0 + tl;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t < T) v = *reinterpret_cast<const uint4*>(qkv + (long)t * row + ((long)2 * n_heads + h) * hd + c * 8);
+    *reinterpret_cast<uint4*>(&tile[tl][c * 8]) = v;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < hd * 4; idx += blockDim.x) {
+    const int d = idx >> 2, ch = idx & 3;
+    if (t0 + ch * 8 >= t_ld) continue;
+    unsigned short e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = __bfloat16_as_ushort(tile[ch * 8 + u][d]);
+    uint4 o;
+    o.x = e[0] | ((uint32_t)e[1] << 16); o.y = e[2] | ((uint32_t)e[3] << 16);
+    o.z = e[4] | ((uint32_t)e[5] << 16); o.w = e[6] | ((uint32_t)e[7] << 16);
+    *reinterpret_cast<uint4*>(vt + ((long)h * hd + d) * t_ld + t0 + ch * 8) = o;
+  }
+}
+
+int vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads, int hd,
+                    float scale, void* vt, int t_ld, cudaStream_t st) {
+  B200_REQUIRE(n_tok > 0 && n_heads > 0 && (hd % 8) == 0 && hd <= 128 && (t_ld % 8) == 0 && t_ld >= n_tok,
+               "vision_qkv_post: bad shape (hd=%d t_ld=%d)", hd, t_ld);
+  const float scale_bf = __bfloat162float(__float2bfloat16_rn(scale));
+  vision_qkv_post_kernel<<<dim3(cdiv(n_tok, 32), n_heads), 256, 0, st>>>((bf16*)qkv, pos_hw, inv_freq, n_tok,
+                                                                       n_heads, hd, scale_bf, (bf16*)vt, t_ld);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -363,7 +436,11 @@ int b200_mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const
                         void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv,
                         int hd, void* st) {
   return mrope_kv_write(qkv, pos3, inv_freq, axis_sel, kc, vc, T, ctx0, cap, n_heads, n_kv, hd,
-                        (cudaStream_t)st);
+                        (cudaStream_t)st, 0.f, nullptr, 0);
+}
+int b200_vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
+                         int hd, float scale, void* vt, int t_ld, void* st) {
+  return vision_qkv_post(qkv, pos_hw, inv_freq, n_tok, n_heads, hd, scale, vt, t_ld, (cudaStream_t)st);
 }
 int b200_swiglu(const void* gu, void* out, int rows, int inter, void* st) {
   return swiglu(gu, out, rows, inter, (cudaStream_t)st);

@@ -149,6 +149,14 @@ class Engine:
     def logprobs_view(self) -> torch.Tensor:
         return self._view(self.lib.b200_engine_logprobs(self.h), self.cfg.vocab, torch.bfloat16)
 
+    def token_log_view(self) -> torch.Tensor:
+        """int32 view of the engine's device token ring (generated ids, index = token number % capacity)."""
+        return self._view(self.lib.b200_engine_token_log(self.h), self.token_log_capacity, torch.int32)
+
+    @property
+    def token_log_capacity(self) -> int:
+        return int(self.lib.b200_engine_token_log_capacity(self.h))
+
     def snapshot(self, which: str = "logprobs") -> torch.Tensor:
         """Stream-ordered copy of the current step's logits/logprobs vector."""
         src = (self.lib.b200_engine_logprobs if which == "logprobs"

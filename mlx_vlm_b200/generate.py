@@ -204,7 +204,7 @@ def _greedy_device_loop(eng, lm, prompt_cache, max_tokens, reserve, return_logpr
     while True:
         next_lp = None
         if n != max_tokens:
-            lm.fused_greedy_decode(1, prompt_cache, reserve_tokens=reserve)
+            lm.fused_greedy_decode_n(1, prompt_cache, reserve_tokens=reserve)
             next_lp = eng.snapshot("logprobs") if return_logprobs else None
             eng.fetch_tokens(base + n + 1, 1, host[n + 1:n + 2])
             events[n + 1].record(eng.stream)

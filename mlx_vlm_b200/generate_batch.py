@@ -337,7 +337,7 @@ class BatchGenerator:
             k = min(self.decode_slice, left)
             eng.set_next(row.last_token, ctx, ctx + row.delta)
             base = eng.tokens_launched
-            lm.fused_greedy_decode(k, row.cache, reserve_tokens=row.reserve)
+            lm.fused_greedy_decode_n(k, row.cache, reserve_tokens=row.reserve)
             host = _host_buf(k)
             eng.fetch_tokens(base, k, host)
             eng.stream.synchronize()

@@ -221,15 +221,61 @@ class LanguageModel:
         return position_ids, delta0
 
     # -------------------------------------------------- fused greedy decoding
-    def fused_greedy_decode(self, n_steps: int, cache, reserve_tokens: int = 0):
-        """The operator hook of the reference (ar.py:1015-1042 probes
-        `language_model.fused_greedy_decode`): run `n_steps` greedy decode steps
-        entirely on the device (token feedback through device memory, no host
-        round trip).  Tokens land in the engine's token log."""
+    def fused_greedy_decode(self, inputs, cache=None, **kwargs):
+        """The reference's operator hook, with its contract (generate/ar.py:1015-1042,
+        `GenerationBatch._fused_greedy_step`):
+
+            sampled = language_model.fused_greedy_decode(inputs[:, None], cache=prompt_cache,
+                                                         **fwd_kwargs)   # fwd_kwargs: rope_deltas
+
+        `inputs` (B, 1) token ids -> greedy token ids (B,) of the NEXT position as an int32 device
+        tensor (or None when this call cannot be served, which makes the reference fall back to
+        `__call__`).  One persistent-kernel launch: forward, logprobs and argmax never leave the
+        device.  When `inputs` is (a view of) the tensor this method returned last time (the
+        reference feeds `_next_tokens[:, None]` straight back), the token is already in the device
+        state and no host round trip happens at all."""
+        if cache is None or kwargs.get("logits_processors"):
+            return None
+        eng = self._engine()
+        last = getattr(self, "_fused_last", None)
+        chained = (last is not None and isinstance(inputs, torch.Tensor) and inputs.is_cuda
+                   and inputs.numel() == 1 and inputs.data_ptr() == last.data_ptr())
+        if not chained:
+            ids = _np(inputs)
+            if ids.ndim == 1:
+                ids = ids[:, None]
+            if ids.shape[1] != 1:
+                return None
+            if ids.shape[0] != 1:
+                return self._fused_greedy_batch(ids, cache, **kwargs)
+        rd = kwargs.get("rope_deltas", None)
+        if rd is not None:
+            self._rope_deltas = _np(rd)
+        off = int(cache[0].offset)
+        self._bind(cache, max(off + 1, int(kwargs.get("reserve_tokens", 0))))
+        if not chained:
+            delta = int(np.asarray(self._rope_deltas).reshape(-1)[0]) if self._rope_deltas is not None else 0
+            eng.set_next(int(ids[0, 0]), off, off + delta)
+        idx = eng.tokens_launched
+        eng.decode(1)
+        for c in cache:
+            c.offset += 1
+        out = eng.token_log_view()[idx % eng.token_log_capacity: idx % eng.token_log_capacity + 1]
+        self._fused_last = out
+        return out
+
+    def _fused_greedy_batch(self, ids, cache, **kwargs):
+        """B > 1: the lock-step batched decode engine (models/batch_decode.py)."""
+        return None
+
+    def fused_greedy_decode_n(self, n_steps: int, cache, reserve_tokens: int = 0):
+        """`n_steps` greedy decode steps entirely on the device (token feedback through device
+        memory, no host round trip between steps).  Tokens land in the engine's token log."""
         eng = self._engine()
         off = int(cache[0].offset)
         self._bind(cache, max(off + n_steps, reserve_tokens))
         eng.decode(n_steps)
+        self._fused_last = None
         for c in cache:
             c.offset += n_steps
 

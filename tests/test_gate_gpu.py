@@ -196,8 +196,11 @@ def test_logits_processors_and_sampler_path_on_gpu():
     samp = [t for t, _ in generate_step(ids, model, pvd, None, max_tokens=n, image_grid_thw=grid,
                                         temperature=0.7, top_k=1, seed=3)]
     assert samp == greedy, (samp, greedy)
-    got = [t for t, _ in generate_step(ids, model, pvd, None, max_tokens=n, image_grid_thw=grid,
-                                       repetition_penalty=1.6, repetition_context_size=20)]
+    got, got_lp = [], []
+    for t, lp_dev in generate_step(ids, model, pvd, None, max_tokens=n, image_grid_thw=grid,
+                                   repetition_penalty=1.6, repetition_context_size=20):
+        got.append(t)
+        got_lp.append(float(lp_dev.float()[t]))
     # CPU evaluation: oracle logits teacher-forced with the CUDA tokens; history = prompt + fed tokens
     R = O.Rounder("bf16")
     embeds, feats, pos, deltas = O.get_input_embeddings(c, W, ids, pv, grid, R)
@@ -206,13 +209,50 @@ def test_logits_processors_and_sampler_path_on_gpu():
     logits = O.lm_head(c, W, hidden[:, -1, :], R)
     proc = make_repetition_penalty(1.6, 20)
     hist = [int(t) for t in ids.reshape(-1)]
+    effect = 0.0
     for i, tok in enumerate(got):
         lg = proc(hist, logits.clone())
         lp = O.logprobs_from_logits(R, lg)
         assert _token_ok(tok, lp[0]), f"penalised token {i}: got {tok}, oracle argmax {int(lp[0].argmax())}"
+        want_lp = float(lp[0][tok])
+        assert abs(got_lp[i] - want_lp) <= 0.03 + 0.03 * abs(want_lp), (i, got_lp[i], want_lp)
+        effect = max(effect, abs(want_lp - float(O.logprobs_from_logits(R, logits)[0][tok])))
         hist.append(tok)
         e = W["language_model.model.embed_tokens.weight"][torch.tensor([tok])][:, None, :]
         p = O.decode_position_ids(cache[0].offset, deltas, 1)
         hidden = O.lm_layers_forward(c, W, e, p, cache, R)
         logits = O.lm_head(c, W, hidden[:, -1, :], R)
-    assert got != greedy or len(set(greedy)) == len(greedy), "the penalty should change a repeating sequence"
+    assert effect > 0.1, "the penalty (history = prompt + fed tokens) must have changed the logprobs"
+
+
+def test_fused_greedy_decode_hook_has_the_reference_contract():
+    """Drive the model exactly as `GenerationBatch._fused_greedy_step` does (ar.py:1015-1042):
+    `sampled = lm.fused_greedy_decode(inputs[:, None], cache=prompt_cache, **fwd_kwargs)` with
+    fwd_kwargs = {"rope_deltas": (B, 1)}; (B,) token ids come back; feeding them straight back in
+    is the steady state.  Tokens must equal the public generate_step's."""
+    from mlx_vlm_b200.generate import generate_step
+    from mlx_vlm_b200.models.cache import make_prompt_cache
+    c, W, model, req = _build("tiny", 12, (56, 56))
+    ids, pv, grid = req["input_ids"], req["pixel_values"], req["image_grid_thw"]
+    pvd = torch.from_numpy(pv).cuda()
+    lm, eng = model.language_model, model.engine
+    want = [t for t, _ in generate_step(ids, model, pvd, None, max_tokens=7, image_grid_thw=grid)]
+    cache = make_prompt_cache(lm)
+    emb = model.get_input_embeddings(ids, pvd, image_grid_thw=grid)
+    out = lm(ids, inputs_embeds=emb.inputs_embeds, cache=cache, position_ids=emb.position_ids,
+             rope_deltas=emb.rope_deltas)
+    eng.stream.synchronize()
+    # the token the fused head + sampler of the prefill call picked (bf16 logprobs, lowest index wins)
+    first = int(eng.token_log_view()[(eng.tokens_launched - 1) % eng.token_log_capacity])
+    assert first == want[0]
+    fwd_kwargs = {"rope_deltas": np.asarray(emb.rope_deltas)}
+    inputs = np.asarray([first])
+    got = [first]
+    for _ in range(6):
+        sampled = lm.fused_greedy_decode(inputs[:, None], cache=cache, **fwd_kwargs)
+        assert sampled is not None and tuple(sampled.shape) == (1,)
+        eng.stream.synchronize()
+        got.append(int(sampled[0]))
+        inputs = sampled          # the reference feeds `_next_tokens` straight back
+    assert got == want, (got, want)
+    assert cache[0].offset == ids.shape[1] + 6

@@ -20,7 +20,7 @@ cache = make_prompt_cache(model.language_model)
 emb = model.get_input_embeddings(ids, pvd, image_grid_thw=grid)
 model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache, position_ids=emb.position_ids,
                      rope_deltas=emb.rope_deltas, logits_to_keep=1, reserve_tokens=T + 600)
-model.language_model.fused_greedy_decode(200, cache, reserve_tokens=T + 600)
+model.language_model.fused_greedy_decode_n(200, cache, reserve_tokens=T + 600)
 eng.stream.synchronize()
 raw = np.zeros(2 * 1024 * 2 + 256, dtype=np.int64)
 buf = raw[:4096].reshape(2, 1024, 2)

@@ -20,6 +20,6 @@ for it in range(2):
     model.language_model(ids, inputs_embeds=emb.inputs_embeds, cache=cache, position_ids=emb.position_ids,
                          rope_deltas=emb.rope_deltas, logits_to_keep=1, reserve_tokens=T + 600)
     # put ~400 tokens of context in the cache first (fast), then the profiled steps
-    model.language_model.fused_greedy_decode(n_steps, cache, reserve_tokens=T + 600)
+    model.language_model.fused_greedy_decode_n(n_steps, cache, reserve_tokens=T + 600)
     eng.stream.synchronize()
 print("done", eng.launch_count)
