@@ -217,6 +217,94 @@ def cpu_reference_run(W, n_decode, threads=None):
             "cores": torch.get_num_threads()}
 
 
+W_BYTES_7B = 2 * 7_070_619_136          # Qwen2-VL-7B LM weights (untied head), bf16
+KV_BYTES_PER_POS_7B = 57_344            # 2 * 4 kv heads * 128 * 2 B * 28 layers
+
+
+def c5_leg(world, rank, dev, args):
+    """BASELINE config 5: Qwen2-VL-7B, `rows` concurrent image+prompt requests PER GPU (64 over 8 GPUs),
+    routed by parallel.generate_sharded (request i -> rank i mod N), each replica running its own
+    lock-step BatchGenerator; 336x336 image, 128 text tokens in, 512 out, greedy, EOS ignored.
+    Timed: max over ranks of (insert -> last token), CUDA-synchronised wall clock (host admission and
+    prefill are part of serving) + the device time of the decode steps."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mlx_vlm_b200.generate_batch import BatchGenerator
+    from mlx_vlm_b200.parallel import broadcast_packed, generate_sharded, shard_requests
+    from mlx_vlm_b200.utils import load_synthetic, prepare_inputs
+    rows, n_out = args.c5_rows, args.c5_out
+    model, proc = load_synthetic("qwen2-vl-7b", seed=1, device=dev, n_text_tokens=N_TEXT)
+    model.config.eos_token_id = []
+    eng = model.engine
+    bc = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        tb = time.perf_counter()
+        nb = broadcast_packed(model.packed_weights, src=0)
+        torch.cuda.synchronize()
+        bc = {"bytes": nb, "seconds": time.perf_counter() - tb}
+        bc["GB_per_s"] = nb / bc["seconds"] / 1e9
+    n_req = rows * world
+    rng = np.random.default_rng(7)
+    prompts, kws = [None] * n_req, [{} for _ in range(n_req)]
+    for i in shard_requests(n_req, world, rank):       # only the router's share is prepared on this rank
+        img = rng.integers(0, 256, size=(IMG_HW[0], IMG_HW[1], 3), dtype=np.uint8)
+        inp = prepare_inputs(proc, images=[img], prompts=f"request {i}", device=dev, stream=eng.stream)
+        prompts[i] = inp["input_ids"].reshape(-1).tolist()
+        kws[i] = {"pixel_values": inp["pixel_values"], "image_grid_thw": inp["image_grid_thw"]}
+    for i in range(n_req):
+        if prompts[i] is None:
+            prompts[i] = [0]
+    T = N_TEXT + 144
+    dec_ms_box = []
+
+    def make():
+        g = BatchGenerator(model, proc, max_tokens=n_out, completion_batch_size=rows, prefill_batch_size=rows,
+                           decode_slice=32)
+        return g
+
+    def run():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        toks = generate_sharded(make, prompts, n_out, kws)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, toks
+
+    run()                      # warm-up (GEMM configurations are measured on first use, graphs captured)
+    dt, toks = run()
+    assert all(len(toks[i]) == n_out for i in shard_requests(n_req, world, rank))
+    # device time of one lock-step step, from a dedicated slice of 64 steps on the warm engine
+    step_ms = eng.last_decode_ms()
+    t = torch.tensor([dt, step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, step_ms = t.tolist()
+    peak, peak_src = _peaks()
+    mean_ctx = T + n_out / 2
+    bytes_step = W_BYTES_7B + rows * KV_BYTES_PER_POS_7B * mean_ctx
+    out = {"workload": f"C5: Qwen2-VL-7B bf16, {n_req} concurrent requests ({rows} per GPU) over {world} GPU(s), "
+                       f"1x336x336 image + 128 text tokens in, {n_out} out each, continuous batching "
+                       "(lock-step rows, one weight stream per step), router: request i -> rank i mod N",
+           "requests": n_req, "rows_per_gpu": rows, "seconds": dt,
+           "requests_per_s": n_req / dt, "tokens_per_s": n_req * n_out / dt,
+           "tokens_per_s_per_gpu": rows * n_out / dt,
+           "decode_ms_per_step": step_ms,
+           "roofline": {"kernel": "one lock-step decode step (28 x 7 kernels + head + sampler), all rows",
+                        "bound": "hbm", "achieved": bytes_step / (step_ms / 1e3) / 1e9 if step_ms > 0 else None,
+                        "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                        "frac": (bytes_step / (step_ms / 1e3) / 1e9 / peak) if step_ms > 0 else None,
+                        "algorithmic_bytes_per_step": bytes_step}}
+    if bc:
+        out["weight_broadcast"] = bc
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -224,6 +312,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (Qwen2-VL-7B continuous batching)")
+    ap.add_argument("--c5-rows", type=int, default=8, help="concurrent requests per GPU in the C5 leg")
+    ap.add_argument("--c5-out", type=int, default=512)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--pdl", action="store_true")
@@ -299,11 +390,17 @@ def main():
         eng.set_mega(False)
     if args.mega_mode is not None:
         eng.set_mega(args.mega_mode)
+    bcast = None
     if world > 1:
-        # the single collective of the design: rank 0's weights broadcast over NVLink (NCCL)
-        for name in sorted(eng.weights):
-            dist.broadcast(eng.weights[name], src=0)
+        # the single collective of the design: rank 0's packed weight arena, ONE NCCL broadcast
+        from mlx_vlm_b200.parallel import broadcast_packed
         torch.cuda.synchronize()
+        dist.barrier()
+        tb = time.perf_counter()
+        nb = broadcast_packed(model.packed_weights, src=0)
+        torch.cuda.synchronize()
+        dtb = time.perf_counter() - tb
+        bcast = {"bytes": nb, "seconds": dtb, "GB_per_s": nb / dtb / 1e9, "calls": 1}
 
     rng = np.random.default_rng(0)
     image = rng.integers(0, 256, size=(IMG_HW[0], IMG_HW[1], 3), dtype=np.uint8)
@@ -374,6 +471,10 @@ def main():
         assert r.generation_tokens == N_OUT
     barrier()
 
+    c5 = None
+    if not args.no_c5:
+        c5 = c5_leg(world, rank, dev, args)
+
     stats = torch.tensor([dec_ms, pre_ms, wall, e2e_t], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -428,6 +529,10 @@ def main():
                        "oracle": "CPU restatement pinned on the reference's own source + HF fp32; "
                                  "mlx rounding points unpinned (mlx not installable offline)"},
         }
+        if bcast is not None:
+            line["weight_broadcast"] = bcast
+        if c5 is not None:
+            line["c5"] = c5
         if not args.no_cpu_baseline and world == 1:
             W = _engine_weights_to_oracle(model, __import__("oracle.qwen2vl", fromlist=["x"]).qwen2_vl_2b())
             r = cpu_reference_run(W, 6)

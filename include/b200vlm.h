@@ -248,6 +248,36 @@ int b200_engine_set_attn_cluster(b200_engine* e, int cluster);
  * copy n generated ids [start, start+n) of the token log to HOST (pinned) memory;
  * copy the current logits/logprobs vector into a caller buffer (device). */
 int b200_engine_fetch_tokens(b200_engine* e, long start, int n, int* host_out, void* stream);
+/* ------------------------------------------------------------------------- */
+/* Lock-step batched decode (continuous batching; generate/ar.py:929-1390        */
+/* GenerationBatch, models/cache.py:972-1201 BatchKVCache)                       */
+/* ------------------------------------------------------------------------- */
+/* The bound KV pool is (layers, 2, rows, kv heads, capacity, head_dim); every row keeps its own
+ * length (no left padding).  b200_engine_set_kv_row selects the row that b200_engine_prefill /
+ * b200_engine_decode read and write (admission of a request = a batch-1 prefill into a free row). */
+int b200_engine_set_kv_row(b200_engine* e, int row);
+/* (Re)arm rows 0..B-1: next input token, cached length, rope position (length + M-RoPE delta) and
+ * an active flag per row (host arrays).  B <= 16. */
+int b200_batch_begin(b200_engine* e, int B, const int* tok, const int* ctx, const int* pos,
+                     const int* active, void* stream);
+/* n lock-step steps (one captured graph per step: ~7 kernels per layer, the weights are streamed
+ * ONCE per step for all rows): greedy tokens + their bf16 logprobs go to a device log; the full
+ * logprob rows are written only when want_logprobs != 0.  This is what
+ * LanguageModel.fused_greedy_decode(inputs (B,1), cache=, rope_deltas=) runs (ar.py:1015-1042). */
+int b200_batch_decode(b200_engine* e, int n_steps, int want_logprobs, void* stream);
+/* tokens (and token logprobs) of steps [first_step, first_step+n) since the last begin:
+ * host arrays [n_steps][B] */
+int b200_batch_fetch(b200_engine* e, long first_step, int n_steps, int* tok_host, float* lp_host,
+                     void* stream);
+const void* b200_batch_logits(b200_engine* e);   /* device bf16 [B][vocab] of the last step */
+const void* b200_batch_logprobs(b200_engine* e); /* device bf16 [B][vocab] (want_logprobs)   */
+const int* b200_batch_token_log(b200_engine* e); /* device int32 [4096 steps][16 rows]        */
+/* BatchKVCache.filter / extend / extract (cache.py:1077-1201) on device pools: copy the first
+ * n_tokens positions of one row of a pool into a row of another (or the same) pool */
+int b200_kv_copy_row(void* dst_pool, int dst_batch, int dst_cap, int dst_row, const void* src_pool,
+                     int src_batch, int src_cap, int src_row, int n_layers, int n_kv, int hd,
+                     int n_tokens, void* stream);
+
 int b200_memcpy_d2d(void* dst, const void* src, long bytes, void* stream);
 int b200_memcpy_h2d(void* dst, const void* src_host, long bytes, void* stream);
 

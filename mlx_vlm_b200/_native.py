@@ -78,6 +78,14 @@ SIGNATURES = {
     "b200_engine_debug_buffer": (_I, [_P, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long)]),
     "b200_engine_device_error": (_I, [_P, C.POINTER(_I)]),
     "b200_engine_fetch_tokens": (_I, [_P, _L, _I, _P, _P]),
+    "b200_engine_set_kv_row": (_I, [_P, _I]),
+    "b200_batch_begin": (_I, [_P, _I, _P, _P, _P, _P, _P]),
+    "b200_batch_decode": (_I, [_P, _I, _I, _P]),
+    "b200_batch_fetch": (_I, [_P, _L, _I, _P, _P, _P]),
+    "b200_batch_logits": (_P, [_P]),
+    "b200_batch_logprobs": (_P, [_P]),
+    "b200_batch_token_log": (_P, [_P]),
+    "b200_kv_copy_row": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_memcpy_d2d": (_I, [_P, _P, _L, _P]),
     "b200_memcpy_h2d": (_I, [_P, _P, _L, _P]),
     "b200_engine_last_decode_ms": (_F, [_P]),

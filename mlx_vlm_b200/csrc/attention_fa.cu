@@ -37,6 +37,7 @@ struct FaParams {
   bf16* out;
   long o_ts;
   int n_heads, n_kv, hd, hdp, Lq, S, causal;
+  int q0, k0;  // token offsets of this segment inside the tensors the maps describe
 };
 
 struct FaBars {
@@ -181,19 +182,19 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       f_expect_tx(&bars.q_full, (uint32_t)kbq * FA_BLK);
-      for (int c = 0; c < kbq; ++c) f_tma_3d(Qs + c * FA_BLK, &tmQ, &bars.q_full, c * 64, h, row0);
+      for (int c = 0; c < kbq; ++c) f_tma_3d(Qs + c * FA_BLK, &tmQ, &bars.q_full, c * 64, h, p.q0 + row0);
       for (int i = 0; i < 2 * n_tiles; ++i) {
         const int j = i % n_tiles, s = i & 1;
         f_wait(&bars.k_empty[s], ((i >> 1) & 1) ^ 1);
         f_expect_tx(&bars.k_full[s], (uint32_t)kbq * FA_BLK);
         for (int c = 0; c < kbq; ++c)
-          f_tma_3d(Ks + s * 2 * FA_BLK + c * FA_BLK, &tmK, &bars.k_full[s], c * 64, kvh, j * FA_TK);
+          f_tma_3d(Ks + s * 2 * FA_BLK + c * FA_BLK, &tmK, &bars.k_full[s], c * 64, kvh, p.k0 + j * FA_TK);
         if (i >= n_tiles) {
           const int sv = j & 1;
           f_wait(&bars.v_empty[sv], ((j >> 1) & 1) ^ 1);
           f_expect_tx(&bars.v_full[sv], 2u * (uint32_t)vblk);
           for (int c = 0; c < 2; ++c)
-            f_tma_3d(Vs + sv * 2 * FA_BLK + c * vblk, &tmV, &bars.v_full[sv], j * FA_TK + c * 64, 0, kvh);
+            f_tma_3d(Vs + sv * 2 * FA_BLK + c * vblk, &tmV, &bars.v_full[sv], p.k0 + j * FA_TK + c * 64, 0, kvh);
         }
       }
     }
@@ -313,7 +314,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ---- epilogue: O row -> bf16 -> global (16-column chunks alternate between the row's two threads) ----
     f_wait(&bars.o_full, 0);
     f_fence_after();
-    bf16* orow = p.out + (long)qi * p.o_ts + (long)h * p.hd;
+    bf16* orow = p.out + (long)(p.q0 + qi) * p.o_ts + (long)h * p.hd;
     for (int c0 = 16 * half; c0 < p.hd; c0 += 32) {
       uint32_t r[16];
       f_tmem_ld16(t_row + 256u + (uint32_t)c0, r);
@@ -431,18 +432,22 @@ bool attention_fa_supported(const void* q, long q_ts, long q_hs, const void* k, 
 // q: PRE-SCALED queries (bf16(q * bf16(scale))), element (t, h, d) at q + t*q_ts + h*q_hs + d
 // k: keys, element (s, kvh, d) at k + s*k_ts + kvh*k_hs + d
 // vt: values transposed, element (kvh, d, s) at vt + kvh*vt_hs + d*vt_ds + s   (keys contiguous)
+// The tensors hold q_tot query tokens / k_tot keys; this call attends queries [q0, q0+Lq) to keys
+// [k0, k0+S) (one vision segment, or the whole prompt); out row t is written at out + t*o_ts.
 int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs, const void* vt,
                  long vt_hs, long vt_ds, void* out, long o_ts, int n_heads, int n_kv, int hd, int Lq, int S,
-                 int causal, cudaStream_t st) {
+                 int causal, cudaStream_t st, int q0, int q_tot, int k0, int k_tot) {
+  if (q_tot <= 0) q_tot = q0 + Lq;
+  if (k_tot <= 0) k_tot = k0 + S;
   B200_REQUIRE(attention_fa_supported(q, q_ts, q_hs, k, k_ts, k_hs, vt, vt_hs, vt_ds, out, o_ts, hd),
                "attention_fa: unsupported layout (hd=%d)", hd);
   B200_REQUIRE(Lq > 0 && S > 0 && n_heads % n_kv == 0, "attention_fa: bad shape");
   const int hdp = (hd + 15) & ~15;
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = fa_tmap3(q, hd, n_heads, q_hs, Lq, q_ts, 64, 1, FA_TQ, &tq))) return rc;
-  if ((rc = fa_tmap3(k, hd, n_kv, k_hs, S, k_ts, 64, 1, FA_TK, &tk))) return rc;
-  if ((rc = fa_tmap3(vt, S, hd, vt_ds, n_kv, vt_hs, 64, hdp, 1, &tv))) return rc;
+  if ((rc = fa_tmap3(q, hd, n_heads, q_hs, q_tot, q_ts, 64, 1, FA_TQ, &tq))) return rc;
+  if ((rc = fa_tmap3(k, hd, n_kv, k_hs, k_tot, k_ts, 64, 1, FA_TK, &tk))) return rc;
+  if ((rc = fa_tmap3(vt, k_tot, hd, vt_ds, n_kv, vt_hs, 64, hdp, 1, &tv))) return rc;
   static unsigned long long set_mask = 0ull;
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
@@ -453,7 +458,7 @@ int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, 
   }
   FaParams p;
   p.out = (bf16*)out; p.o_ts = o_ts; p.n_heads = n_heads; p.n_kv = n_kv; p.hd = hd; p.hdp = hdp;
-  p.Lq = Lq; p.S = S; p.causal = causal;
+  p.Lq = Lq; p.S = S; p.causal = causal; p.q0 = q0; p.k0 = k0;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(cdiv(Lq, FA_TQ), n_heads);
   lc.blockDim = dim3(FA_THREADS);
@@ -474,5 +479,5 @@ extern "C" int b200_attention_fa(const void* q, long q_ts, long q_hs, const void
                                  const void* vt, long vt_hs, long vt_ds, void* out, long o_ts, int n_heads,
                                  int n_kv, int hd, int Lq, int S, int causal, void* stream) {
   return b200::attention_fa(q, q_ts, q_hs, k, k_ts, k_hs, vt, vt_hs, vt_ds, out, o_ts, n_heads, n_kv, hd, Lq, S,
-                            causal, (cudaStream_t)stream);
+                            causal, (cudaStream_t)stream, 0, Lq, 0, S);
 }

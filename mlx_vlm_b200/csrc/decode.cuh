@@ -101,6 +101,25 @@ size_t mega_tc_packed_bytes(int N, int K, bool interleave);
 int mega_tc_pack(const bf16* src, const bf16* src2, int N, int K, bool interleave, void* dst,
                  cudaStream_t s);
 
+// lock-step batched decode (decode_batch.cu)
+struct BdModel {
+  DecodeDims d;
+  int n_layers;
+  const LayerW* layers;
+  const bf16 *embed, *head, *final_norm;
+  const float* inv_freq;
+  bf16* kv;            // layer 0 K plane of row 0
+  long layer_stride, v_off, row_stride;
+  int kv_batch, sm_count;
+};
+int batch_decoder_begin(void** handle, const BdModel& m, int B, const int* tok, const int* ctx, const int* pos,
+                        const int* active, cudaStream_t s);
+int batch_decoder_step(void* handle, const BdModel& m, int n_steps, bool want_logprobs, cudaStream_t s,
+                       cudaStream_t cap_stream, long* launches);
+int batch_decoder_fetch(void* handle, long first_step, int n_steps, int* tok_host, float* lp_host, cudaStream_t s);
+const void* batch_decoder_buffer(void* handle, int which);
+void batch_decoder_destroy(void* handle);
+
 void decode_set_sm_count(int n);
 void decode_set_pdl(bool on);
 int decode_prepare(const DecodeDims& d, int cluster);
@@ -136,7 +155,7 @@ bool attention_fa_supported(const void* q, long q_ts, long q_hs, const void* k, 
                             const void* vt, long vt_hs, long vt_ds, const void* out, long o_ts, int hd);
 int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs, const void* vt,
                  long vt_hs, long vt_ds, void* out, long o_ts, int n_heads, int n_kv, int hd, int Lq, int S,
-                 int causal, cudaStream_t st);
+                 int causal, cudaStream_t st, int q0 = 0, int q_tot = 0, int k0 = 0, int k_tot = 0);
 int swiglu(const void* gu, void* out, int rows, int inter, cudaStream_t st);
 int embed_merge(const int* ids, int B, int T, const void* table, int hidden, const void* feats,
                 int n_feats, int image_token, int video_token, void* out, int* src_out,
@@ -151,6 +170,9 @@ void gemm_wt_auto(int T, int row_blocks, int K, bool allow_split, WtConfig* c, i
 int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
             void* C, long ldc, float* partial, int T, int N, int K, int epilogue, int mode, int inter,
             const WtConfig& cfg, unsigned flags, cudaStream_t st);
+int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
+                  void* C, long ldc, float* partial, long partial_bytes, int T, int N, int K, int epilogue,
+                  int mode, int inter, bool allow_split, int sm_count, int* split_out, cudaStream_t st);
 int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
                 long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn, long ldx,
                 int T, int N, cudaStream_t st);

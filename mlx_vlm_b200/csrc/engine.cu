@@ -52,6 +52,9 @@ struct b200_engine {
   // kv pool (caller-owned)
   bf16* kv = nullptr;
   int kv_batch = 0, kv_cap = 0;
+  int kv_row = 0;        // row of the pool that prefill / single-row decode read and write
+  void* batch = nullptr; // lock-step batched decoder (decode_batch.cu)
+  std::vector<int> b_ctx, b_active;  // host mirrors of the batched rows' lengths
   // engine-owned small device buffers
   DecState* st = nullptr;
   bf16 *h = nullptr, *qbuf = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr,
@@ -62,6 +65,10 @@ struct b200_engine {
   int* axis_sel = nullptr;
   int* pos_hw = nullptr;
   long pos_hw_cap = 0;
+  int* pos_hw_host = nullptr;   // pinned staging of the rot_pos_emb ids (no stream sync per call)
+  long pos_hw_host_cap = 0;
+  cudaEvent_t pos_ev = nullptr;
+  bool v2 = true;               // weight-major GEMMs + pipelined attention (B200_PREFILL_V1=1: round-1 path)
   int log_cap = 1 << 16;
   // host mirrors of the decode state
   int ctx_host = 0, pos_host = 0;
@@ -201,7 +208,7 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
   p.final_norm = e->norm; p.head = e->head; p.embed = e->embed;
   p.h = e->h; p.qbuf = e->qbuf; p.attn = e->attn; p.act = e->act;
   p.logits = e->logits; p.logprobs = e->logprobs;
-  p.kv = e->kptr(0, 0);
+  p.kv = e->kptr(0, e->kv_row);
   p.kv_layer_stride = 2L * e->kv_batch * c.n_kv_heads * (long)e->kv_cap * c.head_dim;
   p.kv_v_offset = (long)e->kv_batch * c.n_kv_heads * (long)e->kv_cap * c.head_dim;
   p.partials = e->partials; p.st = e->st; p.token_log = e->token_log; p.log_cap = e->log_cap;
@@ -296,8 +303,8 @@ static int enqueue_step(b200_engine* e, cudaStream_t s) {
   if (e->active_mega()) return mega_launch(e->mp, e->sm_count, s);
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerW& lw = e->layers[l];
-    bf16* kc = e->kptr(l, 0);
-    bf16* vc = e->vptr(l, 0);
+    bf16* kc = e->kptr(l, e->kv_row);
+    bf16* vc = e->vptr(l, e->kv_row);
     if ((rc = launch_qkv(d, lw, e->h, e->qbuf, kc, vc, e->st, e->lm_inv_freq, s))) return rc;
     if ((rc = launch_attn(d, e->qbuf, kc, vc, e->attn, e->st, e->attn_cluster, s))) return rc;
     if ((rc = launch_res(lw.wo, e->attn, e->h, c.hidden, c.n_heads * c.head_dim, s))) return rc;
@@ -313,6 +320,217 @@ static int enqueue_step(b200_engine* e, cudaStream_t s) {
 
 static int kernels_per_step(const b200_engine* e) {
   return e->active_mega() ? 1 : e->cfg.n_layers * 5 + 2;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// round-2 prefill / vision path: weight-major GEMMs (gemm_wt.cu), split-K partials finished by
+// finish_rows (bias + residual + the NEXT norm fused), pipelined attention (attention_fa.cu)
+// ---------------------------------------------------------------------------------------------
+static long align256(long x) { return (x + 255) & ~255L; }
+static const long WT_PARTIAL_BYTES = 48L << 20;  // fp32 split-K partial tiles (bounded: see gemm_wt_auto)
+static long round8(long x) { return (x + 7) & ~7L; }
+static float* ws_partial(b200_engine* e) {
+  return reinterpret_cast<float*>(e->ws + ((e->ws_bytes - WT_PARTIAL_BYTES - 2048) & ~255L));
+}
+
+// y = epi(bf16(x . W^T + b))
+static int v2_linear(b200_engine* e, const bf16* x, long ldx, const bf16* W, const bf16* b, bf16* y, long ldy,
+                     int T, int N, int K, int epi, cudaStream_t s) {
+  e->launches += 1;
+  return gemm_wt_tuned(x, ldx, W, b, nullptr, 0, y, ldy, nullptr, 0, T, N, K, epi, B200_WT_BF16, 0, false,
+                       e->sm_count, nullptr, s);
+}
+
+// h = bf16(h + bf16(x . W^T + b)); xn = norm(h)   (split-K GEMM + one finishing row op)
+static int v2_linear_residual_norm(b200_engine* e, const bf16* x, long ldx, const bf16* W, const bf16* b,
+                                   bf16* h, long ldh, int norm_kind, const bf16* nw, const bf16* nb, float eps,
+                                   bf16* xn, long ldxn, int T, int N, int K, cudaStream_t s) {
+  float* P = ws_partial(e);
+  int split = 1;
+  int rc = gemm_wt_tuned(x, ldx, W, nullptr, nullptr, 0, nullptr, 0, P, WT_PARTIAL_BYTES, T, N, K, B200_EPI_NONE,
+                         B200_WT_PARTIAL, 0, true, e->sm_count, &split, s);
+  if (rc) return rc;
+  e->launches += 2;
+  return finish_rows(P, split, b, h, ldh, h, ldh, norm_kind, nw, nb, eps, xn, ldxn, T, N, s);
+}
+
+static int v2_upload_pos(b200_engine* e, const std::vector<int>& pos, cudaStream_t s) {
+  const long n = (long)pos.size();
+  if (n > e->pos_hw_cap) {
+    if (e->pos_hw) B200_CUDA(cudaFree(e->pos_hw));
+    B200_CUDA(cudaMalloc(&e->pos_hw, n * 4));
+    e->pos_hw_cap = n;
+  }
+  if (!e->pos_ev) B200_CUDA(cudaEventCreateWithFlags(&e->pos_ev, cudaEventDisableTiming));
+  else B200_CUDA(cudaEventSynchronize(e->pos_ev));  // the previous call's copy has long finished
+  if (n > e->pos_hw_host_cap) {
+    if (e->pos_hw_host) B200_CUDA(cudaFreeHost(e->pos_hw_host));
+    B200_CUDA(cudaMallocHost(&e->pos_hw_host, n * 4));
+    e->pos_hw_host_cap = n;
+  }
+  memcpy(e->pos_hw_host, pos.data(), n * 4);
+  B200_CUDA(cudaMemcpyAsync(e->pos_hw, e->pos_hw_host, n * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaEventRecord(e->pos_ev, s));
+  return B200_OK;
+}
+
+// rot_pos_emb ids (vision.py:219-249), host side, merge-group-major order
+static void build_pos_hw(const int* grid, int n_img, int ms, std::vector<int>* out) {
+  out->clear();
+  for (int i = 0; i < n_img; ++i) {
+    const int t = grid[i * 3], h = grid[i * 3 + 1], w = grid[i * 3 + 2];
+    for (int tt = 0; tt < t; ++tt)
+      for (int bh = 0; bh < h / ms; ++bh)
+        for (int bw = 0; bw < w / ms; ++bw)
+          for (int ih = 0; ih < ms; ++ih)
+            for (int iw = 0; iw < ms; ++iw) {
+              out->push_back(bh * ms + ih);
+              out->push_back(bw * ms + iw);
+            }
+  }
+}
+
+
+static int vision_v2(b200_engine* e, const float* pixel_values, const int* grid, int n_images, long N,
+                     void* feats_out, cudaStream_t s) {
+  const auto& c = e->cfg;
+  const long E = c.v_embed, Em = c.v_mlp;
+  const int nh = c.v_heads, hd = c.v_embed / c.v_heads;
+  const int t_ld = (int)round8(N);
+  uint8_t* p = e->ws;
+  bf16* x = (bf16*)p; p += align256(N * (long)c.v_patch_dim * 2);
+  bf16* h = (bf16*)p; p += align256(N * E * 2);
+  bf16* y = (bf16*)p; p += align256(N * E * 2);
+  bf16* qkv = (bf16*)p; p += align256(N * 3 * E * 2);
+  bf16* mlp = (bf16*)p; p += align256(N * Em * 2);
+  bf16* att = (bf16*)p; p += align256(N * E * 2);
+  bf16* vt = (bf16*)p; p += align256(E * (long)t_ld * 2);
+  int rc;
+  std::vector<int> pos;
+  build_pos_hw(grid, n_images, c.v_merge, &pos);
+  if ((rc = v2_upload_pos(e, pos, s))) return rc;
+  if ((rc = cast_f32_bf16(pixel_values, x, N * c.v_patch_dim, s))) return rc;
+  if ((rc = v2_linear(e, x, c.v_patch_dim, e->v_patch, nullptr, h, E, (int)N, (int)E, c.v_patch_dim, B200_EPI_NONE, s)))
+    return rc;
+  if ((rc = layer_norm(h, e->vblk[0].ln1w, e->vblk[0].ln1b, y, (int)N, (int)E, c.v_ln_eps, s))) return rc;
+  e->launches += 2;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const bool fa = attention_fa_supported(qkv, 3 * E, hd, qkv + E, 3 * E, hd, vt, (long)hd * t_ld, t_ld, att, E, hd);
+  for (int i = 0; i < c.v_depth; ++i) {
+    const VBlk& b = e->vblk[i];
+    if ((rc = v2_linear(e, y, E, b.qkvw, b.qkvb, qkv, 3 * E, (int)N, (int)(3 * E), (int)E, B200_EPI_NONE, s))) return rc;
+    if (fa) {
+      if ((rc = vision_qkv_post(qkv, e->pos_hw, e->v_inv_freq, (int)N, nh, hd, scale, vt, t_ld, s))) return rc;
+    } else {
+      if ((rc = vision_rope(qkv, e->pos_hw, e->v_inv_freq, (int)N, nh, hd, s))) return rc;
+    }
+    e->launches += 1;
+    long off = 0;
+    for (int im = 0; im < n_images; ++im) {
+      const int t = grid[im * 3];
+      const int seg = grid[im * 3 + 1] * grid[im * 3 + 2];
+      for (int tt = 0; tt < t; ++tt) {  // one attention segment per frame (vision.py:270-281)
+        if (fa) {
+          rc = attention_fa(qkv, 3 * E, hd, qkv + E, 3 * E, hd, vt, (long)hd * t_ld, t_ld, att, E, nh, nh, hd, seg,
+                            seg, 0, s, (int)off, (int)N, (int)off, (int)N);
+        } else {
+          const bf16* qb = qkv + off * 3 * E;
+          rc = attention(qb, 3 * E, hd, qb + E, 3 * E, hd, qb + 2 * E, 3 * E, hd, att + off * E, E, nh, nh, hd,
+                         seg, seg, 0, scale, s);
+        }
+        if (rc) return rc;
+        off += seg;
+        e->launches += 1;
+      }
+    }
+    if ((rc = v2_linear_residual_norm(e, att, E, b.projw, b.projb, h, E, B200_NORM_LN, b.ln2w, b.ln2b, c.v_ln_eps,
+                                      y, E, (int)N, (int)E, (int)E, s)))
+      return rc;
+    if ((rc = v2_linear(e, y, E, b.fc1w, b.fc1b, mlp, Em, (int)N, (int)Em, (int)E, B200_EPI_GELU_FAST, s))) return rc;
+    const bool last = (i + 1 == c.v_depth);
+    const bf16* nw = last ? e->m_lnw : e->vblk[i + 1].ln1w;
+    const bf16* nb = last ? e->m_lnb : e->vblk[i + 1].ln1b;
+    if ((rc = v2_linear_residual_norm(e, mlp, Em, b.fc2w, b.fc2b, h, E, B200_NORM_LN, nw, nb,
+                                      last ? 1e-6f : c.v_ln_eps, y, E, (int)N, (int)E, (int)Em, s)))
+      return rc;
+  }
+  // PatchMerger (vision.py:105-120): y already holds LayerNorm(h) of the last block
+  const long mg = (long)c.v_merge * c.v_merge * E;
+  const long Nm = N / ((long)c.v_merge * c.v_merge);
+  if ((rc = v2_linear(e, y, mg, e->m_fc1w, e->m_fc1b, mlp, mg, (int)Nm, (int)mg, (int)mg, B200_EPI_GELU_EXACT, s)))
+    return rc;
+  if ((rc = v2_linear(e, mlp, mg, e->m_fc2w, e->m_fc2b, (bf16*)feats_out, c.v_out, (int)Nm, c.v_out, (int)mg,
+                      B200_EPI_NONE, s)))
+    return rc;
+  return B200_OK;
+}
+
+static int prefill_layers_v2(b200_engine* e, const void* embeds, const int* pos3, int T, int ctx0,
+                             void* all_logits_out, bf16** h_out, cudaStream_t s) {
+  const auto& c = e->cfg;
+  const long H = c.hidden, I = c.inter, QH = (long)c.n_heads * c.head_dim;
+  const long QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  const int hd = c.head_dim, t_ld = (int)round8(T);
+  uint8_t* p = e->ws;
+  bf16* h = (bf16*)p; p += align256((long)T * H * 2);
+  bf16* xn = (bf16*)p; p += align256((long)T * H * 2);
+  bf16* qkv = (bf16*)p; p += align256((long)T * QKV * 2);
+  bf16* att = (bf16*)p; p += align256((long)T * QH * 2);
+  p += align256((long)T * 2 * I * 2);  // (gate/up buffer of the round-1 path)
+  bf16* act = (bf16*)p; p += align256((long)T * I * 2);
+  p += align256(3L * T * 4);
+  bf16* vt = (bf16*)p; p += align256((long)c.n_kv_heads * hd * t_ld * 2);
+  int rc;
+  B200_CUDA(cudaMemcpyAsync(h, embeds, (size_t)T * H * 2, cudaMemcpyDeviceToDevice, s));
+  if ((rc = rms_norm(h, e->layers[0].ln1, xn, T, (int)H, c.rms_eps, s))) return rc;
+  e->launches += 1;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const float scale_bf = __bfloat162float(__float2bfloat16_rn(scale));
+  const int S = ctx0 + T;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const LayerW& lw = e->layers[l];
+    bf16* kc = e->kptr(l, e->kv_row);
+    bf16* vc = e->vptr(l, e->kv_row);
+    if ((rc = v2_linear(e, xn, H, lw.wqkv, lw.bqkv, qkv, QKV, T, (int)QKV, (int)H, B200_EPI_NONE, s))) return rc;
+    // the pipelined kernel needs V^T of EVERY key: available for a fresh prompt (ctx0 == 0)
+    const bool fa = ctx0 == 0 && attention_fa_supported(qkv, QKV, hd, kc, hd, (long)e->kv_cap * hd, vt,
+                                                        (long)hd * t_ld, t_ld, att, QH, hd);
+    if ((rc = mrope_kv_write(qkv, pos3, e->lm_inv_freq, e->axis_sel, kc, vc, T, ctx0, e->kv_cap, c.n_heads,
+                             c.n_kv_heads, hd, s, fa ? scale_bf : 0.f, fa ? vt : nullptr, t_ld)))
+      return rc;
+    if (fa) {
+      rc = attention_fa(qkv, QKV, hd, kc, hd, (long)e->kv_cap * hd, vt, (long)hd * t_ld, t_ld, att, QH, c.n_heads,
+                        c.n_kv_heads, hd, T, S, 1, s, 0, T, 0, S);
+    } else {
+      rc = attention(qkv, QKV, hd, kc, hd, (long)e->kv_cap * hd, vc, hd, (long)e->kv_cap * hd, att, QH, c.n_heads,
+                     c.n_kv_heads, hd, T, S, 1, scale, s);
+    }
+    if (rc) return rc;
+    e->launches += 2;
+    if ((rc = v2_linear_residual_norm(e, att, QH, lw.wo, nullptr, h, H, B200_NORM_RMS, lw.ln2, nullptr, c.rms_eps, xn,
+                                      H, T, (int)H, (int)QH, s)))
+      return rc;
+    {  // gate/up with SwiGLU fused in the epilogue
+      if ((rc = gemm_wt_tuned(xn, H, lw.wgu, nullptr, nullptr, 0, act, I, nullptr, 0, T, (int)(2 * I), (int)H,
+                              B200_EPI_NONE, B200_WT_SWIGLU, (int)I, false, e->sm_count, nullptr, s)))
+        return rc;
+      e->launches += 1;
+    }
+    const bool last = (l + 1 == c.n_layers);
+    const bool want_norm = !last || all_logits_out;
+    const bf16* nw = last ? e->norm : e->layers[l + 1].ln1;
+    if ((rc = v2_linear_residual_norm(e, act, I, lw.wd, nullptr, h, H, want_norm ? B200_NORM_RMS : B200_NORM_NONE, nw,
+                                      nullptr, c.rms_eps, xn, H, T, (int)H, (int)I, s)))
+      return rc;
+  }
+  if (all_logits_out) {  // the reference computes the head on every row (ar.py:358); xn = final norm
+    if ((rc = v2_linear(e, xn, H, e->head, nullptr, (bf16*)all_logits_out, c.vocab, T, c.vocab, (int)H,
+                        B200_EPI_NONE, s)))
+      return rc;
+  }
+  *h_out = h;
+  return B200_OK;
 }
 
 extern "C" {
@@ -348,6 +566,7 @@ int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine**
   e->sm_count = sm;
   decode_set_sm_count(sm);
   if (const char* v = getenv("B200_MEGA_FLOW")) e->flow = atoi(v) != 0;  // tuning aid (A/B)
+  if (const char* v = getenv("B200_PREFILL_V1")) e->v2 = atoi(v) == 0;    // A/B: round-1 prefill kernels
   const auto& c = e->cfg;
   B200_CUDA(cudaMalloc(&e->st, sizeof(DecState)));
   B200_CUDA(cudaMemset(e->st, 0, sizeof(DecState)));
@@ -400,6 +619,8 @@ int b200_engine_destroy(b200_engine* e) {
   cudaFree(e->logits); cudaFree(e->logprobs); cudaFree(e->partials); cudaFree(e->token_log);
   cudaFree(e->force); cudaFree(e->lm_inv_freq); cudaFree(e->axis_sel); cudaFree(e->v_inv_freq);
   if (e->pos_hw) cudaFree(e->pos_hw);
+  if (e->pos_hw_host) cudaFreeHost(e->pos_hw_host);
+  if (e->pos_ev) cudaEventDestroy(e->pos_ev);
   if (e->att_part) cudaFree(e->att_part);
   if (e->att_stats) cudaFree(e->att_stats);
   if (e->bar) cudaFree(e->bar);
@@ -407,6 +628,7 @@ int b200_engine_destroy(b200_engine* e) {
   if (e->packed) cudaFree(e->packed);
   if (e->tc_acc) cudaFree(e->tc_acc);
   if (e->flow_words) cudaFree(e->flow_words);
+  if (e->batch) batch_decoder_destroy(e->batch);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -440,7 +662,6 @@ int b200_engine_set_rope_tables(b200_engine* e, const float* lm_inv_freq_host,
   return B200_OK;
 }
 
-static long align256(long x) { return (x + 255) & ~255L; }
 
 long b200_engine_workspace_bytes(const b200_engine* e, int max_tokens, int max_patches) {
   const auto& c = e->cfg;
@@ -452,7 +673,9 @@ long b200_engine_workspace_bytes(const b200_engine* e, int max_tokens, int max_p
   long v = align256(N * (long)c.v_patch_dim * 2) + align256(N * (long)c.v_embed * 2) * 2 +
            align256(N * 3L * c.v_embed * 2) + align256(N * (long)c.v_mlp * 2) +
            align256(N * (long)c.v_embed * 2);
-  return (lm > v ? lm : v) + 4096;
+  lm += align256((long)c.n_kv_heads * c.head_dim * round8(T) * 2);  // V^T of the prompt chunk
+  v += align256((long)c.v_embed * round8(N) * 2);                   // V^T of the vision tower
+  return (lm > v ? lm : v) + WT_PARTIAL_BYTES + 4096;
 }
 
 int b200_engine_set_workspace(b200_engine* e, void* ptr, long bytes) {
@@ -473,22 +696,6 @@ int b200_engine_bind_kv(b200_engine* e, void* pool, int batch, int cap) {
   return B200_OK;
 }
 
-// rot_pos_emb ids (vision.py:219-249), host side, merge-group-major order
-static void build_pos_hw(const int* grid, int n_img, int ms, std::vector<int>* out) {
-  out->clear();
-  for (int i = 0; i < n_img; ++i) {
-    const int t = grid[i * 3], h = grid[i * 3 + 1], w = grid[i * 3 + 2];
-    for (int tt = 0; tt < t; ++tt)
-      for (int bh = 0; bh < h / ms; ++bh)
-        for (int bw = 0; bw < w / ms; ++bw)
-          for (int ih = 0; ih < ms; ++ih)
-            for (int iw = 0; iw < ms; ++iw) {
-              out->push_back(bh * ms + ih);
-              out->push_back(bw * ms + iw);
-            }
-  }
-}
-
 int b200_engine_vision(b200_engine* e, const float* pixel_values, const int* grid_thw_host,
                        int n_images, void* feats_out, void* stream) {
   B200_REQUIRE(e && pixel_values && grid_thw_host && n_images > 0 && feats_out,
@@ -507,6 +714,7 @@ int b200_engine_vision(b200_engine* e, const float* pixel_values, const int* gri
   }
   B200_REQUIRE(e->ws && b200_engine_workspace_bytes(e, 1, (int)N) <= e->ws_bytes,
                "engine_vision: workspace too small for %ld patches", N);
+  if (e->v2) return vision_v2(e, pixel_values, grid_thw_host, n_images, N, feats_out, s);
   const long E = c.v_embed, Em = c.v_mlp;
   const int nh = c.v_heads, hd = c.v_embed / c.v_heads;
   uint8_t* p = e->ws;
@@ -601,13 +809,16 @@ int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3, int
   bf16* att = (bf16*)p; p += align256((long)T * QH * 2);
   bf16* gu = (bf16*)p; p += align256((long)T * 2 * I * 2);
   bf16* act = (bf16*)p; p += align256((long)T * I * 2);
+  if (e->v2) {
+    if ((rc = prefill_layers_v2(e, embeds, pos3, T, ctx0, all_logits_out, &h, s))) return rc;
+  } else {
   B200_CUDA(cudaMemcpyAsync(h, embeds, (size_t)T * H * 2, cudaMemcpyDeviceToDevice, s));
   const float scale = 1.0f / sqrtf((float)c.head_dim);
   const int S = ctx0 + T;
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerW& lw = e->layers[l];
-    bf16* kc = e->kptr(l, 0);
-    bf16* vc = e->vptr(l, 0);
+    bf16* kc = e->kptr(l, e->kv_row);
+    bf16* vc = e->vptr(l, e->kv_row);
     if ((rc = rms_norm(h, lw.ln1, xn, T, (int)H, c.rms_eps, s))) return rc;
     if ((rc = gemm_bf16_tn(xn, H, lw.wqkv, lw.bqkv, nullptr, 0, qkv, QKV, T, (int)QKV, (int)H,
                            B200_EPI_NONE, s)))
@@ -638,6 +849,7 @@ int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3, int
                            c.vocab, (int)H, B200_EPI_NONE, s)))
       return rc;
     e->launches += 2;
+  }
   }
   // last row through the fused head + sampler; arms the decode state
   const DecodeDims d = e->dims();
@@ -822,6 +1034,96 @@ int b200_engine_fetch_tokens(b200_engine* e, long start, int n, int* host_out, v
                               cudaMemcpyDeviceToHost, s));
   return B200_OK;
 }
+int b200_engine_set_kv_row(b200_engine* e, int row) {
+  B200_REQUIRE(e && row >= 0 && (e->kv_batch == 0 || row < e->kv_batch), "set_kv_row: row %d of %d", row,
+               e ? e->kv_batch : 0);
+  if (row != e->kv_row) invalidate_graph(e);
+  e->kv_row = row;
+  return B200_OK;
+}
+
+static void bd_model(b200_engine* e, BdModel* m) {
+  const auto& c = e->cfg;
+  m->d = e->dims();
+  m->n_layers = c.n_layers;
+  m->layers = e->layers.data();
+  m->embed = e->embed; m->head = e->head; m->final_norm = e->norm;
+  m->inv_freq = e->lm_inv_freq;
+  m->kv = e->kptr(0, 0);
+  m->row_stride = (long)c.n_kv_heads * e->kv_cap * c.head_dim;
+  m->v_off = (long)e->kv_batch * m->row_stride;
+  m->layer_stride = 2L * m->v_off;
+  m->kv_batch = e->kv_batch;
+  m->sm_count = e->sm_count;
+}
+
+int b200_batch_begin(b200_engine* e, int B, const int* tok, const int* ctx, const int* pos, const int* active,
+                     void* stream) {
+  B200_REQUIRE(e && tok && ctx && pos && active, "batch_begin: null argument");
+  int rc = resolve(e);
+  if (rc) return rc;
+  B200_REQUIRE(e->kv, "batch_begin: KV pool not bound");
+  B200_CUDA(cudaSetDevice(e->device));
+  BdModel m;
+  bd_model(e, &m);
+  if ((rc = batch_decoder_begin(&e->batch, m, B, tok, ctx, pos, active, (cudaStream_t)stream))) return rc;
+  e->b_ctx.assign(ctx, ctx + B);
+  e->b_active.assign(active, active + B);
+  e->launches += 1;
+  return B200_OK;
+}
+
+int b200_batch_decode(b200_engine* e, int n_steps, int want_logprobs, void* stream) {
+  B200_REQUIRE(e && e->batch && n_steps > 0, "batch_decode: batch_begin first");
+  for (size_t b = 0; b < e->b_ctx.size(); ++b)
+    B200_REQUIRE(!e->b_active[b] || e->b_ctx[b] + n_steps <= e->kv_cap,
+                 "batch_decode: row %zu: %d cached + %d steps exceeds cache capacity %d", b, e->b_ctx[b], n_steps,
+                 e->kv_cap);
+  B200_CUDA(cudaSetDevice(e->device));
+  BdModel m;
+  bd_model(e, &m);
+  cudaStream_t s = (cudaStream_t)stream;
+  B200_CUDA(cudaEventRecord(e->ev0, s));
+  int rc = batch_decoder_step(e->batch, m, n_steps, want_logprobs != 0, s, e->cap_stream, &e->launches);
+  if (rc) return rc;
+  B200_CUDA(cudaEventRecord(e->ev1, s));
+  e->last_steps = n_steps;
+  e->timing_valid = true;
+  for (size_t b = 0; b < e->b_ctx.size(); ++b)
+    if (e->b_active[b]) e->b_ctx[b] += n_steps;
+  return B200_OK;
+}
+
+int b200_batch_fetch(b200_engine* e, long first_step, int n_steps, int* tok_host, float* lp_host, void* stream) {
+  B200_REQUIRE(e && e->batch && tok_host, "batch_fetch: batch_begin first");
+  return batch_decoder_fetch(e->batch, first_step, n_steps, tok_host, lp_host, (cudaStream_t)stream);
+}
+
+const void* b200_batch_logits(b200_engine* e) { return e ? batch_decoder_buffer(e->batch, 0) : nullptr; }
+const void* b200_batch_logprobs(b200_engine* e) { return e ? batch_decoder_buffer(e->batch, 1) : nullptr; }
+/* device int32 [4096 steps][16 rows]: token of (step since the last begin, row) */
+const int* b200_batch_token_log(b200_engine* e) { return e ? (const int*)batch_decoder_buffer(e->batch, 2) : nullptr; }
+
+/* cache management of the batched pool (the reference's BatchKVCache.filter / extend / extract,
+ * models/cache.py:1077-1201, move rows between arrays): copy the first n_tokens positions of one row
+ * of a pool (n_layers, 2, batch, n_kv, cap, hd) into a row of another (or the same) pool */
+int b200_kv_copy_row(void* dst_pool, int dst_batch, int dst_cap, int dst_row, const void* src_pool, int src_batch,
+                     int src_cap, int src_row, int n_layers, int n_kv, int hd, int n_tokens, void* stream) {
+  B200_REQUIRE(dst_pool && src_pool && dst_row >= 0 && dst_row < dst_batch && src_row >= 0 && src_row < src_batch &&
+                   n_tokens >= 0 && n_tokens <= dst_cap && n_tokens <= src_cap,
+               "kv_copy_row: bad arguments");
+  if (n_tokens == 0) return B200_OK;
+  const size_t w = (size_t)n_tokens * hd * 2;
+  for (int l = 0; l < n_layers; ++l)
+    for (int kv = 0; kv < 2; ++kv) {
+      const char* sp = (const char*)src_pool + ((((size_t)l * 2 + kv) * src_batch + src_row) * n_kv) * (size_t)src_cap * hd * 2;
+      char* dp = (char*)dst_pool + ((((size_t)l * 2 + kv) * dst_batch + dst_row) * n_kv) * (size_t)dst_cap * hd * 2;
+      B200_CUDA(cudaMemcpy2DAsync(dp, (size_t)dst_cap * hd * 2, sp, (size_t)src_cap * hd * 2, w, n_kv,
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+  return B200_OK;
+}
+
 int b200_memcpy_d2d(void* dst, const void* src, long bytes, void* stream) {
   B200_REQUIRE(dst && src && bytes >= 0, "memcpy_d2d: bad arguments");
   B200_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

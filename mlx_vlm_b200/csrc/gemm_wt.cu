@@ -28,6 +28,7 @@
 // oracle/mlx_semantics.py::linear (+ activations, residual add).
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 #include "decode.cuh"
@@ -565,38 +566,92 @@ void gemm_wt_set_pdl(bool on) { g_wt_pdl = on; }
 
 static int round16(int x) { return (x + 15) & ~15; }
 
-// Tile / pipeline configuration for (T, rows, K).  `rows` = weight rows (SwiGLU: 2 * channels).
-//   TN: tokens per tile, balanced over ceil(T / 256) tiles;  KS: k-blocks per stage (2: 256 B of a
-//   weight row per request burst);  split: K splits so that ~one wave of CTAs exists;
-//   stages: as many as fit the shared-memory budget (<= 110 KB when 2 CTAs per SM pay off).
-void gemm_wt_auto(int T, int row_blocks, int K, bool allow_split, WtConfig* c, int sm_count) {
-  const int nt = cdiv(T, 256);
-  c->TN = round16(cdiv(T, nt));
-  if (c->TN > 256) c->TN = 256;
-  const int tok_tiles = cdiv(T, c->TN);
+// Tile / pipeline configuration for (T, row blocks, K): a small cost model calibrated on the round-2
+// sweep (profiles/r2_gemm_wt_sweep.txt, B200):
+//   * a CTA costs ~4.5 us of fixed latency (launch, barrier/TMEM set-up, first TMA round trip,
+//     epilogue) + per k-block max(MMA time, shared-memory fill time at ~130 GB/s per SM);
+//   * two CTAs share an SM when a configuration needs <= ~110 KB of shared memory: the fixed part of
+//     one overlaps the main loop of the other, which wins whenever more than one wave exists;
+//   * split-K buys parallelism for the GEMMs with few weight rows at the price of fp32 partial
+//     traffic (written here, read by finish_rows);
+//   * the weights are streamed from HBM once: nothing is faster than bytes / ~6 TB/s.
+void gemm_wt_auto(int T, int row_blocks, int K, bool allow_split, WtConfig* best, int sm_count) {
   const int kb_total = cdiv(K, WT_BK);
-  const long base = (long)row_blocks * tok_tiles;
-  int split = 1;
-  if (allow_split && base < (long)sm_count * 3 / 4) {
-    split = (int)(sm_count / base);
-    const int max_by_k = kb_total / 8 > 0 ? kb_total / 8 : 1;  // at least 8 k-blocks per split
-    if (split > max_by_k) split = max_by_k;
-    if (split < 1) split = 1;
+  const int t16 = round16(T);
+  int tn_c[12];
+  int n_tn = 0;
+  auto add_tn = [&](int tn) {
+    if (tn < 16) tn = 16;
+    if (tn > 256) tn = 256;
+    if (tn > t16) tn = t16;
+    for (int i = 0; i < n_tn; ++i)
+      if (tn_c[i] == tn) return;
+    tn_c[n_tn++] = tn;
+  };
+  for (int k = 1; k <= 3; ++k) add_tn(round16(cdiv(T, k)));
+  if (T > 256) {
+    const int nt = cdiv(T, 256);
+    for (int k = 0; k < 3; ++k) add_tn(round16(cdiv(T, nt + k)));
   }
-  split = cdiv(kb_total, cdiv(kb_total, split));  // no empty split
-  c->split = split;
-  c->KS = 2;
-  const int stage = c->KS * (WT_WBLK + c->TN * 128);
-  // two CTAs per SM when several waves exist (one CTA's epilogue under the other's main loop)
-  const long ctas = base * split;
-  const int budget = (ctas > sm_count) ? 108 * 1024 : 208 * 1024;
-  int st = budget / stage;
-  if (st < 2) {  // large token tiles: fall back to one k-block per stage / one CTA per SM
-    c->KS = 1;
-    st = (208 * 1024) / (WT_WBLK + c->TN * 128);
+  add_tn(96); add_tn(128); add_tn(144); add_tn(192);
+  double best_t = 1e30;
+  best->TN = tn_c[0]; best->KS = 1; best->stages = 2; best->split = 1;
+  for (int it = 0; it < n_tn; ++it) {
+    const int TN = tn_c[it];
+    const int tt = cdiv(T, TN);
+    const long base = (long)row_blocks * tt;
+    for (int KS = 1; KS <= 4; KS *= 2) {
+      const int stage = KS * (WT_WBLK + TN * 128);
+      for (int occ = 2; occ >= 1; --occ) {
+        const int budget = occ == 2 ? 110 * 1024 : 208 * 1024;
+        int st = budget / stage;
+        if (st > 8) st = 8;
+        if (st < 2 || st * KS < 3 || (long)st * stage < (long)WT_EPI_TOK * WT_ROWS * 4) continue;
+        if (occ == 1 && (long)st * stage + 2048 <= 110 * 1024) continue;  // same as the occ == 2 case
+        int cand[6] = {1, 0, 0, 0, 0, 0};
+        int n_sp = 1;
+        if (allow_split) {
+          for (int target : {sm_count, 2 * sm_count, 3 * sm_count}) {
+            int sp = (int)(target / base);
+            if (sp > kb_total / 4) sp = kb_total / 4;
+            if (sp < 1) sp = 1;
+            sp = cdiv(kb_total, cdiv(kb_total, sp));
+            bool dup = false;
+            for (int i = 0; i < n_sp; ++i) dup |= cand[i] == sp;
+            if (!dup) cand[n_sp++] = sp;
+          }
+        }
+        for (int is = 0; is < n_sp; ++is) {
+          const int split = cand[is];
+          if (split > 1 && (long)split * T * row_blocks * 128 * 4 > (40L << 20)) continue;  // partial-tile budget
+          const long ctas = base * split;
+          const int kbs = cdiv(kb_total, split);
+          const double t_mma = 4.0 * (TN / 2.0) / 1900.0;                          // us per k-block
+          const double t_fill = (WT_WBLK + TN * 128) / 130e3 * (KS == 1 ? 1.15 : 1.0);
+          const double t_kb = t_mma > t_fill ? t_mma : t_fill;
+          const double t_fix = 5.2;                                  // first wave, prologue hidden by PDL
+          const long per_sm = (ctas + sm_count - 1) / sm_count;      // CTAs an SM has to run
+          double t;
+          if (occ == 2) {
+            const long waves = (ctas + 2L * sm_count - 1) / (2L * sm_count);
+            t = t_fix + per_sm * kbs * t_kb + (waves - 1) * 4.0;
+          } else {
+            t = t_fix + kbs * t_kb + (per_sm - 1) * (9.5 + kbs * t_kb);  // serialised waves pay the full CTA latency
+          }
+          if (st * KS < 4) t *= 1.08;
+          const double fill_total = (double)ctas * kbs * (WT_WBLK + TN * 128);
+          if (t < t_fix + fill_total / 12e6) t = t_fix + fill_total / 12e6;   // chip-wide L2 -> SM fill rate
+          const double hbm = (double)row_blocks * 128 * K * 2 / 6e6 + 3.0;   // weights stream from HBM once
+          if (t < hbm) t = hbm + 0.01 * kbs * t_kb;
+          if (split > 1) t += (double)split * T * row_blocks * 128 * 4 / 6e6 + 0.2 * split;
+          if (t < best_t) {
+            best_t = t;
+            best->TN = TN; best->KS = KS; best->stages = st; best->split = split;
+          }
+        }
+      }
+    }
   }
-  if (st > 8) st = 8;
-  c->stages = st;
 }
 
 int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
@@ -653,6 +708,158 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
   lc.numAttrs = g_wt_pdl ? 1 : 0;
   B200_CUDA(cudaLaunchKernelEx(&lc, gemm_wt_kernel, tw, tx, p));
   return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Measured configuration choice ("measure, don't guess"): the first call for a problem class
+// (tokens rounded up to 64, N, K, mode) times a short list of candidate configurations on the
+// caller's stream with the call's own operands (CUDA events, one warm-up + two timed launches
+// each) and caches the winner; later calls cost one hash lookup.  Candidates follow what the
+// round-2 sweep showed matters: token tile {96,128,144,192,256}, one CTA per SM with 2 k-blocks
+// per stage vs two CTAs per SM with 1, and split-K to one or two waves.  The list is ordered and
+// the first candidate within 3 % of the best wins, so the choice is stable run to run.
+// B200_WT_TUNE=0 uses the cost model (gemm_wt_auto) instead.
+// ---------------------------------------------------------------------------------------------
+struct TuneKey {
+  int tb, N, K, mode, split_ok, dev;
+  bool operator==(const TuneKey& o) const {
+    return tb == o.tb && N == o.N && K == o.K && mode == o.mode && split_ok == o.split_ok && dev == o.dev;
+  }
+};
+struct TuneHash {
+  size_t operator()(const TuneKey& k) const {
+    size_t h = (size_t)k.tb;
+    for (int v : {k.N, k.K, k.mode, k.split_ok, k.dev}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+
+static int tune_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_WT_TUNE");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+
+int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
+                  void* C, long ldc, float* partial, long partial_bytes, int T, int N, int K, int epilogue,
+                  int mode, int inter, bool allow_split, int sm_count, int* split_out, cudaStream_t st) {
+  static std::unordered_map<TuneKey, WtConfig, TuneHash> cache;
+  static std::mutex mu;
+  const int row_blocks = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, WT_ROWS);
+  const int kb_total = cdiv(K, WT_BK);
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  const TuneKey key{(T + 63) / 64, N, K, mode, allow_split ? 1 : 0, dev};
+  WtConfig cfg;
+  bool have = false;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      cfg = it->second;
+      have = true;
+    }
+  }
+  auto fits = [&](const WtConfig& c) {
+    return !(mode == B200_WT_PARTIAL && (long)c.split * T * N * 4 > partial_bytes);
+  };
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (!have && (!tune_enabled() || cap != cudaStreamCaptureStatusNone)) {
+    gemm_wt_auto(T, row_blocks, K, allow_split, &cfg, sm_count);
+    while (cfg.split > 1 && !fits(cfg)) cfg.split = cdiv(kb_total, cdiv(kb_total, cfg.split - 1));
+    have = true;  // not cached: a later un-captured call may still tune
+  } else if (!have) {
+    // ---- candidate list ----
+    std::vector<WtConfig> cand;
+    auto add = [&](int tn, int ks, int budget, int split) {
+      if (tn > round16(T)) tn = round16(T);
+      if (tn > 256) tn = 256;
+      const int stage = ks * (WT_WBLK + tn * 128);
+      int stg = budget / stage;
+      if (stg > 6) stg = 6;
+      if (stg < 2 || (long)stg * stage < (long)WT_EPI_TOK * WT_ROWS * 4) return;
+      split = cdiv(kb_total, cdiv(kb_total, split < 1 ? 1 : split));
+      WtConfig c{tn, ks, stg, split};
+      if (!fits(c)) return;
+      for (const auto& o : cand)
+        if (o.TN == c.TN && o.KS == c.KS && o.stages == c.stages && o.split == c.split) return;
+      cand.push_back(c);
+    };
+    WtConfig model;
+    gemm_wt_auto(T, row_blocks, K, allow_split, &model, sm_count);
+    if (fits(model)) cand.push_back(model);
+    int tns[8], n_tn = 0;
+    if (T <= 96) {
+      tns[n_tn++] = round16(T);
+      if (T > 48) tns[n_tn++] = round16(cdiv(T, 2));
+    } else {
+      for (int tn : {144, 96, 192, 128}) tns[n_tn++] = tn;
+      if (T > 512) tns[n_tn++] = 256;
+    }
+    for (int i = 0; i < n_tn; ++i) {
+      const int tn = tns[i];
+      const long base = (long)row_blocks * cdiv(T, tn);
+      int sps[3] = {1, 1, 1};
+      if (allow_split) {
+        int a = (int)(sm_count / base), b = (int)(2L * sm_count / base);
+        const int cap_k = kb_total / 4 > 0 ? kb_total / 4 : 1;
+        sps[1] = a < 1 ? 1 : (a > cap_k ? cap_k : a);
+        sps[2] = b < 1 ? 1 : (b > cap_k ? cap_k : b);
+      }
+      for (int sp : sps) {
+        add(tn, 2, 208 * 1024, sp);  // one CTA per SM, 256-byte weight-row bursts
+        add(tn, 1, 110 * 1024, sp);  // two CTAs per SM
+      }
+    }
+    if (cand.empty()) {
+      gemm_wt_auto(T, row_blocks, K, false, &model, sm_count);
+      cand.push_back(model);
+    }
+    // ---- time them ----
+    cudaEvent_t e0, e1;
+    B200_CUDA(cudaEventCreate(&e0));
+    B200_CUDA(cudaEventCreate(&e1));
+    std::vector<float> ms(cand.size(), 1e30f);
+    int rc = B200_OK;
+    for (size_t i = 0; i < cand.size() && rc == B200_OK; ++i) {
+      rc = gemm_wt(X, ldx, W, bias, nullptr, 0, C, ldc, partial, T, N, K, epilogue, mode, inter, cand[i], 0, st);
+      if (rc) break;
+      cudaEventRecord(e0, st);
+      for (int r = 0; r < 2 && rc == B200_OK; ++r)
+        rc = gemm_wt(X, ldx, W, bias, nullptr, 0, C, ldc, partial, T, N, K, epilogue, mode, inter, cand[i], 0, st);
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) rc = B200_ERR_CUDA;
+      float t = 0.f;
+      cudaEventElapsedTime(&t, e0, e1);
+      ms[i] = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    float best = 1e30f;
+    for (float t : ms) best = t < best ? t : best;
+    size_t pick = 0;
+    for (size_t i = 0; i < cand.size(); ++i)
+      if (ms[i] <= best * 1.03f) {
+        pick = i;
+        break;
+      }
+    cfg = cand[pick];
+    if (getenv("B200_WT_TUNE_LOG"))
+      fprintf(stderr, "[gemm_wt tune] T=%d N=%d K=%d mode=%d -> TN=%d KS=%d stages=%d split=%d (%.1f us, %zu candidates)\n",
+              T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, ms[pick] * 500.f, cand.size());
+    std::lock_guard<std::mutex> g(mu);
+    cache[key] = cfg;
+  }
+  // a cached configuration was tuned for a token count in the same 64-bucket: re-check the bounds
+  if (cfg.TN > round16(T)) cfg.TN = round16(T);
+  while (cfg.split > 1 && !fits(cfg)) cfg.split = cdiv(kb_total, cdiv(kb_total, cfg.split - 1));
+  if (split_out) *split_out = cfg.split;
+  return gemm_wt(X, ldx, W, bias, residual, ldr, C, ldc, partial, T, N, K, epilogue, mode, inter, cfg, 0, st);
 }
 
 int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,

@@ -130,6 +130,43 @@ class Engine:
         if force_tokens is not None:
             self.stream.synchronize()  # the H2D copies read `force_tokens` (pageable)
 
+    # -- lock-step batched decode (decode_batch.cu) -----------------------------
+    def set_kv_row(self, row: int):
+        N.check(self.lib.b200_engine_set_kv_row(self.h, int(row)), "set_kv_row")
+
+    def batch_begin(self, tok, ctx, pos, active):
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (tok, ctx, pos, active)]
+        B = a[0].shape[0]
+        assert all(x.shape == (B,) for x in a)
+        N.check(self.lib.b200_batch_begin(self.h, B, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+                                          a[3].ctypes.data, self.s), "batch_begin")
+        self._batch_B = B
+
+    def batch_decode(self, n_steps: int, want_logprobs: bool = False):
+        N.check(self.lib.b200_batch_decode(self.h, int(n_steps), int(want_logprobs), self.s), "batch_decode")
+
+    def batch_fetch(self, first_step: int, n_steps: int, tok_host: torch.Tensor, lp_host: Optional[torch.Tensor] = None):
+        """async copy of tokens (and their logprobs) of steps [first, first+n) into pinned (n, B) buffers"""
+        N.check(self.lib.b200_batch_fetch(self.h, int(first_step), int(n_steps), tok_host.data_ptr(),
+                                          N.ptr(lp_host), self.s), "batch_fetch")
+
+    def batch_logits_view(self, which: str = "logits") -> torch.Tensor:
+        p = (self.lib.b200_batch_logits if which == "logits" else self.lib.b200_batch_logprobs)(self.h)
+        return self._view(p, self._batch_B * self.cfg.vocab, torch.bfloat16).view(self._batch_B, self.cfg.vocab)
+
+    BATCH_LOG_STEPS, BATCH_LOG_ROWS = 4096, 16
+
+    def batch_token_log_view(self) -> torch.Tensor:
+        """int32 (steps since the last batch_begin, 16) view of the batched decoder's token log"""
+        p = self.lib.b200_batch_token_log(self.h)
+        return self._view(p, self.BATCH_LOG_STEPS * self.BATCH_LOG_ROWS, torch.int32).view(self.BATCH_LOG_STEPS,
+                                                                                        self.BATCH_LOG_ROWS)
+
+    def kv_copy_row(self, dst: KVPool, dst_row: int, src: KVPool, src_row: int, n_tokens: int):
+        N.check(self.lib.b200_kv_copy_row(dst.buf.data_ptr(), dst.batch, dst.capacity, int(dst_row), src.buf.data_ptr(),
+                                          src.batch, src.capacity, int(src_row), dst.n_layers, dst.n_kv, dst.hd,
+                                          int(n_tokens), self.s), "kv_copy_row")
+
     def set_next(self, token: int, ctx: int, position: int):
         N.check(self.lib.b200_engine_set_next(self.h, int(token), int(ctx), int(position), self.s),
                 "set_next")

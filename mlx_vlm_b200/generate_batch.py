@@ -3,17 +3,17 @@
 `BatchGenerationResult` :519-545, `_left_pad_prompts` / `_right_pad_prompts` :548-560,
 `batch_generate` :2890-3097).
 
-How the rows run on the B200 engine (round 1): the decode engine is a batch-1 persistent
-kernel, so the rows of a batch are TIME-MULTIPLEXED: every request keeps its own KV pool
-(`models/cache.py::KVPool`) and the generator hands the engine to one row at a time for a
-slice of `decode_slice` greedy steps that run entirely on the device (token feedback through
-device memory); the tokens are buffered and surfaced one per `next()` call, exactly as a
-lock-step batch would.  Scheduling policy is the reference's: decode-first, then admit up to
-`prefill_batch_size` waiting prompts (shortest first) while fewer than
-`completion_batch_size` rows are active.  The rows are independent (own cache, own M-RoPE
-delta), which is also how requests are spread over GPUs (`parallel.shard_requests`).
-[round 2: the tcgen05 decode kernel (decode_mega_tc.cu) has 16 activation columns per
-weight tile; a lock-step batch of <= 16 rows costs one weight stream.]
+How the rows run on the B200 engine: LOCK STEP on the device (csrc/decode_batch.cu).  All active
+rows live in ONE batched KV pool (layers, 2, rows, kv heads, capacity, head_dim), each with its own
+length (no left padding); a decode step is one captured CUDA graph that streams the weights ONCE
+for all rows (weight-major tcgen05 GEMMs with the rows as a 16-wide token tile), so B rows cost
+about one batch-1 step.  Admission of a request = a batch-1 prefill straight into a free row of
+the pool; a finished row is replaced by the last row (one row copy); the device state is re-armed
+only when the set of rows changes.  Tokens are produced in slices of `decode_slice` steps and
+surfaced one per row per `next()` call.  Scheduling policy is the reference's: decode-first, then
+admit up to `prefill_batch_size` waiting prompts (shortest first) while fewer than
+`completion_batch_size` rows are active.  Engines without the batched decoder (the CPU stand-in
+of the host-logic tests) run the rows time-multiplexed over the batch-1 path instead.
 """
 from __future__ import annotations
 
@@ -104,6 +104,7 @@ class _Row:
     last_token: int = -1       # last computed token (input of the next decode step)
     buffer: List[Tuple[int, float]] = field(default_factory=list)
     reserve: int = 0
+    ctx: int = 0               # tokens in the row's KV cache (lock-step mode)
 
 
 class GenerationBatch:
@@ -195,6 +196,16 @@ class BatchGenerator:
             self.tokenizer.stopping_criteria = StoppingCriteria(eos if eos is not None else [], self.tokenizer)
         if stop_tokens:
             self.tokenizer.stopping_criteria.add_eos_token_ids(list(stop_tokens))
+        eng = getattr(model, "engine", None)
+        lm = getattr(model, "language_model", None)
+        # lock-step batched decode needs the native batched decoder (<= 16 rows per weight stream)
+        self._lockstep = (hasattr(eng, "batch_begin") and hasattr(lm, "make_cache_row")
+                          and not unsupported.pop("time_multiplex", False))
+        if self._lockstep:
+            self.completion_batch_size = min(self.completion_batch_size, 16)
+        self._pool = None          # the shared batched KV pool (lock-step mode)
+        self._armed_key = None     # (uids, live flags) the device state was armed for
+        self._steps_since_begin = 0
         self.uid_count = 0
         self._unprocessed_sequences: List[_Row] = []
         self._generation_batch = GenerationBatch.empty()
@@ -233,6 +244,8 @@ class BatchGenerator:
         if uid in self._generation_batch.uids:                 # already decoding
             idx = self._generation_batch.uids.index(uid)
             self._generation_batch.filter([i for i in range(len(self._generation_batch)) if i != idx])
+            if self._lockstep:
+                self._compact()
             return True
         return False
 
@@ -288,9 +301,13 @@ class BatchGenerator:
         if emb is None:
             out = model.get_input_embeddings(ids, kw.pop("pixel_values", None), mask=kw.pop("mask", None), **kw)
             emb, pos, deltas = out.inputs_embeds, out.position_ids, out.rope_deltas
-        row.cache = cache_mod.make_prompt_cache(lm)
         T = emb.shape[1]
         row.reserve = T + row.max_tokens + 1
+        if self._lockstep:
+            row.cache = lm.make_cache_row(self._pool_for(row.reserve), len(self._active) + self._admitting)
+            self._admitting += 1
+        else:
+            row.cache = cache_mod.make_prompt_cache(lm)
         row.delta = int(np.asarray(deltas).reshape(-1)[0]) if deltas is not None else 0
         step = self.prefill_step_size
         ids_left = ids
@@ -309,6 +326,7 @@ class BatchGenerator:
         else:
             tok, lp = self._sample(out.logits[:, -1, :])
         row.last_token, row.n_decoded = tok, 1
+        row.ctx = int(row.cache[0].offset)
         row.buffer.append((tok, lp))
         dt = time.perf_counter() - tic
         self._prompt_tokens_counter += len(row.ids)
@@ -324,6 +342,85 @@ class BatchGenerator:
             y = self.sampler(logprobs)
             tok = int(y.reshape(-1)[0].item())
             return tok, float(logprobs.reshape(-1)[tok].float().item())
+
+    # ------------------------------------------------------------------ lock-step rows
+    _admitting = 0
+
+    def _pool_for(self, need_tokens: int):
+        """the shared batched pool, with room for `need_tokens` positions per row"""
+        lm, eng = self.model.language_model, self.model.engine
+        step = cache_mod.KVPool.step
+        cap = ((need_tokens + step - 1) // step) * step
+        if self._pool is None:
+            self._pool = cache_mod.KVPool(lm.args.num_hidden_layers, lm.n_kv_heads, lm.head_dim, eng.device,
+                                          batch=self.completion_batch_size, capacity=cap)
+        elif cap > self._pool.capacity:
+            import contextlib
+            eng.stream.synchronize()
+            on = torch.cuda.stream(eng.stream) if torch.cuda.is_available() else contextlib.nullcontext()
+            with on:
+                self._pool.reserve(cap, live_tokens=self._pool.capacity)
+            self._armed_key = None
+        return self._pool
+
+    def _compact(self):
+        """rows are pool rows 0..B-1 in `_active` order: after a filter, move rows down"""
+        eng = self.model.engine
+        for slot, row in enumerate(self._active):
+            cur = row.cache[0]._row
+            if cur != slot:
+                eng.kv_copy_row(self._pool, slot, self._pool, cur, row.ctx)
+                for c in row.cache:
+                    c._row = slot
+                self._armed_key = None
+
+    def _lockstep_slice(self):
+        """one slice of lock-step decode steps for every row that still has tokens to compute"""
+        eng = self.model.engine
+        rows = self._active
+        live = [r.n_decoded < r.max_tokens for r in rows]
+        if not any(live):
+            return
+        k = min([self.decode_slice] + [r.max_tokens - r.n_decoded for r, a in zip(rows, live) if a])
+        greedy = self.greedy_sampling
+        if not greedy:
+            k = 1
+        key = (tuple(r.uid for r in rows), tuple(live))
+        if key != self._armed_key or self._steps_since_begin + k > 4000 or not greedy:
+            eng.bind_pool(self._pool)
+            eng.batch_begin([r.last_token for r in rows], [r.ctx for r in rows],
+                            [r.ctx + (r.delta or 0) for r in rows], [int(a) for a in live])
+            self._armed_key = key
+            self._steps_since_begin = 0
+        eng.batch_decode(k, want_logprobs=not greedy)
+        B = len(rows)
+        if greedy:
+            toks = _host_buf(k * B).view(k, B)
+            lps = torch.empty(k, B, dtype=torch.float32)
+            lps = lps.pin_memory() if torch.cuda.is_available() else lps
+            eng.batch_fetch(self._steps_since_begin, k, toks, lps)
+            eng.stream.synchronize()
+            self._steps_since_begin += k
+            for b, (r, a) in enumerate(zip(rows, live)):
+                if not a:
+                    continue
+                col = toks[:, b].tolist()
+                r.buffer.extend((int(t), float(l)) for t, l in zip(col, lps[:, b].tolist()))
+                r.last_token, r.n_decoded, r.ctx = int(col[-1]), r.n_decoded + k, r.ctx + k
+                for c in r.cache:
+                    c.offset = r.ctx
+        else:   # sampler on the host-visible logits of every row (one step at a time)
+            logits = eng.batch_logits_view("logits")
+            self._steps_since_begin += 1
+            for b, (r, a) in enumerate(zip(rows, live)):
+                if not a:
+                    continue
+                tok, lp = self._sample(logits[b:b + 1])
+                r.buffer.append((tok, lp))
+                r.last_token, r.n_decoded, r.ctx = tok, r.n_decoded + 1, r.ctx + 1
+                for c in r.cache:
+                    c.offset = r.ctx
+            self._armed_key = None
 
     def _decode_slice(self, row: _Row):
         """Refill the row's token buffer: hand the engine to this row for up to `decode_slice`
@@ -366,6 +463,8 @@ class BatchGenerator:
         if self._active:
             tic = time.perf_counter()
             keep = []
+            if self._lockstep and any(not r.buffer for r in self._active):
+                self._lockstep_slice()
             for i, row in enumerate(self._active):
                 if not row.buffer:
                     self._decode_slice(row)
@@ -384,14 +483,18 @@ class BatchGenerator:
             self._gen_time_counter += time.perf_counter() - tic
             if len(keep) < len(self._generation_batch):
                 self._generation_batch.filter(keep)
+                if self._lockstep:
+                    self._compact()
         # 2. admit waiting prompts while there is room (shortest first)
         room = self.completion_batch_size - len(self._active)
         n_admit = min(room, self.prefill_batch_size, len(self._unprocessed_sequences))
         admitted = []
+        self._admitting = 0
         for _ in range(max(0, n_admit)):
             row = self._unprocessed_sequences.pop(0)
             prompt_responses.append(self._prefill(row))
             admitted.append(row)
+        self._admitting = 0
         if admitted:
             self._generation_batch.extend(GenerationBatch(admitted))
         return prompt_responses, generation_responses

@@ -64,9 +64,10 @@ class _BaseCache:
 class KVCache(_BaseCache):
     step = 256
 
-    def __init__(self, pool: Optional[KVPool] = None, layer: int = 0):
+    def __init__(self, pool: Optional[KVPool] = None, layer: int = 0, row: Optional[int] = None):
         self._pool = pool
         self._layer = layer
+        self._row = row   # None: the whole (batch-1) pool; r: row r of a batched pool
         self.offset = 0
         self._own = None  # standalone storage when used without a pool (API parity)
 
@@ -74,13 +75,19 @@ class KVCache(_BaseCache):
     @property
     def keys(self):
         if self._pool is not None:
-            return None if self._pool.buf is None else self._pool.buf[self._layer, 0]
+            if self._pool.buf is None:
+                return None
+            k = self._pool.buf[self._layer, 0]
+            return k if self._row is None else k[self._row:self._row + 1]
         return None if self._own is None else self._own[0]
 
     @property
     def values(self):
         if self._pool is not None:
-            return None if self._pool.buf is None else self._pool.buf[self._layer, 1]
+            if self._pool.buf is None:
+                return None
+            v = self._pool.buf[self._layer, 1]
+            return v if self._row is None else v[self._row:self._row + 1]
         return None if self._own is None else self._own[1]
 
     def update_and_fetch(self, keys: torch.Tensor, values: torch.Tensor):
@@ -377,3 +384,176 @@ class BatchKVCache(_BaseCache):
         if self.keys is None:
             return 0
         return self.keys.numel() * self.keys.element_size() + self.values.numel() * self.values.element_size()
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-resident batch cache of the lock-step decoder (csrc/decode_batch.cu)
+# ------------------------------------------------------------------------------------------------
+class BatchRows:
+    """Row bookkeeping of ONE batched device pool (layers, 2, rows, kv heads, capacity, head_dim)
+    shared by the per-layer `RowBatchKVCache` views.  Row b of the logical batch is row b of the
+    pool (live rows are kept compact); every row has its own length — there is no left padding
+    and no common write index, the kernels read the per-row lengths from device arrays.
+
+    `filter / extend / extract / trim` are the reference's BatchKVCache operations
+    (cache.py:1077-1201) as row copies inside / between pools (`b200_kv_copy_row`)."""
+
+    def __init__(self, pool: KVPool, engine, lengths: Optional[List[int]] = None):
+        self.pool = pool
+        self.eng = engine
+        self.lengths: List[int] = list(lengths or [])
+        self.version = 0   # bumped by every structural change (the decoder re-arms its rows)
+
+    @property
+    def B(self) -> int:
+        return len(self.lengths)
+
+    def _touch(self):
+        self.version += 1
+
+    def ensure(self, rows: int, tokens: int):
+        """room for `rows` rows of `tokens` positions (re-allocates and copies the live part)"""
+        p = self.pool
+        if rows > p.batch:
+            new = KVPool(p.n_layers, p.n_kv, p.hd, p.device, batch=rows, capacity=max(p.capacity, tokens),
+                         dtype=p.dtype)
+            with torch.cuda.stream(self.eng.stream):
+                for b, n in enumerate(self.lengths):
+                    self.eng.kv_copy_row(new, b, p, b, n)
+            new.generation = p.generation + 1
+            self.pool.__dict__.update(new.__dict__)
+            self._touch()
+        elif tokens > p.capacity:
+            self.eng.stream.synchronize()
+            with torch.cuda.stream(self.eng.stream):
+                p.reserve(tokens, live_tokens=max(self.lengths) if self.lengths else 0)
+            self._touch()
+
+    def filter(self, keep):
+        keep = [int(i) for i in keep]
+        assert keep == sorted(keep) and len(set(keep)) == len(keep), "filter: ascending unique row indices"
+        for new_i, old_i in enumerate(keep):
+            if new_i != old_i:
+                self.eng.kv_copy_row(self.pool, new_i, self.pool, old_i, self.lengths[old_i])
+        self.lengths = [self.lengths[i] for i in keep]
+        self._touch()
+
+    def extend(self, other: "BatchRows"):
+        n = max(self.lengths + other.lengths + [0])
+        self.ensure(self.B + other.B, n)
+        for b, ln in enumerate(other.lengths):
+            self.eng.kv_copy_row(self.pool, self.B + b, other.pool, b, ln)
+        self.lengths = self.lengths + list(other.lengths)
+        self._touch()
+
+    def append_row(self, src_pool: KVPool, src_row: int, length: int) -> int:
+        self.ensure(self.B + 1, max(self.lengths + [length]))
+        self.eng.kv_copy_row(self.pool, self.B, src_pool, src_row, length)
+        self.lengths.append(int(length))
+        self._touch()
+        return self.B - 1
+
+    def trim(self, n: int) -> int:
+        n = min([n] + self.lengths) if self.lengths else 0
+        self.lengths = [ln - n for ln in self.lengths]
+        self._touch()
+        return n
+
+    def layer_caches(self) -> List["RowBatchKVCache"]:
+        return [RowBatchKVCache(self, l) for l in range(self.pool.n_layers)]
+
+
+class RowBatchKVCache(_BaseCache):
+    """One layer's view of a `BatchRows` pool with the reference batch-cache surface
+    (`offset`, `keys`, `values`, `state`, `filter`, `extend`, `extract`, `trim`, `merge`, `size`,
+    `empty`, `nbytes`).  The pool is shared by all layers, so the structural operations act on the
+    WHOLE pool when invoked on layer 0 and are no-ops on the other layers (the reference calls them
+    on every layer's object in a loop; the net effect is the same)."""
+
+    def __init__(self, rows: BatchRows, layer: int):
+        self._rows = rows
+        self._layer = layer
+
+    @property
+    def offset(self):
+        import numpy as np
+        return np.asarray(self._rows.lengths, dtype=np.int64)
+
+    @property
+    def left_padding(self):
+        import numpy as np
+        return np.zeros(self._rows.B, dtype=np.int64)
+
+    @property
+    def keys(self):
+        return self._rows.pool.buf[self._layer, 0][:self._rows.B]
+
+    @property
+    def values(self):
+        return self._rows.pool.buf[self._layer, 1][:self._rows.B]
+
+    @property
+    def state(self):
+        n = self.size()
+        return self.keys[..., :n, :], self.values[..., :n, :], self.offset, self.left_padding
+
+    def size(self):
+        return max(self._rows.lengths) if self._rows.lengths else 0
+
+    def empty(self):
+        return self._rows.B == 0
+
+    def is_trimmable(self):
+        return True
+
+    @property
+    def batch_size(self) -> int:
+        return self._rows.B
+
+    def trim(self, n):
+        if self._layer == 0:
+            self._trimmed = self._rows.trim(n)
+            return self._trimmed
+        return min([n] + [ln + n for ln in self._rows.lengths]) if self._rows.lengths else 0
+
+    def filter(self, batch_indices):
+        if self._layer == 0:
+            idx = batch_indices.tolist() if hasattr(batch_indices, "tolist") else list(batch_indices)
+            self._rows.filter(idx)
+
+    def extend(self, other: "RowBatchKVCache"):
+        if self._layer == 0:
+            self._rows.extend(other._rows)
+
+    def extract(self, idx: int) -> KVCache:
+        """row `idx` as a standalone single-request KVCache of this layer (a copy)"""
+        n = self._rows.lengths[idx]
+        out = KVCache()
+        out.update_and_fetch(self.keys[idx:idx + 1, :, :n].clone(), self.values[idx:idx + 1, :, :n].clone())
+        return out
+
+    def make_mask(self, N: int, return_array: bool = False, **kwargs):
+        return None if N == 1 else "causal"   # per-row lengths are applied by the kernels
+
+    @property
+    def nbytes(self):
+        k = self.keys
+        return 2 * k.numel() * k.element_size()
+
+    @classmethod
+    def merge(cls, caches: List[KVCache], engine=None, rows: Optional[BatchRows] = None):
+        """Batch cache from single-request caches (cache.py:1180-1201).  `caches` are this layer's
+        pool-backed KVCache objects of the requests; the rows of ALL layers are copied when the
+        layer-0 caches are merged (one shared pool).  Returns this layer's view."""
+        c0 = caches[0]
+        if rows is None:
+            assert c0._pool is not None and engine is not None, "merge needs pool-backed caches and the engine"
+            p = c0._pool
+            cap = max(int(c.offset) for c in caches)
+            pool = KVPool(p.n_layers, p.n_kv, p.hd, p.device, batch=max(len(caches), 1), capacity=max(cap, 1),
+                          dtype=p.dtype)
+            rows = BatchRows(pool, engine)
+            with torch.cuda.stream(engine.stream):
+                for c in caches:
+                    rows.append_row(c._pool, c._row or 0, int(c.offset))
+        return cls(rows, c0._layer)

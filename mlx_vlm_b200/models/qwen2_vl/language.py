@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..base import LanguageModelOutput
-from ..cache import KVCache, KVPool
+from ..cache import BatchRows, KVCache, KVPool, RowBatchKVCache
 from .config import ModelConfig, TextConfig
 
 
@@ -116,6 +116,18 @@ class LanguageModel:
         self._pool = pool
         return [KVCache(pool, l) for l in range(self.args.num_hidden_layers)]
 
+    def make_cache_row(self, pool: KVPool, row: int):
+        """per-layer KVCache views of ROW `row` of a batched pool (a request admitted to a batch)"""
+        return [KVCache(pool, l, row=row) for l in range(self.args.num_hidden_layers)]
+
+    def make_batch_cache(self, rows: int, capacity: int = 0):
+        """device-resident batch cache for `rows` requests: (BatchRows, per-layer RowBatchKVCache)"""
+        eng = self._engine()
+        pool = KVPool(self.args.num_hidden_layers, self.args.num_key_value_heads, self.head_dim, eng.device,
+                      batch=rows, capacity=max(capacity, KVPool.step))
+        r = BatchRows(pool, eng)
+        return r, r.layer_caches()
+
     def _bind(self, cache, need_tokens: int) -> KVPool:
         c0 = cache[0]
         pool = getattr(c0, "_pool", None)
@@ -125,8 +137,11 @@ class LanguageModel:
         if pool.capacity < need_tokens:
             eng.stream.synchronize()
             with torch.cuda.stream(eng.stream):
-                pool.reserve(need_tokens, live_tokens=c0.offset)
+                # a batched pool moves as a whole: keep every row's live prefix
+                live = c0.offset if pool.batch == 1 else pool.capacity
+                pool.reserve(need_tokens, live_tokens=live)
         eng.bind_pool(pool)
+        eng.set_kv_row(c0._row or 0)
         return pool
 
     # ------------------------------------------------------------------ call
@@ -152,8 +167,12 @@ class LanguageModel:
         if ids_host.ndim == 1:
             ids_host = ids_host[None]
         B, L = ids_host.shape
+        if isinstance(cache[0], RowBatchKVCache):
+            return self._call_batch(ids_host, inputs_embeds, mask, cache, rope_deltas_kw, position_ids,
+                                    reserve_tokens)
         if B != 1:
-            raise NotImplementedError("batched LanguageModel calls arrive with BatchKVCache (next round)")
+            raise ValueError("a batch of rows needs a batch cache: LanguageModel.make_batch_cache(rows) "
+                             "(device-resident RowBatchKVCache)")
         position_ids, delta0 = self.resolve_position_ids(ids_host, cache_offset, position_ids, mask,
                                                          image_grid_thw, video_grid_thw, rope_deltas_kw)
 
@@ -247,7 +266,7 @@ class LanguageModel:
             if ids.shape[1] != 1:
                 return None
             if ids.shape[0] != 1:
-                return self._fused_greedy_batch(ids, cache, **kwargs)
+                return self._fused_greedy_batch(ids, cache, _inputs_tensor=inputs, **kwargs)
         rd = kwargs.get("rope_deltas", None)
         if rd is not None:
             self._rope_deltas = _np(rd)
@@ -264,9 +283,93 @@ class LanguageModel:
         self._fused_last = out
         return out
 
+    # ----------------------------------------------------------- batched rows
+    def _arm_batch(self, rows: BatchRows, toks, deltas, need: int):
+        eng = self._engine()
+        B = rows.B
+        d = np.zeros(B, dtype=np.int64) if deltas is None else np.asarray(deltas, dtype=np.int64).reshape(-1)[:B]
+        if d.shape[0] < B:
+            d = np.resize(d, B)
+        rows.ensure(B, need)
+        eng.bind_pool(rows.pool)
+        ctx = np.asarray(rows.lengths, dtype=np.int64)
+        eng.batch_begin(np.asarray(toks).reshape(-1)[:B], ctx, ctx + d, np.ones(B, dtype=np.int32))
+        self._batch_key = (id(rows), rows.version, rows.pool.buf.data_ptr())
+        self._batch_step = 0
+
     def _fused_greedy_batch(self, ids, cache, **kwargs):
-        """B > 1: the lock-step batched decode engine (models/batch_decode.py)."""
-        return None
+        """B > 1 rows in lock step (csrc/decode_batch.cu): ONE weight stream per step for all rows.
+        cache: per-layer RowBatchKVCache of `make_batch_cache` / `RowBatchKVCache.merge`."""
+        rows = getattr(cache[0], "_rows", None)
+        if rows is None or rows.B != ids.shape[0]:
+            return None
+        eng = self._engine()
+        inputs = kwargs.get("_inputs_tensor", None)
+        last = getattr(self, "_fused_last", None)
+        key = (id(rows), rows.version, rows.pool.buf.data_ptr() if rows.pool.buf is not None else 0)
+        chained = (last is not None and isinstance(inputs, torch.Tensor) and inputs.is_cuda and
+                   inputs.data_ptr() == last.data_ptr() and getattr(self, "_batch_key", None) == key and
+                   self._batch_step + 1 < eng.BATCH_LOG_STEPS and
+                   max(rows.lengths) + 1 <= rows.pool.capacity)
+        if not chained:
+            self._arm_batch(rows, ids[:, 0], kwargs.get("rope_deltas", None),
+                            max(max(rows.lengths) + 1, int(kwargs.get("reserve_tokens", 0))))
+        eng.batch_decode(1)
+        out = eng.batch_token_log_view()[self._batch_step, :rows.B]
+        self._batch_step += 1
+        rows.lengths = [n + 1 for n in rows.lengths]
+        self._fused_last = out
+        return out
+
+    def _call_batch(self, ids_host, inputs_embeds, mask, cache, rope_deltas_kw, position_ids, reserve_tokens):
+        """LanguageModel.__call__ for B rows with a device batch cache (language.py:404-518, batched
+        decode branch).  L == 1: one lock-step step, logits (B, 1, V).  L > 1: rows are prefilled
+        one by one into their pool rows (`mask` (B, L) marks each row's real, right-aligned tokens)."""
+        rows: BatchRows = cache[0]._rows
+        eng = self._engine()
+        B, L = ids_host.shape
+        V = self.args.vocab_size
+        if L == 1 and inputs_embeds is None:
+            assert B == rows.B, (B, rows.B)
+            self._arm_batch(rows, ids_host[:, 0], rope_deltas_kw,
+                            max(max(rows.lengths) + 1, int(reserve_tokens)))
+            eng.batch_decode(1)
+            self._batch_step = 1
+            self._fused_last = None
+            rows.lengths = [n + 1 for n in rows.lengths]
+            rows_logits = eng.empty((B, V))
+            from ... import _native as Nn
+            Nn.check(eng.lib.b200_memcpy_d2d(rows_logits.data_ptr(), eng.lib.b200_batch_logits(eng.h), B * V * 2,
+                                             eng.s), "memcpy_d2d")
+            return LanguageModelOutput(logits=rows_logits.view(B, 1, V))
+        # ---- prompt rows: batch-1 prefills into the pool rows (admission) ----
+        m = np.ones((B, L), dtype=np.int64) if mask is None else _np(mask)
+        if rows.B == 0:
+            rows.lengths = [0] * B
+        assert rows.B == B
+        rows.ensure(B, max(int(reserve_tokens), max(rows.lengths) + L))
+        out = eng.empty((B, 1, V))
+        from ... import _native as Nn
+        deltas = []
+        for b in range(B):
+            n = int(m[b].sum())
+            sub = ids_host[b:b + 1, L - n:]
+            emb = None if inputs_embeds is None else inputs_embeds[b:b + 1, L - n:]
+            saved = (self._rope_deltas, self._position_ids)
+            self._rope_deltas, self._position_ids = None, None
+            rc = self.make_cache_row(rows.pool, b)
+            for c in rc:
+                c.offset = rows.lengths[b]
+            pid = None if position_ids is None else _np(position_ids)[:, b:b + 1, L - n:]
+            o = self(sub, inputs_embeds=emb, cache=rc, position_ids=pid, logits_to_keep=1,
+                     reserve_tokens=rows.pool.capacity)
+            Nn.check(eng.lib.b200_memcpy_d2d(out[b].data_ptr(), o.logits.data_ptr(), V * 2, eng.s), "memcpy_d2d")
+            deltas.append(0 if self._rope_deltas is None else int(np.asarray(self._rope_deltas).reshape(-1)[0]))
+            self._rope_deltas, self._position_ids = saved
+            rows.lengths[b] += n
+        rows._touch()
+        self._batch_rope_deltas = np.asarray(deltas, dtype=np.int64).reshape(-1, 1)
+        return LanguageModelOutput(logits=out)
 
     def fused_greedy_decode_n(self, n_steps: int, cache, reserve_tokens: int = 0):
         """`n_steps` greedy decode steps entirely on the device (token feedback through device

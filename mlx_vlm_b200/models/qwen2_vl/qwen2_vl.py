@@ -36,6 +36,47 @@ def embed_tokens(eng: Engine, ids_host: np.ndarray) -> torch.Tensor:
     return out
 
 
+def weight_manifest(c: N.Qwen2VLConfig):
+    """(engine name, shape) of every tensor of the engine layout, in a fixed order."""
+    E, Em, mg = c.v_embed, c.v_mlp, c.v_merge ** 2 * c.v_embed
+    H, I = c.hidden, c.inter
+    QKV = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim
+    out = [("v.patch_embed.w", (E, c.v_patch_dim))]
+    for i in range(c.v_depth):
+        q = f"v.blk.{i}."
+        out += [(q + "ln1.w", (E,)), (q + "ln1.b", (E,)), (q + "ln2.w", (E,)), (q + "ln2.b", (E,)),
+                (q + "qkv.w", (3 * E, E)), (q + "qkv.b", (3 * E,)), (q + "proj.w", (E, E)), (q + "proj.b", (E,)),
+                (q + "fc1.w", (Em, E)), (q + "fc1.b", (Em,)), (q + "fc2.w", (E, Em)), (q + "fc2.b", (E,))]
+    out += [("v.merger.ln.w", (E,)), ("v.merger.ln.b", (E,)), ("v.merger.fc1.w", (mg, mg)), ("v.merger.fc1.b", (mg,)),
+            ("v.merger.fc2.w", (c.v_out, mg)), ("v.merger.fc2.b", (c.v_out,))]
+    out += [("lm.embed", (c.vocab, H)), ("lm.norm", (H,))]
+    if not c.tie_embeddings:
+        out.append(("lm.head", (c.vocab, H)))
+    for i in range(c.n_layers):
+        q = f"lm.{i}."
+        out += [(q + "ln1", (H,)), (q + "ln2", (H,)), (q + "wqkv", (QKV, H)), (q + "bqkv", (QKV,)),
+                (q + "wo", (H, c.n_heads * c.head_dim)), (q + "wgu", (2 * I, H)), (q + "wd", (H, I))]
+    return out
+
+
+class WeightArena:
+    """ONE device buffer for all weights of a replica (views at 256-byte aligned offsets): the
+    multi-GPU start-up is then a single NCCL broadcast of `flat` (parallel.broadcast_packed)."""
+
+    def __init__(self, manifest, device):
+        self.offsets = {}
+        off = 0
+        for name, shape in manifest:
+            n = int(np.prod(shape))
+            self.offsets[name] = (off, shape)
+            off += (n + 127) // 128 * 128
+        self.flat = torch.empty(off, dtype=torch.bfloat16, device=device)
+
+    def view(self, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        return self.flat[off:off + int(np.prod(shape))].view(*shape)
+
+
 class Model:
     def __init__(self, config: ModelConfig, device=None):
         self.config = config
@@ -66,6 +107,22 @@ class Model:
         if self._eng is None:
             self._eng = Engine(self.native_config(), self._device)
         return self._eng
+
+    def _arena(self) -> WeightArena:
+        if getattr(self, "_weights", None) is None:
+            self._weights = WeightArena(weight_manifest(self.native_config()), self._engine().device)
+        return self._weights
+
+    @property
+    def packed_weights(self) -> torch.Tensor:
+        """the flat device buffer every engine weight is a view of"""
+        return self._arena().flat
+
+    def _put(self, name: str, value: torch.Tensor):
+        """copy `value` into the arena view of `name` (bf16) and register it with the engine"""
+        v = self._arena().view(name)
+        v.copy_(value.reshape(v.shape).to(device=v.device, dtype=torch.bfloat16))
+        self._engine().set_weight(name, v)
 
     @property
     def engine(self) -> Engine:
@@ -104,7 +161,8 @@ class Model:
 
         w = self.vision_tower.sanitize({k: x for k, x in weights.items() if "vision_tower" in k})
         E = v.embed_dim
-        eng.set_weight("v.patch_embed.w", dv(w["vision_tower.patch_embed.proj.weight"].reshape(E, -1)))
+        put = self._put
+        put("v.patch_embed.w", w["vision_tower.patch_embed.proj.weight"].reshape(E, -1))
         for i in range(v.depth):
             p, q = f"vision_tower.blocks.{i}.", f"v.blk.{i}."
             for a, b in (("norm1.weight", "ln1.w"), ("norm1.bias", "ln1.b"), ("norm2.weight", "ln2.w"),
@@ -112,26 +170,23 @@ class Model:
                          ("attn.proj.weight", "proj.w"), ("attn.proj.bias", "proj.b"),
                          ("mlp.fc1.weight", "fc1.w"), ("mlp.fc1.bias", "fc1.b"),
                          ("mlp.fc2.weight", "fc2.w"), ("mlp.fc2.bias", "fc2.b")):
-                eng.set_weight(q + b, dv(get(p + a)))
+                put(q + b, get(p + a))
         for a, b in (("ln_q.weight", "ln.w"), ("ln_q.bias", "ln.b"), ("mlp.0.weight", "fc1.w"),
                      ("mlp.0.bias", "fc1.b"), ("mlp.2.weight", "fc2.w"), ("mlp.2.bias", "fc2.b")):
-            eng.set_weight("v.merger." + b, dv(get("vision_tower.merger." + a)))
-        eng.set_weight("lm.embed", dv(get("language_model.model.embed_tokens.weight")))
-        eng.set_weight("lm.norm", dv(get("language_model.model.norm.weight")))
+            put("v.merger." + b, get("vision_tower.merger." + a))
+        put("lm.embed", get("language_model.model.embed_tokens.weight"))
+        put("lm.norm", get("language_model.model.norm.weight"))
         if not t.tie_word_embeddings:
-            eng.set_weight("lm.head", dv(get("language_model.lm_head.weight")))
+            put("lm.head", get("language_model.lm_head.weight"))
         for i in range(t.num_hidden_layers):
             p, q = f"language_model.model.layers.{i}.", f"lm.{i}."
-            eng.set_weight(q + "ln1", dv(get(p + "input_layernorm.weight")))
-            eng.set_weight(q + "ln2", dv(get(p + "post_attention_layernorm.weight")))
-            eng.set_weight(q + "wqkv", dv(torch.cat([get(p + f"self_attn.{n}_proj.weight").to(dev)
-                                                     for n in "qkv"], 0)))
-            eng.set_weight(q + "bqkv", dv(torch.cat([get(p + f"self_attn.{n}_proj.bias").to(dev)
-                                                     for n in "qkv"], 0)))
-            eng.set_weight(q + "wo", dv(get(p + "self_attn.o_proj.weight")))
-            eng.set_weight(q + "wgu", dv(torch.cat([get(p + "mlp.gate_proj.weight").to(dev),
-                                                    get(p + "mlp.up_proj.weight").to(dev)], 0)))
-            eng.set_weight(q + "wd", dv(get(p + "mlp.down_proj.weight")))
+            put(q + "ln1", get(p + "input_layernorm.weight"))
+            put(q + "ln2", get(p + "post_attention_layernorm.weight"))
+            put(q + "wqkv", torch.cat([get(p + f"self_attn.{n}_proj.weight").to(dev) for n in "qkv"], 0))
+            put(q + "bqkv", torch.cat([get(p + f"self_attn.{n}_proj.bias").to(dev) for n in "qkv"], 0))
+            put(q + "wo", get(p + "self_attn.o_proj.weight"))
+            put(q + "wgu", torch.cat([get(p + "mlp.gate_proj.weight").to(dev), get(p + "mlp.up_proj.weight").to(dev)], 0))
+            put(q + "wd", get(p + "mlp.down_proj.weight"))
         torch.cuda.synchronize(dev)
 
     def init_random(self, seed: int = 0, std: float = 0.02):
@@ -152,31 +207,16 @@ class Model:
             return torch.zeros(n, device=eng.device, dtype=torch.bfloat16)
 
         c = self.native_config()
-        E, Em, mg = c.v_embed, c.v_mlp, c.v_merge ** 2 * c.v_embed
-        eng.set_weight("v.patch_embed.w", rnd(E, c.v_patch_dim))
-        for i in range(c.v_depth):
-            q = f"v.blk.{i}."
-            eng.set_weight(q + "ln1.w", ones(E)); eng.set_weight(q + "ln1.b", zeros(E))
-            eng.set_weight(q + "ln2.w", ones(E)); eng.set_weight(q + "ln2.b", zeros(E))
-            eng.set_weight(q + "qkv.w", rnd(3 * E, E)); eng.set_weight(q + "qkv.b", rnd(3 * E))
-            eng.set_weight(q + "proj.w", rnd(E, E)); eng.set_weight(q + "proj.b", rnd(E))
-            eng.set_weight(q + "fc1.w", rnd(Em, E)); eng.set_weight(q + "fc1.b", rnd(Em))
-            eng.set_weight(q + "fc2.w", rnd(E, Em)); eng.set_weight(q + "fc2.b", rnd(E))
-        eng.set_weight("v.merger.ln.w", ones(E)); eng.set_weight("v.merger.ln.b", zeros(E))
-        eng.set_weight("v.merger.fc1.w", rnd(mg, mg)); eng.set_weight("v.merger.fc1.b", rnd(mg))
-        eng.set_weight("v.merger.fc2.w", rnd(c.v_out, mg)); eng.set_weight("v.merger.fc2.b", rnd(c.v_out))
-        H, I = c.hidden, c.inter
-        QKV = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim
-        eng.set_weight("lm.embed", rnd(c.vocab, H))
-        eng.set_weight("lm.norm", ones(H))
-        if not c.tie_embeddings:
-            eng.set_weight("lm.head", rnd(c.vocab, H))
-        for i in range(c.n_layers):
-            q = f"lm.{i}."
-            eng.set_weight(q + "ln1", ones(H)); eng.set_weight(q + "ln2", ones(H))
-            eng.set_weight(q + "wqkv", rnd(QKV, H)); eng.set_weight(q + "bqkv", rnd(QKV))
-            eng.set_weight(q + "wo", rnd(H, c.n_heads * c.head_dim))
-            eng.set_weight(q + "wgu", rnd(2 * I, H)); eng.set_weight(q + "wd", rnd(H, I))
+        arena = self._arena()
+        for name, shape in weight_manifest(c):
+            v = arena.view(name)
+            if name.endswith(("ln1.w", "ln2.w", "ln.w", ".ln1", ".ln2", "lm.norm")):
+                v.fill_(1.0)              # norm weights 1
+            elif name.endswith(("ln1.b", "ln2.b", "ln.b")):
+                v.zero_()                 # norm biases 0
+            else:
+                v.copy_(rnd(*shape))
+            eng.set_weight(name, v)
         torch.cuda.synchronize(eng.device)
         return self
 

@@ -3,9 +3,12 @@
 `prepare_inputs` :1918-2136, `load_image`/`process_image` :1503-1567,
 `StoppingCriteria` :2191-2249).
 
-B200-first differences: safetensors shards are read straight into pinned host
-memory and packed into the engine's device layout (bf16); inputs are moved to
-the device with one pinned-memory H2D copy per tensor on the generation stream.
+B200-first differences: safetensors shards are memory-mapped on the host and every tensor is
+packed (q/k/v and gate/up fused, conv layout fixed) straight into ONE device arena
+(`Model.packed_weights`, bf16) — which is also what a multi-GPU start-up broadcasts with a single
+NCCL call; inputs are moved to the device with one pinned-memory H2D copy per tensor on the
+generation stream.  `lazy` has no meaning here (weights must be resident for the kernels);
+`revision` is rejected (local directories only, no hub).
 """
 from __future__ import annotations
 
@@ -88,13 +91,17 @@ def load(path_or_hf_repo: str, adapter_path: Optional[str] = None, lazy: bool = 
     random-init model with a SyntheticProcessor (benchmarks, no checkpoint)."""
     if adapter_path is not None:
         raise NotImplementedError("adapters (LoRA) are outside the B200 hot-path scope")
+    if revision is not None:
+        raise NotImplementedError("`revision` needs the hub; only local model directories are supported")
     if path_or_hf_repo.startswith("synthetic:"):
         return load_synthetic(path_or_hf_repo.split(":", 1)[1], **kwargs)
     if not os.path.isdir(path_or_hf_repo):
         raise FileNotFoundError(
             f"{path_or_hf_repo}: only local model directories are supported (no hub download)")
+    processor = kwargs.pop("processor", None)   # a ready ProcessorLike (tests / custom pipelines)
     model = load_model(path_or_hf_repo, lazy=lazy, strict=strict, device=kwargs.pop("device", None))
-    processor = load_processor(path_or_hf_repo)
+    if processor is None:
+        processor = load_processor(path_or_hf_repo)
     return model, processor
 
 

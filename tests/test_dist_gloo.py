@@ -18,7 +18,7 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from mlx_vlm_b200.parallel import broadcast_weights, max_over_ranks, shard_requests
+    from mlx_vlm_b200.parallel import broadcast_packed, broadcast_weights, max_over_ranks, shard_requests
     g = torch.Generator().manual_seed(100 + rank)  # different init on every rank
     w = {"b": torch.randn(7, 5, generator=g), "a": torch.randn(33, generator=g).to(torch.bfloat16)}
     nbytes = broadcast_weights(w, src=0)
@@ -26,6 +26,12 @@ def _worker(rank, world, port, ret):
     want_b = torch.randn(7, 5, generator=ref)
     want_a = torch.randn(33, generator=ref).to(torch.bfloat16)
     ok = torch.equal(w["b"], want_b) and torch.equal(w["a"], want_a) and nbytes == 7 * 5 * 4 + 33 * 2
+    # the packed arena: every weight is a view of ONE flat buffer -> one broadcast moves them all
+    flat_w = torch.randn(1000, generator=g).to(torch.bfloat16)
+    views = [flat_w[0:128].view(8, 16), flat_w[256:300]]
+    nb = broadcast_packed(flat_w, src=0)
+    want_flat = torch.randn(1000, generator=ref).to(torch.bfloat16)
+    ok = ok and nb == 2000 and torch.equal(views[0], want_flat[0:128].view(8, 16)) and torch.equal(views[1], want_flat[256:300])
     mine = shard_requests(11, world, rank)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
@@ -47,6 +53,12 @@ def _worker(rank, world, port, ret):
         model, proc = _fake_model()
         return BatchGenerator(model, proc, completion_batch_size=2, prefill_batch_size=2, decode_slice=4)
     got = generate_sharded(make, prompts, maxes)
+    ok = ok and got == [_alone(p, m)[0] for p, m in zip(prompts, maxes)]
+
+    def make_lockstep():   # the same through the lock-step batched decoder's host logic
+        model, proc = _fake_model(lockstep=True)
+        return BatchGenerator(model, proc, completion_batch_size=3, prefill_batch_size=2, decode_slice=4)
+    got = generate_sharded(make_lockstep, prompts, maxes)
     ok = ok and got == [_alone(p, m)[0] for p, m in zip(prompts, maxes)]
     ret[rank] = ok
     dist.destroy_process_group()
