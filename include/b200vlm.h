@@ -51,6 +51,8 @@ int b200_cast_f32_bf16(const float* src, void* dst, long n, void* stream);
 #define B200_WT_BF16 0    /* C[t][n] = epi(bf16(acc + bias)) (+ residual), bf16            */
 #define B200_WT_PARTIAL 1 /* fp32 split-K partial tiles P[split][t][n] (finish_rows adds them) */
 #define B200_WT_SWIGLU 2  /* W = [gate rows; up rows]: C[t][i] = silu(gate) * up, bf16     */
+#define B200_WT_F32 3     /* fp32 output (bias, fp32 activation, fp32 residual): fp32 towers  */
+#define B200_WT_SPLIT 4   /* fp32 result written as [hi | lo] bf16 halves (next GEMM's operand) */
 #define B200_NORM_NONE 0
 #define B200_NORM_RMS 1   /* mx.fast.rms_norm   (language.py:139-140)                      */
 #define B200_NORM_LN 2    /* mx.fast.layer_norm (vision.py:180-181)                        */
@@ -58,6 +60,7 @@ int b200_cast_f32_bf16(const float* src, void* dst, long n, void* stream);
 #define B200_EPI_NONE 0
 #define B200_EPI_GELU_FAST 1  /* nn.GELU(approx="fast")  vision.py:167          */
 #define B200_EPI_GELU_EXACT 2 /* nn.GELU()               vision.py:112          */
+#define B200_EPI_GELU_TANH 3  /* nn.GELU(approx="precise") (fp32 towers only)   */
 
 /* nn.Linear / nn.Conv3d(kernel==stride) / Embedding.as_linear:
  *   C[M,N] = epi( bf16( A[M,K] . W[N,K]^T + bias[N] ) )  then, if residual,
@@ -159,6 +162,8 @@ typedef struct {
   /* vision (config.py:9-23) */
   int v_depth, v_embed, v_heads, v_mlp, v_patch_dim, v_merge, v_out;
   float v_ln_eps;
+  int external_vision; /* 1: the engine holds the language model only (LLaVA / Idefics2: their fp32 towers
+                          run through the tower ops); no v.* weights are required */
 } b200_qwen2vl_config;
 
 int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine** out);
@@ -248,6 +253,37 @@ int b200_engine_set_attn_cluster(b200_engine* e, int cluster);
  * copy n generated ids [start, start+n) of the token log to HOST (pinned) memory;
  * copy the current logits/logprobs vector into a caller buffer (device). */
 int b200_engine_fetch_tokens(b200_engine* e, long start, int n, int* host_out, void* stream);
+/* ------------------------------------------------------------------------- */
+/* fp32-accurate vision towers (LLaVA-1.5 CLIP, Idefics2 SigLIP + perceiver):    */
+/* the reference runs them in fp32 with bf16-valued weights (llava.py:61-63,     */
+/* idefics2.py:212-251).  Activations travel as split operands [hi | lo] (two    */
+/* bf16 halves of an fp32 value, n_pad columns apart); the GEMMs run on the      */
+/* tensor cores (W.x = W.x_hi + W.x_lo, fp32 accumulate), the rest in fp32.      */
+/* ------------------------------------------------------------------------- */
+/* nn.LayerNorm on fp32 rows -> fp32 and / or split output (llava/vision.py:84-104, idefics2/vision.py:94-121) */
+int b200_f32_layer_norm(const float* x, long ldx, const void* w, const void* b, float eps, float* out32,
+                        long ld32, void* out_split, long ld_split, int n_pad, int T, int N, void* stream);
+int b200_f32_split(const float* x, long ldx, void* out_split, long ld_split, int n_pad, int T, int N, void* stream);
+/* Conv2d(kernel == stride) patch rows, (kh, kw, c) order, from NHWC fp32 pixels, as a split operand
+ * [B*gh*gw, Kp | Kp] (llava/vision.py:108-127, idefics2/vision.py:123-148) */
+int b200_clip_patchify(const float* pixels_nhwc, int B, int H, int W, int C, int patch, void* out_split, int Kp,
+                       void* stream);
+/* class token + learned positions (CLIP), or positions gathered by pos_ids (SigLIP, idefics2/vision.py:150-173;
+ * negative ids index from the end like numpy) */
+int b200_tower_embed(const float* patch, const void* cls, const void* pos, const int* pos_ids, float* emb, int B,
+                     int P, int E, int n_pos, void* stream);
+/* fp32 SDPA (mx.fast.scaled_dot_product_attention on fp32 arrays), n_seg independent segments of Lq queries /
+ * S keys q_seg / k_seg tokens apart; optional key mask [n_seg][S]; output fp32 and / or split */
+int b200_attention_f32(const float* q, long q_ts, long q_hs, const float* k, long k_ts, long k_hs, const float* v,
+                       long v_ts, long v_hs, float* out32, long o_ts, void* out_split, long os_ts, int n_pad,
+                       int n_heads, int n_kv, int hd, int Lq, int S, int n_seg, long q_seg, long k_seg,
+                       const unsigned char* key_mask, float scale, void* stream);
+/* nn.Linear on fp32 activations: X split operand [T, n_parts x Kp], W [N, K_w] bf16 (row pitch ldw);
+ * mode B200_WT_F32: C32 = act(acc + bias) + res32; mode B200_WT_SPLIT: Csplit = [hi | lo] of act(acc + bias) */
+int b200_gemm_wt_f32(const void* X, long ldx, const void* W, long ldw, const void* bias, const float* res32,
+                     long ldr32, float* C32, long ldc32, void* Csplit, long ld_split, int n_pad, int T, int N,
+                     int K_w, int n_parts, int epilogue, int mode, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Lock-step batched decode (continuous batching; generate/ar.py:929-1390        */
 /* GenerationBatch, models/cache.py:972-1201 BatchKVCache)                       */

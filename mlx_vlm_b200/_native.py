@@ -27,7 +27,7 @@ class Qwen2VLConfig(C.Structure):
         ("tie_embeddings", C.c_int),
         ("v_depth", C.c_int), ("v_embed", C.c_int), ("v_heads", C.c_int), ("v_mlp", C.c_int),
         ("v_patch_dim", C.c_int), ("v_merge", C.c_int), ("v_out", C.c_int),
-        ("v_ln_eps", C.c_float),
+        ("v_ln_eps", C.c_float), ("external_vision", C.c_int),
     ]
 
 
@@ -78,6 +78,13 @@ SIGNATURES = {
     "b200_engine_debug_buffer": (_I, [_P, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long)]),
     "b200_engine_device_error": (_I, [_P, C.POINTER(_I)]),
     "b200_engine_fetch_tokens": (_I, [_P, _L, _I, _P, _P]),
+    "b200_f32_layer_norm": (_I, [_P, _L, _P, _P, _F, _P, _L, _P, _L, _I, _I, _I, _P]),
+    "b200_f32_split": (_I, [_P, _L, _P, _L, _I, _I, _I, _P]),
+    "b200_clip_patchify": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "b200_tower_embed": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200_attention_f32": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _L, _L,
+                                _P, _F, _P]),
+    "b200_gemm_wt_f32": (_I, [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_engine_set_kv_row": (_I, [_P, _I]),
     "b200_batch_begin": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "b200_batch_decode": (_I, [_P, _I, _I, _P]),

@@ -123,6 +123,12 @@ __device__ __forceinline__ void f_tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void f_sbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// 2^x on the SFU (one MUFU instruction, rel. error 2^-22: far below the bf16 rounding of p that follows)
+__device__ __forceinline__ float f_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -244,29 +250,41 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int vis = (qi < p.Lq) ? (p.causal ? min(S, S - p.Lq + qi + 1) : S) : S;
     const uint32_t t_row = tmem + ((uint32_t)(q4 * 32) << 16);
     constexpr float LOG2E = 1.4426950408889634f;
+    // The softmax warps are the instruction-bound part of the kernel (2 warps per scheduler, 288+ score
+    // elements per thread and pass), so the inner loops are kept to ~6 instructions per element: bf16
+    // rounding by cvt + shift, one FMA into the exponent, ex2 on the SFU, multiplication by 1/l.
     float m = -INFINITY, l = 0.f;
     for (int i = 0; i < n_tiles; ++i) {  // ---- pass 1: row max and sum of exp over bf16 scores ----
       const int s = i & 1;
       f_wait(&bars.s_full[s], (i >> 1) & 1);
       f_fence_after();
+      const int jbase = i * FA_TK + half * 64;
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t r[32];
         f_tmem_ld32(t_row + (uint32_t)(s * 128 + half * 64 + c0), r);
         float sc[32];
         float cm = -INFINITY;
+        if (jbase + c0 + 32 <= vis) {  // whole chunk visible: no per-element mask
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int j = i * FA_TK + half * 64 + c0 + e;
-          sc[e] = (j < vis) ? rbf(__uint_as_float(r[e])) : -INFINITY;
-          cm = fmaxf(cm, sc[e]);
+          for (int e = 0; e < 32; ++e) {
+            sc[e] = rbf(__uint_as_float(r[e]));
+            cm = fmaxf(cm, sc[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            sc[e] = (jbase + c0 + e < vis) ? rbf(__uint_as_float(r[e])) : -INFINITY;
+            cm = fmaxf(cm, sc[e]);
+          }
         }
         if (cm > -INFINITY) {
           const float mn = fmaxf(m, cm);
+          const float nb = -mn * LOG2E;
           float add = 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) add += exp2f((sc[e] - mn) * LOG2E);
-          l = l * exp2f((m - mn) * LOG2E) + add;
+          for (int e = 0; e < 32; ++e) add += f_ex2(fmaf(sc[e], LOG2E, nb));
+          l = l * f_ex2((m - mn) * LOG2E) + add;
           m = mn;
         }
       }
@@ -278,27 +296,29 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     {
       const float2 a = stat[0][row], b = stat[1][row];
       m = fmaxf(a.x, b.x);
-      l = (a.y > 0.f ? a.y * exp2f((a.x - m) * LOG2E) : 0.f) + (b.y > 0.f ? b.y * exp2f((b.x - m) * LOG2E) : 0.f);
+      l = (a.y > 0.f ? a.y * f_ex2((a.x - m) * LOG2E) : 0.f) + (b.y > 0.f ? b.y * f_ex2((b.x - m) * LOG2E) : 0.f);
     }
     const float inv_l = 1.0f / l;
-    (void)inv_l;
+    const float nbm = -m * LOG2E;
     for (int j = 0; j < n_tiles; ++j) {  // ---- pass 2: p = bf16(exp(s - m) / l) -> shared memory ----
       const int i = n_tiles + j, s = i & 1;
       f_wait(&bars.s_full[s], (i >> 1) & 1);
       f_fence_after();
       f_wait(&bars.p_empty, (j & 1) ^ 1);  // the previous P.V has consumed the P tile
       uint8_t* prow = Ps + half * FA_BLK + row * 128;
+      const int jbase = j * FA_TK + half * 64;
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t r[32];
         f_tmem_ld32(t_row + (uint32_t)(s * 128 + half * 64 + c0), r);
+        const bool full = jbase + c0 + 32 <= vis;
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           float pv[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int key = j * FA_TK + half * 64 + c0 + e + u;
-            pv[u] = (key < vis) ? exp2f((rbf(__uint_as_float(r[e + u])) - m) * LOG2E) / l : 0.f;
+            const float pe = f_ex2(fmaf(rbf(__uint_as_float(r[e + u])), LOG2E, nbm)) * inv_l;
+            pv[u] = (full || jbase + c0 + e + u < vis) ? pe : 0.f;
           }
           uint4 o;
           o.x = pack2(pv[0], pv[1]); o.y = pack2(pv[2], pv[3]); o.z = pack2(pv[4], pv[5]); o.w = pack2(pv[6], pv[7]);

@@ -139,6 +139,14 @@ int launch_sample(const DecodeDims& d, const bf16* logits, const float2* partial
 int launch_set_state(DecState* st, int tok, int ctx, int pos, int use_force, int set_tok,
                      const bf16* E, bf16* h, int hidden, cudaStream_t s);
 
+// where the bound KV pool lives (device copy: kernels of captured graphs read it instead of baked pointers)
+struct KvRef {
+  bf16* k0;            // K plane of layer 0, bound row
+  long layer_stride;   // elements between layers
+  long v_off;          // elements from a K plane to its V plane
+  int cap;
+};
+
 // row ops / gemm / attention (other translation units)
 int cast_f32_bf16(const float* src, void* dst, long n, cudaStream_t st);
 int layer_norm(const void* x, const void* w, const void* b, void* y, int rows, int dim, float eps,
@@ -148,7 +156,8 @@ int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, 
                 int hd, cudaStream_t st);
 int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
                    void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
-                   cudaStream_t st, float q_scale = 0.f, void* vt = nullptr, int t_ld = 0);
+                   cudaStream_t st, float q_scale = 0.f, void* vt = nullptr, int t_ld = 0,
+                   const KvRef* ref = nullptr, int layer = 0, void* kws = nullptr);
 int vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads, int hd,
                     float scale, void* vt, int t_ld, cudaStream_t st);
 bool attention_fa_supported(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
@@ -166,13 +175,26 @@ int gemm_bf16_tn(const void* A, long lda, const void* W, const void* bias, const
 struct WtConfig {
   int TN, KS, stages, split;
 };
+// extension for the fp32-accurate (split bf16) GEMMs of the LLaVA / Idefics2 towers
+struct WtExt {
+  int kb_w;          // > 0: X holds n parts [x_hi | x_lo | ..] of kb_w k-blocks each; W k-block = k-block % kb_w
+  int k_w;           // columns of W (kb_w > 0)
+  long ldw;          // row pitch of W in elements (0: k_w)
+  float* C32;        // B200_WT_F32 output
+  const float* res32;
+  long ldc32, ldr32;
+  bf16* Csplit;      // B200_WT_SPLIT output [hi | lo]
+  long ld_split;
+  int n_pad;         // columns between the hi and the lo half
+};
 void gemm_wt_auto(int T, int row_blocks, int K, bool allow_split, WtConfig* c, int sm_count);
 int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
             void* C, long ldc, float* partial, int T, int N, int K, int epilogue, int mode, int inter,
-            const WtConfig& cfg, unsigned flags, cudaStream_t st);
+            const WtConfig& cfg, unsigned flags, cudaStream_t st, const WtExt* ext = nullptr);
 int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
                   void* C, long ldc, float* partial, long partial_bytes, int T, int N, int K, int epilogue,
-                  int mode, int inter, bool allow_split, int sm_count, int* split_out, cudaStream_t st);
+                  int mode, int inter, bool allow_split, int sm_count, int* split_out, cudaStream_t st,
+                  const WtExt* ext = nullptr);
 int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
                 long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn, long ldx,
                 int T, int N, cudaStream_t st);

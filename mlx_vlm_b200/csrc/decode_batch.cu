@@ -96,7 +96,11 @@ template <int HD>
 __global__ void __launch_bounds__(256) bd_attn_kernel(const BdAttnP p) {
   bd_pdl_launch();
   extern __shared__ __align__(16) uint8_t bd_sm[];
-  constexpr int EPL = HD / 32, NCH = HD / 8, AG = BD_AG, half = HD / 2;
+  constexpr int NCH = HD / 8, AG = BD_AG, half = HD / 2;
+  constexpr int SEG = HD / 8;   // dims per lane in the P.V phase (lane = key sub-index x dim segment)
+  constexpr int NV = SEG / 8;   // 16-byte vectors per lane and key
+  constexpr int VU = 8;         // key trips in flight per warp in the P.V phase (32 keys)
+  constexpr int PMAX = 12;      // split-K partials summed with all loads in flight
   float* qs = reinterpret_cast<float*>(bd_sm);  // [AG][HD] q * scale (rotated)
   float* kn = qs + AG * HD;                     // [HD] new key (rotated)
   float* vn = kn + HD;                          // [HD] new value
@@ -115,12 +119,29 @@ __global__ void __launch_bounds__(256) bd_attn_kernel(const BdAttnP p) {
   bd_pdl_wait();
   const int ctx = p.ctx[row], pos = p.pos[row];
   const int nkeys = ctx + 1;
+  // Every dependent global round trip costs ~1 us here, so the requests are issued as early as their
+  // addresses are known: the first block of cached keys (one row per lane) goes out BEFORE the
+  // split-K partials of q/k/v are summed, the first block of values before the softmax.
+  uint4 kfirst[NCH];
+  {
+    const int j = warp * 32 + lane;
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long)j * HD);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) kfirst[c] = (j < ctx) ? __ldcg(kr + c) : make_uint4(0, 0, 0, 0);
+  }
   // ---- finish q (G heads), k, v of this step: sum of the split-K partials + bias, one rounding ----
   for (int i = threadIdx.x; i < (G + 2) * HD; i += 256) {
     const int slot = i / HD, j = i % HD;
     const int n = (slot < G ? (h0 + slot) : (slot == G ? p.n_heads + kvh : p.n_heads + p.n_kv + kvh)) * HD + j;
     float a = 0.f;
-    for (int s = 0; s < p.S; ++s) a += __ldcg(p.P + ((long)s * p.B + row) * p.QKV + n);
+    for (int s0 = 0; s0 < p.S; s0 += PMAX) {
+      float v[PMAX];
+#pragma unroll
+      for (int u = 0; u < PMAX; ++u)
+        v[u] = (s0 + u < p.S) ? __ldcg(p.P + ((long)(s0 + u) * p.B + row) * p.QKV + n) : 0.f;
+#pragma unroll
+      for (int u = 0; u < PMAX; ++u) a += v[u];
+    }
     a = rbf(a + bf2f(p.bias[n]));
     (slot < G ? qs + slot * HD : (slot == G ? kn : vn))[j] = a;
   }
@@ -155,13 +176,17 @@ __global__ void __launch_bounds__(256) bd_attn_kernel(const BdAttnP p) {
   for (int g = 0; g < AG; ++g) lm[g] = -INFINITY;
   for (int j0 = warp * 32; j0 < nkeys; j0 += 256) {
     const int j = j0 + lane;
-    if (j < nkeys) {
-      uint4 kv[NCH];
-      if (j < ctx) {
-        const uint4* kr = reinterpret_cast<const uint4*>(kb + (long)j * HD);
+    uint4 kv[NCH];
+    if (j0 == warp * 32) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) kv[c] = __ldcg(kr + c);
-      } else {
+      for (int c = 0; c < NCH; ++c) kv[c] = kfirst[c];
+    } else if (j < ctx) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kb + (long)j * HD);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) kv[c] = __ldcg(kr + c);
+    }
+    if (j < nkeys) {
+      if (j == ctx) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           kv[c].x = pack2(kn[c * 8 + 0], kn[c * 8 + 1]); kv[c].y = pack2(kn[c * 8 + 2], kn[c * 8 + 3]);
@@ -190,6 +215,17 @@ __global__ void __launch_bounds__(256) bd_attn_kernel(const BdAttnP p) {
         lm[g] = fmaxf(lm[g], r);
       }
     }
+  }
+  // first block of values: warp w, trip q, key = 32 * w + 4 * q + ksub; lane = (ksub, dim segment)
+  const int seg = lane & 7, ksub = lane >> 3;
+  uint4 vfirst[VU][NV];
+#pragma unroll
+  for (int q = 0; q < VU; ++q) {
+    const int j = warp * 32 + q * 4 + ksub;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      vfirst[q][v] = (j < ctx) ? __ldcg(reinterpret_cast<const uint4*>(vb + (long)j * HD + seg * SEG + v * 8))
+                               : make_uint4(0, 0, 0, 0);
   }
 #pragma unroll
   for (int g = 0; g < AG; ++g) {
@@ -233,53 +269,58 @@ __global__ void __launch_bounds__(256) bd_attn_kernel(const BdAttnP p) {
     for (int g = 0; g < AG; ++g) sc[(long)g * p.cap + j] = rbf(sc[(long)g * p.cap + j] / L[g]);
   }
   __syncthreads();
-  // ---- P.V: warp w takes keys w, w+8, ...; 4 keys in flight ----
-  float acc[AG][EPL];
+  // ---- P.V: 256 keys per CTA iteration, 8 x NV 16-byte loads in flight per lane ----
+  float acc[AG][SEG];
 #pragma unroll
   for (int g = 0; g < AG; ++g)
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[g][e] = 0.f;
-  for (int j0 = warp; j0 < nkeys; j0 += 32) {
-    float vf[4][EPL];
+    for (int e = 0; e < SEG; ++e) acc[g][e] = 0.f;
+  for (int j0 = 0; j0 < nkeys; j0 += 256) {
+    uint4 vv[VU][NV];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j0 + 8 * q;
+    for (int q = 0; q < VU; ++q) {
+      const int j = j0 + warp * 32 + q * 4 + ksub;
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) vf[q][e] = 0.f;
-      if (j < ctx) {
-        const bf16* vr = vb + (long)j * HD + lane * EPL;
-        if (EPL == 4) {
-          float t4[4];
-          unpack4(__ldcg(reinterpret_cast<const uint2*>(vr)), t4);
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) vf[q][e] = t4[e];
-        } else {
-          const uint32_t w = __ldcg(reinterpret_cast<const uint32_t*>(vr));
-          vf[q][0] = __uint_as_float(w << 16);
-          vf[q][EPL - 1] = __uint_as_float(w & 0xffff0000u);
-        }
-      } else if (j == ctx) {
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) vf[q][e] = vn[lane * EPL + e];
+      for (int v = 0; v < NV; ++v) {
+        if (j0 == 0) vv[q][v] = vfirst[q][v];
+        else vv[q][v] = (j < ctx) ? __ldcg(reinterpret_cast<const uint4*>(vb + (long)j * HD + seg * SEG + v * 8))
+                                  : make_uint4(0, 0, 0, 0);
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j0 + 8 * q;
+    for (int q = 0; q < VU; ++q) {
+      const int j = j0 + warp * 32 + q * 4 + ksub;
       if (j < nkeys) {
+        float pj[AG];
 #pragma unroll
-        for (int g = 0; g < AG; ++g) {
-          const float pj = sc[(long)g * p.cap + j];
+        for (int g = 0; g < AG; ++g) pj[g] = sc[(long)g * p.cap + j];
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) acc[g][e] = fmaf(pj, vf[q][e], acc[g][e]);
+        for (int v = 0; v < NV; ++v) {
+          float vf[8];
+          if (j == ctx) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) vf[e] = rbf(vn[seg * SEG + v * 8 + e]);
+          } else {
+            unpack8(vv[q][v], vf);
+          }
+#pragma unroll
+          for (int g = 0; g < AG; ++g)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[g][v * 8 + e] = fmaf(pj[g], vf[e], acc[g][v * 8 + e]);
         }
       }
     }
   }
+  // sum over the 4 key sub-indices of the warp, then over the 8 warps through shared memory
 #pragma unroll
   for (int g = 0; g < AG; ++g)
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) red[((long)warp * AG + g) * HD + lane * EPL + e] = acc[g][e];
+    for (int e = 0; e < SEG; ++e) {
+      float a = acc[g][e];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if (ksub == 0) red[((long)warp * AG + g) * HD + seg * SEG + e] = a;
+    }
   __syncthreads();
   bf16* orow = p.out + (long)row * p.n_heads * HD + (long)h0 * HD;
   for (int i = threadIdx.x; i < G * HD; i += 256) {

@@ -68,6 +68,20 @@ struct b200_engine {
   int* pos_hw_host = nullptr;   // pinned staging of the rot_pos_emb ids (no stream sync per call)
   long pos_hw_host_cap = 0;
   cudaEvent_t pos_ev = nullptr;
+  // captured CUDA graphs of the vision tower / the prefill layers, keyed by everything that is baked
+  // into their nodes (shapes, workspace, KV binding): the sequences are ~500 small launches, which
+  // the host cannot enqueue as fast as the B200 executes them
+  struct SeqGraph {
+    std::vector<long> key;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;
+    long n_launch = 0;
+  };
+  std::vector<SeqGraph> vis_graphs, pre_graphs;
+  bool seq_graphs = true;       // B200_SEQ_GRAPH=0: plain launches
+  KvRef* kvref = nullptr;       // device: where the bound pool row lives (read by the captured prefill)
+  KvRef* kvref_host = nullptr;  // pinned staging
+  cudaEvent_t kvref_ev = nullptr;
   bool v2 = true;               // weight-major GEMMs + pipelined attention (B200_PREFILL_V1=1: round-1 path)
   int log_cap = 1 << 16;
   // host mirrors of the decode state
@@ -140,9 +154,10 @@ static int resolve(b200_engine* e) {
   const auto& c = e->cfg;
   bool ok = true;
   const long E = c.v_embed, Em = c.v_mlp, mg = (long)c.v_merge * c.v_merge * E;
-  e->v_patch = need(e, "v.patch_embed.w", E * c.v_patch_dim, &ok);
-  e->vblk.resize(c.v_depth);
-  for (int i = 0; i < c.v_depth && ok; ++i) {
+  const bool vis = !c.external_vision;
+  if (vis) e->v_patch = need(e, "v.patch_embed.w", E * c.v_patch_dim, &ok);
+  e->vblk.resize(vis ? c.v_depth : 0);
+  for (int i = 0; vis && i < c.v_depth && ok; ++i) {
     const std::string p = "v.blk." + std::to_string(i) + ".";
     VBlk& b = e->vblk[i];
     b.ln1w = need(e, p + "ln1.w", E, &ok); b.ln1b = need(e, p + "ln1.b", E, &ok);
@@ -152,7 +167,7 @@ static int resolve(b200_engine* e) {
     b.fc1w = need(e, p + "fc1.w", Em * E, &ok); b.fc1b = need(e, p + "fc1.b", Em, &ok);
     b.fc2w = need(e, p + "fc2.w", E * Em, &ok); b.fc2b = need(e, p + "fc2.b", E, &ok);
   }
-  if (ok) {
+  if (ok && vis) {
     e->m_lnw = need(e, "v.merger.ln.w", E, &ok); e->m_lnb = need(e, "v.merger.ln.b", E, &ok);
     e->m_fc1w = need(e, "v.merger.fc1.w", mg * mg, &ok); e->m_fc1b = need(e, "v.merger.fc1.b", mg, &ok);
     e->m_fc2w = need(e, "v.merger.fc2.w", (long)c.v_out * mg, &ok);
@@ -176,6 +191,14 @@ static int resolve(b200_engine* e) {
   if (!ok) return B200_ERR_STATE;
   e->resolved = true;
   return B200_OK;
+}
+
+static void drop_seq_graphs(b200_engine* e) {
+  for (auto* v : {&e->vis_graphs, &e->pre_graphs}) {
+    for (auto& g : *v)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    v->clear();
+  }
 }
 
 static void invalidate_graph(b200_engine* e) {
@@ -392,8 +415,82 @@ static void build_pos_hw(const int* grid, int n_img, int ms, std::vector<int>* o
 }
 
 
+// Run `body` (a fixed sequence of launches on stream s) eagerly the first time a key is seen (the GEMM
+// configurations are measured then), capture + instantiate it the second time, replay it afterwards.
+template <class F>
+static int seq_run(b200_engine* e, std::vector<b200_engine::SeqGraph>& cache, const std::vector<long>& key,
+                   cudaStream_t s, F body) {
+  if (!e->seq_graphs) return body();
+  b200_engine::SeqGraph* g = nullptr;
+  for (auto& c : cache)
+    if (c.key == key) g = &c;
+  if (!g) {
+    if (cache.size() >= 8) {
+      if (cache.front().exec) cudaGraphExecDestroy(cache.front().exec);
+      cache.erase(cache.begin());
+    }
+    cache.emplace_back();
+    g = &cache.back();
+    g->key = key;
+  }
+  if (g->exec) {
+    B200_CUDA(cudaGraphLaunch(g->exec, s));
+    e->launches += g->n_launch;
+    return B200_OK;
+  }
+  if (g->seen++ == 0) return body();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (cap != cudaStreamCaptureStatusNone) return body();  // already inside somebody else's capture
+  const long l0 = e->launches;
+  cudaGraph_t graph = nullptr;
+  B200_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  const int rc = body();
+  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture(sequence)", __FILE__, __LINE__);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ci != cudaSuccess) return cuda_fail(ci, "cudaGraphInstantiate(sequence)", __FILE__, __LINE__);
+  g->exec = exec;
+  g->n_launch = e->launches - l0;
+  B200_CUDA(cudaGraphLaunch(exec, s));
+  return B200_OK;
+}
+
+static int vision_v2_body(b200_engine* e, const float* pixel_values, const int* grid, int n_images, long N,
+                          void* feats_out, cudaStream_t s);
+
 static int vision_v2(b200_engine* e, const float* pixel_values, const int* grid, int n_images, long N,
                      void* feats_out, cudaStream_t s) {
+  const auto& c = e->cfg;
+  // graph input / output live at fixed workspace addresses: stage them around the captured body
+  uint8_t* p = e->ws;
+  p += align256(N * (long)c.v_patch_dim * 2) + 2 * align256(N * (long)c.v_embed * 2) +
+       align256(N * 3L * c.v_embed * 2) + align256(N * (long)c.v_mlp * 2) + align256(N * (long)c.v_embed * 2) +
+       align256((long)c.v_embed * round8(N) * 2);
+  float* xin = (float*)p; p += align256(N * (long)c.v_patch_dim * 4);
+  bf16* fout = (bf16*)p;
+  const long Nm = N / ((long)c.v_merge * c.v_merge);
+  int rc;
+  std::vector<int> pos;
+  build_pos_hw(grid, n_images, c.v_merge, &pos);
+  if ((rc = v2_upload_pos(e, pos, s))) return rc;
+  B200_CUDA(cudaMemcpyAsync(xin, pixel_values, (size_t)N * c.v_patch_dim * 4, cudaMemcpyDeviceToDevice, s));
+  std::vector<long> key = {(long)(uintptr_t)e->ws, (long)e->ws_bytes, N, (long)n_images, (long)(uintptr_t)e->pos_hw};
+  for (int i = 0; i < n_images * 3; ++i) key.push_back(grid[i]);
+  rc = seq_run(e, e->vis_graphs, key, s, [&]() { return vision_v2_body(e, xin, grid, n_images, N, fout, s); });
+  if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(feats_out, fout, (size_t)Nm * c.v_out * 2, cudaMemcpyDeviceToDevice, s));
+  return B200_OK;
+}
+
+static int vision_v2_body(b200_engine* e, const float* pixel_values, const int* grid, int n_images, long N,
+                          void* feats_out, cudaStream_t s) {
   const auto& c = e->cfg;
   const long E = c.v_embed, Em = c.v_mlp;
   const int nh = c.v_heads, hd = c.v_embed / c.v_heads;
@@ -407,9 +504,6 @@ static int vision_v2(b200_engine* e, const float* pixel_values, const int* grid,
   bf16* att = (bf16*)p; p += align256(N * E * 2);
   bf16* vt = (bf16*)p; p += align256(E * (long)t_ld * 2);
   int rc;
-  std::vector<int> pos;
-  build_pos_hw(grid, n_images, c.v_merge, &pos);
-  if ((rc = v2_upload_pos(e, pos, s))) return rc;
   if ((rc = cast_f32_bf16(pixel_values, x, N * c.v_patch_dim, s))) return rc;
   if ((rc = v2_linear(e, x, c.v_patch_dim, e->v_patch, nullptr, h, E, (int)N, (int)E, c.v_patch_dim, B200_EPI_NONE, s)))
     return rc;
@@ -466,8 +560,45 @@ static int vision_v2(b200_engine* e, const float* pixel_values, const int* grid,
   return B200_OK;
 }
 
+static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ctx0, void* all_logits_out,
+                                  cudaStream_t s);
+
 static int prefill_layers_v2(b200_engine* e, const void* embeds, const int* pos3, int T, int ctx0,
                              void* all_logits_out, bf16** h_out, cudaStream_t s) {
+  const auto& c = e->cfg;
+  const long H = c.hidden, I = c.inter, QH = (long)c.n_heads * c.head_dim;
+  const long QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  uint8_t* p = e->ws;
+  bf16* h = (bf16*)p;
+  p += 2 * align256((long)T * H * 2) + align256((long)T * QKV * 2) + align256((long)T * QH * 2) +
+       align256((long)T * 2 * I * 2) + align256((long)T * I * 2);
+  int* pos_stage = (int*)p;
+  // graph inputs at fixed workspace addresses: the embeddings (residual stream) and the position ids
+  B200_CUDA(cudaMemcpyAsync(h, embeds, (size_t)T * H * 2, cudaMemcpyDeviceToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(pos_stage, pos3, (size_t)3 * T * 4, cudaMemcpyDeviceToDevice, s));
+  *h_out = h;
+  // where the cache lives travels through device memory (the captured graph survives a new pool)
+  if (!e->kvref) {
+    B200_CUDA(cudaMalloc(&e->kvref, sizeof(KvRef)));
+    B200_CUDA(cudaMallocHost(&e->kvref_host, sizeof(KvRef)));
+    B200_CUDA(cudaEventCreateWithFlags(&e->kvref_ev, cudaEventDisableTiming));
+  } else {
+    B200_CUDA(cudaEventSynchronize(e->kvref_ev));
+  }
+  e->kvref_host->k0 = e->kptr(0, e->kv_row);
+  e->kvref_host->v_off = (long)e->kv_batch * c.n_kv_heads * (long)e->kv_cap * c.head_dim;
+  e->kvref_host->layer_stride = 2L * e->kvref_host->v_off;
+  e->kvref_host->cap = e->kv_cap;
+  B200_CUDA(cudaMemcpyAsync(e->kvref, e->kvref_host, sizeof(KvRef), cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaEventRecord(e->kvref_ev, s));
+  if (all_logits_out || ctx0 != 0)  // all-row logits into a caller buffer / a later chunk: plain launches
+    return prefill_layers_v2_body(e, pos_stage, T, ctx0, all_logits_out, s);
+  const std::vector<long> key = {(long)(uintptr_t)e->ws, (long)e->ws_bytes, (long)T};
+  return seq_run(e, e->pre_graphs, key, s, [&]() { return prefill_layers_v2_body(e, pos_stage, T, 0, nullptr, s); });
+}
+
+static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ctx0, void* all_logits_out,
+                                  cudaStream_t s) {
   const auto& c = e->cfg;
   const long H = c.hidden, I = c.inter, QH = (long)c.n_heads * c.head_dim;
   const long QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
@@ -481,8 +612,8 @@ static int prefill_layers_v2(b200_engine* e, const void* embeds, const int* pos3
   bf16* act = (bf16*)p; p += align256((long)T * I * 2);
   p += align256(3L * T * 4);
   bf16* vt = (bf16*)p; p += align256((long)c.n_kv_heads * hd * t_ld * 2);
+  bf16* kws = (bf16*)p; p += align256((long)c.n_kv_heads * hd * T * 2);
   int rc;
-  B200_CUDA(cudaMemcpyAsync(h, embeds, (size_t)T * H * 2, cudaMemcpyDeviceToDevice, s));
   if ((rc = rms_norm(h, e->layers[0].ln1, xn, T, (int)H, c.rms_eps, s))) return rc;
   e->launches += 1;
   const float scale = 1.0f / sqrtf((float)hd);
@@ -493,14 +624,17 @@ static int prefill_layers_v2(b200_engine* e, const void* embeds, const int* pos3
     bf16* kc = e->kptr(l, e->kv_row);
     bf16* vc = e->vptr(l, e->kv_row);
     if ((rc = v2_linear(e, xn, H, lw.wqkv, lw.bqkv, qkv, QKV, T, (int)QKV, (int)H, B200_EPI_NONE, s))) return rc;
-    // the pipelined kernel needs V^T of EVERY key: available for a fresh prompt (ctx0 == 0)
-    const bool fa = ctx0 == 0 && attention_fa_supported(qkv, QKV, hd, kc, hd, (long)e->kv_cap * hd, vt,
-                                                        (long)hd * t_ld, t_ld, att, QH, hd);
+    // the pipelined kernel needs V^T of EVERY key: available for a fresh prompt (ctx0 == 0).  It then
+    // reads the chunk's own rotated K copy and V^T from the workspace, and the cache is addressed through
+    // e->kvref: nothing about the KV pool is baked into the captured graph.
+    const bool fa = ctx0 == 0 && attention_fa_supported(qkv, QKV, hd, kws, hd, (long)T * hd, vt, (long)hd * t_ld,
+                                                        t_ld, att, QH, hd);
     if ((rc = mrope_kv_write(qkv, pos3, e->lm_inv_freq, e->axis_sel, kc, vc, T, ctx0, e->kv_cap, c.n_heads,
-                             c.n_kv_heads, hd, s, fa ? scale_bf : 0.f, fa ? vt : nullptr, t_ld)))
+                             c.n_kv_heads, hd, s, fa ? scale_bf : 0.f, fa ? vt : nullptr, t_ld,
+                             fa ? e->kvref : nullptr, l, fa ? kws : nullptr)))
       return rc;
     if (fa) {
-      rc = attention_fa(qkv, QKV, hd, kc, hd, (long)e->kv_cap * hd, vt, (long)hd * t_ld, t_ld, att, QH, c.n_heads,
+      rc = attention_fa(qkv, QKV, hd, kws, hd, (long)T * hd, vt, (long)hd * t_ld, t_ld, att, QH, c.n_heads,
                         c.n_kv_heads, hd, T, S, 1, s, 0, T, 0, S);
     } else {
       rc = attention(qkv, QKV, hd, kc, hd, (long)e->kv_cap * hd, vc, hd, (long)e->kv_cap * hd, att, QH, c.n_heads,
@@ -529,7 +663,6 @@ static int prefill_layers_v2(b200_engine* e, const void* embeds, const int* pos3
                         B200_EPI_NONE, s)))
       return rc;
   }
-  *h_out = h;
   return B200_OK;
 }
 
@@ -567,6 +700,7 @@ int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine**
   decode_set_sm_count(sm);
   if (const char* v = getenv("B200_MEGA_FLOW")) e->flow = atoi(v) != 0;  // tuning aid (A/B)
   if (const char* v = getenv("B200_PREFILL_V1")) e->v2 = atoi(v) == 0;    // A/B: round-1 prefill kernels
+  if (const char* v = getenv("B200_SEQ_GRAPH")) e->seq_graphs = atoi(v) != 0;
   const auto& c = e->cfg;
   B200_CUDA(cudaMalloc(&e->st, sizeof(DecState)));
   B200_CUDA(cudaMemset(e->st, 0, sizeof(DecState)));
@@ -615,12 +749,16 @@ int b200_engine_destroy(b200_engine* e) {
   if (!e) return B200_OK;
   cudaSetDevice(e->device);
   invalidate_graph(e);
+  drop_seq_graphs(e);
   cudaFree(e->st); cudaFree(e->h); cudaFree(e->qbuf); cudaFree(e->attn); cudaFree(e->act);
   cudaFree(e->logits); cudaFree(e->logprobs); cudaFree(e->partials); cudaFree(e->token_log);
   cudaFree(e->force); cudaFree(e->lm_inv_freq); cudaFree(e->axis_sel); cudaFree(e->v_inv_freq);
   if (e->pos_hw) cudaFree(e->pos_hw);
   if (e->pos_hw_host) cudaFreeHost(e->pos_hw_host);
   if (e->pos_ev) cudaEventDestroy(e->pos_ev);
+  if (e->kvref) cudaFree(e->kvref);
+  if (e->kvref_host) cudaFreeHost(e->kvref_host);
+  if (e->kvref_ev) cudaEventDestroy(e->kvref_ev);
   if (e->att_part) cudaFree(e->att_part);
   if (e->att_stats) cudaFree(e->att_stats);
   if (e->bar) cudaFree(e->bar);
@@ -641,6 +779,7 @@ int b200_engine_set_weight(b200_engine* e, const char* name, const void* ptr, lo
   B200_REQUIRE(((uintptr_t)ptr & 15) == 0, "set_weight: '%s' must be 16-byte aligned", name);
   e->w[name] = (const bf16*)ptr;
   e->wn[name] = n_elems;
+  drop_seq_graphs(e);
   e->resolved = false;
   e->packed_ready = false;
   invalidate_graph(e);
@@ -674,13 +813,17 @@ long b200_engine_workspace_bytes(const b200_engine* e, int max_tokens, int max_p
            align256(N * 3L * c.v_embed * 2) + align256(N * (long)c.v_mlp * 2) +
            align256(N * (long)c.v_embed * 2);
   lm += align256((long)c.n_kv_heads * c.head_dim * round8(T) * 2);  // V^T of the prompt chunk
+  lm += align256((long)c.n_kv_heads * c.head_dim * T * 2);          // rotated K of the prompt chunk
   v += align256((long)c.v_embed * round8(N) * 2);                   // V^T of the vision tower
+  v += align256(N * (long)c.v_patch_dim * 4);                       // staged fp32 pixel_values (graph input)
+  v += align256((N / ((long)c.v_merge * c.v_merge) + 1) * c.v_out * 2);  // staged features (graph output)
   return (lm > v ? lm : v) + WT_PARTIAL_BYTES + 4096;
 }
 
 int b200_engine_set_workspace(b200_engine* e, void* ptr, long bytes) {
   B200_REQUIRE(e && ptr && bytes > 0 && ((uintptr_t)ptr & 255) == 0,
                "set_workspace: need a 256-byte aligned buffer");
+  drop_seq_graphs(e);
   e->ws = (uint8_t*)ptr;
   e->ws_bytes = bytes;
   return B200_OK;
@@ -702,6 +845,7 @@ int b200_engine_vision(b200_engine* e, const float* pixel_values, const int* gri
                "engine_vision: null argument");
   int rc = resolve(e);
   if (rc) return rc;
+  B200_REQUIRE(!e->cfg.external_vision, "engine_vision: this engine was created without a vision tower");
   B200_CUDA(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   const auto& c = e->cfg;

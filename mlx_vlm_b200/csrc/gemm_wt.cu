@@ -55,6 +55,16 @@ struct WtParams {
   int epilogue, mode;
   int inter;
   unsigned flags;  // debug: 1 = no MMA (loads only), 2 = no loads (MMA on stale smem), 4 = no epilogue stores
+  // fp32-accurate towers (LLaVA / Idefics2: the reference runs them in fp32 with bf16-valued weights):
+  // X is a SPLIT operand [x_hi | x_lo] (n parts of K_w columns, each padded to 64) multiplied by the SAME
+  // weight k-blocks (kb_w of them): D = W.x_hi + W.x_lo in fp32 — exact to ~2^-17 relative.
+  int kb_w;          // > 0: weight k-block = k-block % kb_w
+  float* C32;        // B200_WT_F32: fp32 output (bias, activation, fp32 residual)
+  const float* res32;
+  long ldc32, ldr32;
+  bf16* Csplit;      // B200_WT_SPLIT: output written as [hi | lo] bf16 halves, n_pad columns apart
+  long ld_split;
+  int n_pad;
 };
 
 __device__ __forceinline__ uint32_t w_smem_u32(const void* p) {
@@ -173,7 +183,9 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     }
     w_mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (WT_WBLK + xblk));
     for (int j = 0; j < cnt; ++j) {
-      const int kc = (kb0 + it * p.KS + j) * WT_BK;
+      int kbw = kb0 + it * p.KS + j;
+      if (p.kb_w > 0) kbw %= p.kb_w;
+      const int kc = kbw * WT_BK;
       if (swiglu) {
         w_tma_2d(sW + j * WT_WBLK, &tmW, &full_bar[s], kc, n0);
         w_tma_2d(sW + j * WT_WBLK + 64 * 128, &tmW, &full_bar[s], kc, p.inter + n0);
@@ -263,7 +275,8 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;  // weight row of the tile == TMEM lane
   float bias_v = 0.f;
-  if (p.mode == B200_WT_BF16 && p.bias && n0 + row < p.N) bias_v = bf2f(p.bias[n0 + row]);
+  if ((p.mode == B200_WT_BF16 || p.mode == B200_WT_F32 || p.mode == B200_WT_SPLIT) && p.bias && n0 + row < p.N)
+    bias_v = bf2f(p.bias[n0 + row]);
   uint8_t* stg = ring;  // every TMA load has landed and every MMA has retired: the ring is free
   const int tid = threadIdx.x;
   for (int c0 = 0; c0 < p.TN; c0 += WT_EPI_TOK) {
@@ -275,6 +288,19 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         float* sf = reinterpret_cast<float*>(stg);
 #pragma unroll
         for (int j = 0; j < 32; ++j) sf[(half * 32 + j) * WT_ROWS + row] = __uint_as_float(a[j]);
+      } else if (p.mode == B200_WT_F32 || p.mode == B200_WT_SPLIT) {
+        float* sf = reinterpret_cast<float*>(stg);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(a[j]) + bias_v;   // fp32 semantics: no rounding anywhere
+          if (p.epilogue == B200_EPI_GELU_FAST) v = v * sigmoid_f(1.702f * v);
+          else if (p.epilogue == B200_EPI_GELU_EXACT) v = v * (1.0f + erff(v / 1.41421356237309515f)) * 0.5f;
+          else if (p.epilogue == B200_EPI_GELU_TANH) {
+            const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+            v = 0.5f * v * (1.0f + tanhf(u));
+          }
+          sf[(half * 32 + j) * WT_ROWS + row] = v;
+        }
       } else {
         bf16* sb = reinterpret_cast<bf16*>(stg);
 #pragma unroll
@@ -335,6 +361,47 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           uint4 ov;
           ov.x = pack2(o[0], o[1]); ov.y = pack2(o[2], o[3]); ov.z = pack2(o[4], o[5]); ov.w = pack2(o[6], o[7]);
           *reinterpret_cast<uint4*>(p.C + (long)t * p.ldc + i) = ov;
+        }
+      } else if (p.mode == B200_WT_F32 || p.mode == B200_WT_SPLIT) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = tid + 256 * u;
+          const int tl = idx >> 5, ch = idx & 31;
+          const int t = t0 + c0 + tl, n = n0 + ch * 4;
+          if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
+          float4 v = *reinterpret_cast<const float4*>(stg + (tl * WT_ROWS + ch * 4) * 4);
+          if (p.mode == B200_WT_F32) {
+            float* dst = p.C32 + (long)t * p.ldc32 + n;
+            if (n + 4 <= p.N && (p.ldc32 & 3) == 0) {
+              if (p.res32) {
+                const float4 r = *reinterpret_cast<const float4*>(p.res32 + (long)t * p.ldr32 + n);
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+              }
+              *reinterpret_cast<float4*>(dst) = v;
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+              for (int e = 0; e < 4 && n + e < p.N; ++e)
+                dst[e] = vv[e] + (p.res32 ? p.res32[(long)t * p.ldr32 + n + e] : 0.f);
+            }
+          } else {  // [hi | lo]: hi = bf16(v), lo = bf16(v - hi)
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[e] = rbf(vv[e]);
+              lo[e] = vv[e] - hi[e];
+            }
+            bf16* dh = p.Csplit + (long)t * p.ld_split + n;
+            if (n + 4 <= p.N) {
+              *reinterpret_cast<uint2*>(dh) = make_uint2(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]));
+              *reinterpret_cast<uint2*>(dh + p.n_pad) = make_uint2(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]));
+            } else {
+              for (int e = 0; e < 4 && n + e < p.N; ++e) {
+                dh[e] = f2bf(hi[e]);
+                dh[p.n_pad + e] = f2bf(lo[e]);
+              }
+            }
+          }
         }
       } else {  // fp32 partial tile -> P[split][t][n]
 #pragma unroll
@@ -403,10 +470,18 @@ finish_rows_kernel(const float* __restrict__ P, int S, const bf16* __restrict__ 
     const int c = threadIdx.x + FIN_THREADS * u;
     h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < nv) {
-      float4 a = __ldcg(reinterpret_cast<const float4*>(P + (long)t * N + c * 4));
-      for (int s = 1; s < S; ++s) {
-        const float4 b = __ldcg(reinterpret_cast<const float4*>(P + ((long)s * T + t) * N + c * 4));
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      // the split-K partials of this chunk: up to 8 loads in flight, added in split order
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s0 = 0; s0 < S; s0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[i] = (s0 + i < S) ? __ldcg(reinterpret_cast<const float4*>(P + ((long)(s0 + i) * T + t) * N + c * 4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w;
+        }
       }
       if (bias) {
         float bb[4];
@@ -656,14 +731,19 @@ void gemm_wt_auto(int T, int row_blocks, int K, bool allow_split, WtConfig* best
 
 int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
             void* C, long ldc, float* partial, int T, int N, int K, int epilogue, int mode, int inter,
-            const WtConfig& cfg, unsigned flags, cudaStream_t st) {
+            const WtConfig& cfg, unsigned flags, cudaStream_t st, const WtExt* ext) {
   B200_REQUIRE(T > 0 && N > 0 && K > 0, "gemm_wt: empty problem T=%d N=%d K=%d", T, N, K);
   B200_REQUIRE((ldx % 8) == 0 && (K % 8) == 0, "gemm_wt: ldx (%ld) and K (%d) must be multiples of 8", ldx, K);
   B200_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm_wt: X and W must be 16-byte aligned");
   B200_REQUIRE(cfg.TN >= 16 && cfg.TN <= 256 && (cfg.TN % 16) == 0, "gemm_wt: TN=%d", cfg.TN);
   B200_REQUIRE(cfg.KS >= 1 && cfg.stages >= 2 && cfg.stages <= WT_MAX_STAGES && cfg.split >= 1,
                "gemm_wt: bad config KS=%d stages=%d split=%d", cfg.KS, cfg.stages, cfg.split);
-  B200_REQUIRE(mode == B200_WT_BF16 || mode == B200_WT_PARTIAL || mode == B200_WT_SWIGLU, "gemm_wt: mode %d", mode);
+  B200_REQUIRE(mode >= B200_WT_BF16 && mode <= B200_WT_SPLIT, "gemm_wt: mode %d", mode);
+  B200_REQUIRE((mode != B200_WT_F32 && mode != B200_WT_SPLIT) || ext, "gemm_wt: fp32 / split output needs WtExt");
+  B200_REQUIRE(mode != B200_WT_F32 || (ext->C32 && ((uintptr_t)ext->C32 & 15) == 0), "gemm_wt: fp32 output missing / misaligned");
+  B200_REQUIRE(mode != B200_WT_SPLIT || (ext->Csplit && (ext->n_pad % 8) == 0 && (ext->ld_split % 8) == 0 &&
+                                         ((uintptr_t)ext->Csplit & 15) == 0),
+               "gemm_wt: split output missing / misaligned");
   B200_REQUIRE(mode != B200_WT_PARTIAL || partial, "gemm_wt: partial buffer missing");
   B200_REQUIRE(mode == B200_WT_PARTIAL || cfg.split == 1, "gemm_wt: split-K needs the partial mode");
   B200_REQUIRE(mode != B200_WT_SWIGLU || (inter > 0 && (inter % 8) == 0 && N == 2 * inter),
@@ -678,12 +758,18 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
   const int splits = cdiv(kb_total, p.kb_per_split);
   B200_REQUIRE(splits == cfg.split, "gemm_wt: split %d leaves empty splits (%d k-blocks)", cfg.split, kb_total);
   p.epilogue = epilogue; p.mode = mode; p.inter = inter; p.flags = flags;
+  int k_w = K;  // columns of W (the split operand repeats the weight k-blocks)
+  if (ext) {
+    p.kb_w = ext->kb_w; p.C32 = ext->C32; p.res32 = ext->res32; p.ldc32 = ext->ldc32; p.ldr32 = ext->ldr32;
+    p.Csplit = ext->Csplit; p.ld_split = ext->ld_split; p.n_pad = ext->n_pad;
+    if (ext->kb_w > 0) k_w = ext->k_w;
+  }
   const int stage = cfg.KS * (WT_WBLK + cfg.TN * 128);
   const size_t smem = (size_t)cfg.stages * stage + 1024;
   B200_REQUIRE(smem <= 227 * 1024 - 1024, "gemm_wt: %zu B of shared memory", smem);
   B200_REQUIRE((size_t)cfg.stages * stage >= (size_t)WT_EPI_TOK * WT_ROWS * 4, "gemm_wt: ring smaller than the epilogue staging tile");
   CUtensorMap tw, tx;
-  int rc = wt_tmap(W, (long)K, N, K, mode == B200_WT_SWIGLU ? 64 : WT_ROWS, &tw);
+  int rc = wt_tmap(W, (long)(ext && ext->ldw > 0 ? ext->ldw : k_w), N, k_w, mode == B200_WT_SWIGLU ? 64 : WT_ROWS, &tw);
   if (rc) return rc;
   if ((rc = wt_tmap(X, ldx, T, K, cfg.TN, &tx))) return rc;
   static unsigned long long set_mask = 0ull;
@@ -745,7 +831,8 @@ static int tune_enabled() {
 
 int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, const void* residual, long ldr,
                   void* C, long ldc, float* partial, long partial_bytes, int T, int N, int K, int epilogue,
-                  int mode, int inter, bool allow_split, int sm_count, int* split_out, cudaStream_t st) {
+                  int mode, int inter, bool allow_split, int sm_count, int* split_out, cudaStream_t st,
+                  const WtExt* ext) {
   static std::unordered_map<TuneKey, WtConfig, TuneHash> cache;
   static std::mutex mu;
   const int row_blocks = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, WT_ROWS);
@@ -819,27 +906,60 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
       gemm_wt_auto(T, row_blocks, K, false, &model, sm_count);
       cand.push_back(model);
     }
-    // ---- time them ----
+    // ---- time them (the tuning launches never add a residual: the output stays idempotent) ----
+    WtExt ext_copy;
+    const WtExt* ext_t = nullptr;
+    if (ext) {
+      ext_copy = *ext;
+      ext_copy.res32 = nullptr;
+      ext_t = &ext_copy;
+    }
+    // each candidate is replayed from a small captured graph (6 launches): the measurement sees the
+    // kernel back to back with its programmatic dependent launch, not the host's launch overhead
     cudaEvent_t e0, e1;
     B200_CUDA(cudaEventCreate(&e0));
     B200_CUDA(cudaEventCreate(&e1));
     std::vector<float> ms(cand.size(), 1e30f);
     int rc = B200_OK;
+    constexpr int REP = 16;
     for (size_t i = 0; i < cand.size() && rc == B200_OK; ++i) {
-      rc = gemm_wt(X, ldx, W, bias, nullptr, 0, C, ldc, partial, T, N, K, epilogue, mode, inter, cand[i], 0, st);
-      if (rc) break;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t gx = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        rc = B200_ERR_CUDA;
+        break;
+      }
+      for (int r = 0; r < REP && rc == B200_OK; ++r)
+        rc = gemm_wt(X, ldx, W, bias, nullptr, 0, C, ldc, partial, T, N, K, epilogue, mode, inter, cand[i], 0, st, ext_t);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc != B200_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (rc == B200_OK) rc = B200_ERR_CUDA;
+        break;
+      }
+      ce = cudaGraphInstantiate(&gx, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        rc = B200_ERR_CUDA;
+        break;
+      }
+      cudaGraphLaunch(gx, st);  // warm-up
       cudaEventRecord(e0, st);
-      for (int r = 0; r < 2 && rc == B200_OK; ++r)
-        rc = gemm_wt(X, ldx, W, bias, nullptr, 0, C, ldc, partial, T, N, K, epilogue, mode, inter, cand[i], 0, st);
+      cudaGraphLaunch(gx, st);
+      cudaGraphLaunch(gx, st);
       cudaEventRecord(e1, st);
       if (cudaEventSynchronize(e1) != cudaSuccess) rc = B200_ERR_CUDA;
       float t = 0.f;
       cudaEventElapsedTime(&t, e0, e1);
-      ms[i] = t;
+      ms[i] = t / (2.f * REP);
+      cudaGraphExecDestroy(gx);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    if (rc) return rc;
+    if (rc) {
+      set_error("gemm_wt: configuration measurement failed (T=%d N=%d K=%d mode=%d)", T, N, K, mode);
+      return rc;
+    }
     float best = 1e30f;
     for (float t : ms) best = t < best ? t : best;
     size_t pick = 0;
@@ -851,7 +971,7 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
     cfg = cand[pick];
     if (getenv("B200_WT_TUNE_LOG"))
       fprintf(stderr, "[gemm_wt tune] T=%d N=%d K=%d mode=%d -> TN=%d KS=%d stages=%d split=%d (%.1f us, %zu candidates)\n",
-              T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, ms[pick] * 500.f, cand.size());
+              T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, ms[pick] * 1000.f, cand.size());
     std::lock_guard<std::mutex> g(mu);
     cache[key] = cfg;
   }

@@ -3,11 +3,13 @@
 // merge.  All are HBM-bound: 16-byte vector accesses, one warp per row where a
 // reduction is needed.  Rounding points follow oracle/mlx_semantics.py.
 #include "common.cuh"
+#include "decode.cuh"
 
 namespace b200 {
 
 // ---------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  pdl_prologue();
   long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const long stride = (long)gridDim.x * blockDim.x * 4;
   for (; i + 3 < n; i += stride) {
@@ -28,6 +30,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
 __global__ void layer_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                   const bf16* __restrict__ b, bf16* __restrict__ y, int rows,
                                   int dim, float eps) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -78,6 +81,7 @@ __global__ void layer_norm_kernel(const bf16* __restrict__ x, const bf16* __rest
 // mx.fast.rms_norm CPU fallback: bf16(x * rsqrt(mean(x^2)+eps)) then * w (round).
 __global__ void rms_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                 bf16* __restrict__ y, int rows, int dim, float eps) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -146,7 +150,14 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
                                       const int* __restrict__ axis_sel, bf16* __restrict__ kc,
                                       bf16* __restrict__ vc, int T, int ctx0, int cap, int n_heads,
                                       int n_kv, int hd, float q_scale, bf16* __restrict__ vt,
-                                      int t_ld) {
+                                      int t_ld, const KvRef* __restrict__ ref, int layer,
+                                      bf16* __restrict__ kws) {
+  pdl_prologue();
+  if (ref) {  // cache location read from device memory: a captured graph stays valid when the pool moves
+    kc = ref->k0 + (long)layer * ref->layer_stride;
+    vc = kc + ref->v_off;
+    cap = ref->cap;
+  }
   const int half = hd >> 1;
   const int slots = n_heads + 2 * n_kv;
   const long total = (long)T * slots * half;
@@ -183,6 +194,11 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
       bf16* dst = kc + ((long)kvh * cap + ctx0 + t) * hd;
       dst[j] = f2bf(o1);
       dst[j + half] = f2bf(o2);
+      if (kws) {  // the prompt chunk's rotated keys [kv head][token][dim] for the pipelined attention
+        bf16* d2 = kws + ((long)kvh * T + t) * hd;
+        d2[j] = f2bf(o1);
+        d2[j + half] = f2bf(o2);
+      }
     }
   }
 }
@@ -278,26 +294,23 @@ int cast_f32_bf16(const float* src, void* dst, long n, cudaStream_t st) {
   B200_REQUIRE(n >= 0, "cast: n<0");
   if (n == 0) return B200_OK;
   B200_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "cast: misaligned");
-  cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(src, (bf16*)dst, n);
-  B200_CHECK_LAUNCH();
+  B200_CUDA(launch_pdl(cast_f32_bf16_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), 0, st, src, (bf16*)dst, n));
   return B200_OK;
 }
 
 int layer_norm(const void* x, const void* w, const void* b, void* y, int rows, int dim, float eps,
                cudaStream_t st) {
   B200_REQUIRE(rows > 0 && dim > 0 && (dim % 8) == 0, "layer_norm: rows=%d dim=%d", rows, dim);
-  layer_norm_kernel<<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)b,
-                                                  (bf16*)y, rows, dim, eps);
-  B200_CHECK_LAUNCH();
+  B200_CUDA(launch_pdl(layer_norm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, (const bf16*)x, (const bf16*)w,
+                       (const bf16*)b, (bf16*)y, rows, dim, eps));
   return B200_OK;
 }
 
 int rms_norm(const void* x, const void* w, void* y, int rows, int dim, float eps,
              cudaStream_t st) {
   B200_REQUIRE(rows > 0 && dim > 0 && (dim % 8) == 0 && w, "rms_norm: rows=%d dim=%d", rows, dim);
-  rms_norm_kernel<<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rows,
-                                                dim, eps);
-  B200_CHECK_LAUNCH();
+  B200_CUDA(launch_pdl(rms_norm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, (const bf16*)x, (const bf16*)w,
+                       (bf16*)y, rows, dim, eps));
   return B200_OK;
 }
 
@@ -313,15 +326,14 @@ int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, 
 
 int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
                    void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
-                   cudaStream_t st, float q_scale, void* vt, int t_ld) {
-  B200_REQUIRE(T > 0 && ctx0 >= 0 && ctx0 + T <= cap, "mrope_kv_write: T=%d ctx0=%d cap=%d", T,
+                   cudaStream_t st, float q_scale, void* vt, int t_ld, const KvRef* ref, int layer, void* kws) {
+  B200_REQUIRE(T > 0 && ctx0 >= 0 && (ref || ctx0 + T <= cap), "mrope_kv_write: T=%d ctx0=%d cap=%d", T,
                ctx0, cap);
   B200_REQUIRE(!vt || t_ld >= T, "mrope_kv_write: V^T pitch %d < T %d", t_ld, T);
   const long total = (long)T * (n_heads + 2 * n_kv) * (hd / 2);
-  mrope_kv_write_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-      (bf16*)qkv, pos3, inv_freq, axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd,
-      q_scale, (bf16*)vt, t_ld);
-  B200_CHECK_LAUNCH();
+  B200_CUDA(launch_pdl(mrope_kv_write_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, (bf16*)qkv, pos3, inv_freq,
+                       axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd, q_scale, (bf16*)vt, t_ld, ref,
+                       layer, (bf16*)kws));
   return B200_OK;
 }
 
@@ -334,6 +346,7 @@ int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int*
 __global__ void vision_qkv_post_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos_hw,
                                        const float* __restrict__ inv_freq, int T, int n_heads, int hd,
                                        float scale_bf, bf16* __restrict__ vt, int t_ld) {
+  pdl_prologue();
   __shared__ bf16 tile[32][136];
   const int t0 = blockIdx.x * 32, h = blockIdx.y;
   const int half = hd >> 1, quarter = hd >> 2;
@@ -384,9 +397,8 @@ int vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_t
   B200_REQUIRE(n_tok > 0 && n_heads > 0 && (hd % 8) == 0 && hd <= 128 && (t_ld % 8) == 0 && t_ld >= n_tok,
                "vision_qkv_post: bad shape (hd=%d t_ld=%d)", hd, t_ld);
   const float scale_bf = __bfloat162float(__float2bfloat16_rn(scale));
-  vision_qkv_post_kernel<<<dim3(cdiv(n_tok, 32), n_heads), 256, 0, st>>>((bf16*)qkv, pos_hw, inv_freq, n_tok,
-                                                                       n_heads, hd, scale_bf, (bf16*)vt, t_ld);
-  B200_CHECK_LAUNCH();
+  B200_CUDA(launch_pdl(vision_qkv_post_kernel, dim3(cdiv(n_tok, 32), n_heads), dim3(256), 0, st, (bf16*)qkv, pos_hw,
+                       inv_freq, n_tok, n_heads, hd, scale_bf, (bf16*)vt, t_ld));
   return B200_OK;
 }
 
@@ -436,7 +448,7 @@ int b200_mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const
                         void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv,
                         int hd, void* st) {
   return mrope_kv_write(qkv, pos3, inv_freq, axis_sel, kc, vc, T, ctx0, cap, n_heads, n_kv, hd,
-                        (cudaStream_t)st, 0.f, nullptr, 0);
+                        (cudaStream_t)st, 0.f, nullptr, 0, nullptr, 0, nullptr);
 }
 int b200_vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
                          int hd, float scale, void* vt, int t_ld, void* st) {

@@ -1,0 +1,365 @@
+// fp32-accurate vision towers (LLaVA-1.5 CLIP-L/14, Idefics2 SigLIP + perceiver).
+//
+// The reference never casts `pixel_values` for these models (utils.py:2091 builds a float32 array,
+// llava.py:61-63 / idefics2.py:212-251 feed it straight in), so mlx type promotion makes every op
+// of the tower an fp32 computation with bf16-VALUED weights; the features are rounded to bf16
+// only at the merge (llava.py:101-104).  A bf16 tower is 1.4e-2 away from that (87 % of the
+// feature elements differ, tools/tower_precision_study.py), so it is not a drop-in.
+//
+// How the tensor cores still do the work: an fp32 activation x is carried as TWO bf16 halves
+// x_hi = bf16(x), x_lo = bf16(x - x_hi) ("split operand", 16 mantissa bits); because the weights are
+// exactly bf16, W.x = W.x_hi + W.x_lo needs two kind::f16 MMAs with fp32 accumulation — the GEMM
+// (gemm_wt.cu) simply sees a K twice as long whose weight k-blocks repeat.  Everything between the
+// GEMMs is fp32 here: LayerNorm, residual stream, GELU, softmax, attention.
+#include "common.cuh"
+#include "decode.cuh"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ void split_store4(bf16* dst, int n_pad, float a, float b, float c, float d) {
+  const float h0 = rbf(a), h1 = rbf(b), h2 = rbf(c), h3 = rbf(d);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(h0, h1), pack2(h2, h3));
+  *reinterpret_cast<uint2*>(dst + n_pad) = make_uint2(pack2(a - h0, b - h1), pack2(c - h2, d - h3));
+}
+
+__device__ __forceinline__ void split_store2(bf16* dst, int n_pad, float a, float b) {
+  const float h0 = rbf(a), h1 = rbf(b);
+  *reinterpret_cast<uint32_t*>(dst) = pack2(h0, h1);
+  *reinterpret_cast<uint32_t*>(dst + n_pad) = pack2(a - h0, b - h1);
+}
+
+__device__ __forceinline__ float t_block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+// LayerNorm in fp32 (nn.LayerNorm on an fp32 array: fp32 statistics, fp32 affine); output as fp32
+// and / or as the split operand of the next GEMM.  One CTA per row, N % 4 == 0, N <= 8192.
+__global__ void __launch_bounds__(256) f32_layer_norm_kernel(const float* __restrict__ x, long ldx,
+                                                             const bf16* __restrict__ w,
+                                                             const bf16* __restrict__ b, float eps,
+                                                             float* __restrict__ out32, long ld32,
+                                                             bf16* __restrict__ out_split, long ld_split,
+                                                             int n_pad, int N) {
+  __shared__ float red[8];
+  const int t = blockIdx.x;
+  const int nv = N >> 2;
+  float4 h[8];
+  float s1 = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nv) {
+      h[u] = *reinterpret_cast<const float4*>(x + (long)t * ldx + c * 4);
+      s1 += (h[u].x + h[u].y) + (h[u].z + h[u].w);
+    }
+  }
+  const float mu = t_block_sum(s1, red) / (float)N;
+  float v = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    if (c < nv) {
+      const float d0 = h[u].x - mu, d1 = h[u].y - mu, d2 = h[u].z - mu, d3 = h[u].w - mu;
+      v += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  }
+  const float rstd = rsqrtf(t_block_sum(v, red) / (float)N + eps);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    if (c < nv) {
+      float wf[4] = {1.f, 1.f, 1.f, 1.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (w) unpack4(*reinterpret_cast<const uint2*>(w + c * 4), wf);
+      if (b) unpack4(*reinterpret_cast<const uint2*>(b + c * 4), bb);
+      const float o0 = (h[u].x - mu) * rstd * wf[0] + bb[0], o1 = (h[u].y - mu) * rstd * wf[1] + bb[1];
+      const float o2 = (h[u].z - mu) * rstd * wf[2] + bb[2], o3 = (h[u].w - mu) * rstd * wf[3] + bb[3];
+      if (out32) *reinterpret_cast<float4*>(out32 + (long)t * ld32 + c * 4) = make_float4(o0, o1, o2, o3);
+      if (out_split) split_store4(out_split + (long)t * ld_split + c * 4, n_pad, o0, o1, o2, o3);
+    }
+  }
+}
+
+// fp32 [T, N] -> split operand [T, hi | lo] (zero padding columns are the caller's: buffers are zeroed once)
+__global__ void f32_split_kernel(const float* __restrict__ x, long ldx, bf16* __restrict__ out, long ld_split,
+                                 int n_pad, int T, int N) {
+  const int nv = N >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)T * nv; i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / nv), c = (int)(i % nv);
+    const float4 v = *reinterpret_cast<const float4*>(x + (long)t * ldx + c * 4);
+    split_store4(out + (long)t * ld_split + c * 4, n_pad, v.x, v.y, v.z, v.w);
+  }
+}
+
+// Conv2d(kernel == stride) as a Linear: NHWC fp32 pixels -> rows of (kh, kw, c)-ordered patches, written
+// as a split operand [B * gh * gw, Kp | Kp] (K = ps * ps * C, zero padded to Kp).  (llava/vision.py:108-127)
+__global__ void clip_patchify_kernel(const float* __restrict__ pix, int B, int H, int W, int C, int ps,
+                                     bf16* __restrict__ out, int Kp) {
+  const int gh = H / ps, gw = W / ps, K = ps * ps * C;
+  const long total = (long)B * gh * gw * Kp;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    const long r = i / Kp;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C, kw = (k / C) % ps, kh = k / (C * ps);
+      const int gx = (int)(r % gw), gy = (int)((r / gw) % gh), b = (int)(r / ((long)gw * gh));
+      v = pix[(((long)b * H + gy * ps + kh) * W + gx * ps + kw) * C + c];
+    }
+    const float hi = rbf(v);
+    out[r * 2 * Kp + k] = f2bf(hi);
+    out[r * 2 * Kp + Kp + k] = f2bf(v - hi);
+  }
+}
+
+// emb[b][0] = cls + pos[0];  emb[b][1 + p] = patch[b][p] + pos[1 + p]   (fp32; cls == nullptr: no class
+// token, emb[b][p] = patch[b][p] + pos[pos_ids[b][p]] — the SigLIP form with bucketed position ids)
+__global__ void tower_embed_kernel(const float* __restrict__ patch, const bf16* __restrict__ cls,
+                                   const bf16* __restrict__ pos, const int* __restrict__ pos_ids,
+                                   float* __restrict__ emb, int B, int P, int E, int n_pos) {
+  const int L = P + (cls ? 1 : 0);
+  const long total = (long)B * L * (E >> 2);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (E >> 2));
+    const long r = i / (E >> 2);
+    const int l = (int)(r % L), b = (int)(r / L);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pe[4];
+    int pid = l;
+    if (cls) {
+      if (l == 0) {
+        float cf[4];
+        unpack4(*reinterpret_cast<const uint2*>(cls + c * 4), cf);
+        v = make_float4(cf[0], cf[1], cf[2], cf[3]);
+      } else {
+        v = *reinterpret_cast<const float4*>(patch + ((long)b * P + l - 1) * E + c * 4);
+      }
+    } else {
+      v = *reinterpret_cast<const float4*>(patch + ((long)b * P + l) * E + c * 4);
+      if (pos_ids) {
+        pid = pos_ids[(long)b * P + l];
+        if (pid < 0) pid += n_pos;  // numpy-style negative index (the reference's digitize(...) - 1 quirk)
+      }
+    }
+    unpack4(*reinterpret_cast<const uint2*>(pos + (long)pid * E + c * 4), pe);
+    *reinterpret_cast<float4*>(emb + r * E + c * 4) = make_float4(v.x + pe[0], v.y + pe[1], v.z + pe[2], v.w + pe[3]);
+  }
+}
+
+// ---- fp32 attention on the CUDA cores (exact fp32 softmax; flash-style running max / sum) -----------
+// CTA = 64 query rows of one head of one segment; 4 threads per row, each owns HD/4 dims of q and o.
+struct AttnF32P {
+  const float *q, *k, *v;
+  long q_ts, q_hs, k_ts, k_hs, v_ts, v_hs;  // element strides: token, head
+  float* out32;
+  long o_ts;
+  bf16* out_split;
+  long os_ts;
+  int n_pad;
+  int n_heads, n_kv, Lq, S;
+  long q_seg, k_seg;   // tokens between consecutive segments (blockIdx.z)
+  const unsigned char* key_mask;  // optional [segments][S]: 0 = key masked out
+  float scale;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
+  constexpr int DQ = HD / 4;     // dims per thread
+  constexpr int TK = HD > 80 ? 32 : 64;  // keys per tile (static shared memory <= 48 KB)
+  __shared__ __align__(16) float Ks[TK][HD];
+  __shared__ __align__(16) float Vs[TK][HD];
+  __shared__ unsigned char Ms[TK];
+  const int row = threadIdx.x >> 2, sub = threadIdx.x & 3;
+  const int h = blockIdx.y, kvh = h / (p.n_heads / p.n_kv), seg = blockIdx.z;
+  const int qi = blockIdx.x * 64 + row;
+  const float* qb = p.q + (long)seg * p.q_seg * p.q_ts + (long)h * p.q_hs;
+  const float* kb = p.k + (long)seg * p.k_seg * p.k_ts + (long)kvh * p.k_hs;
+  const float* vb = p.v + (long)seg * p.k_seg * p.v_ts + (long)kvh * p.v_hs;
+  float q[DQ], o[DQ];
+#pragma unroll
+  for (int i = 0; i < DQ; ++i) {
+    q[i] = (qi < p.Lq) ? qb[(long)qi * p.q_ts + sub * DQ + i] * p.scale : 0.f;
+    o[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < p.S; j0 += TK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < TK * (HD / 4); i += 256) {
+      const int kr = i / (HD / 4), c = i % (HD / 4);
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j0 + kr < p.S) {
+        kv = *reinterpret_cast<const float4*>(kb + (long)(j0 + kr) * p.k_ts + c * 4);
+        vv = *reinterpret_cast<const float4*>(vb + (long)(j0 + kr) * p.v_ts + c * 4);
+      }
+      *reinterpret_cast<float4*>(&Ks[kr][c * 4]) = kv;
+      *reinterpret_cast<float4*>(&Vs[kr][c * 4]) = vv;
+    }
+    if (threadIdx.x < TK)
+      Ms[threadIdx.x] = (j0 + threadIdx.x < p.S) &&
+                        (!p.key_mask || p.key_mask[(long)seg * p.S + j0 + threadIdx.x]);
+    __syncthreads();
+#pragma unroll 2
+    for (int kk = 0; kk < TK; ++kk) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < DQ; ++i) s = fmaf(q[i], Ks[kk][sub * DQ + i], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (!Ms[kk]) continue;   // uniform across the 4 threads of a row (and the warp: same key)
+      if (s > m) {             // rescale the running sum / output (rare after the first keys)
+        const float f = __expf(m - s);
+        l *= f;
+#pragma unroll
+        for (int i = 0; i < DQ; ++i) o[i] *= f;
+        m = s;
+      }
+      const float pj = __expf(s - m);
+      l += pj;
+#pragma unroll
+      for (int i = 0; i < DQ; ++i) o[i] = fmaf(pj, Vs[kk][sub * DQ + i], o[i]);
+    }
+  }
+  if (qi >= p.Lq) return;
+  const float inv = 1.0f / l;
+  const long t = (long)seg * p.q_seg + qi;
+  if constexpr (DQ % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < DQ; i += 4) {
+      const float a = o[i] * inv, b = o[i + 1] * inv, c = o[i + 2] * inv, d = o[i + 3] * inv;
+      const int col = h * HD + sub * DQ + i;
+      if (p.out32) *reinterpret_cast<float4*>(p.out32 + t * p.o_ts + col) = make_float4(a, b, c, d);
+      if (p.out_split) split_store4(p.out_split + t * p.os_ts + col, p.n_pad, a, b, c, d);
+    }
+  } else {  // head_dim 72: 18 dims per thread
+#pragma unroll
+    for (int i = 0; i < DQ; i += 2) {
+      const float a = o[i] * inv, b = o[i + 1] * inv;
+      const int col = h * HD + sub * DQ + i;
+      if (p.out32) *reinterpret_cast<float2*>(p.out32 + t * p.o_ts + col) = make_float2(a, b);
+      if (p.out_split) split_store2(p.out_split + t * p.os_ts + col, p.n_pad, a, b);
+    }
+  }
+}
+
+static inline int t_grid(long work, int block) {
+  long g = (work + block - 1) / block;
+  if (g > 148L * 16) g = 148L * 16;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+int f32_layer_norm(const float* x, long ldx, const void* w, const void* b, float eps, float* out32, long ld32,
+                   void* out_split, long ld_split, int n_pad, int T, int N, cudaStream_t st) {
+  B200_REQUIRE(x && T > 0 && N > 0 && (N % 4) == 0 && N <= 8192 && (ldx % 4) == 0, "f32_layer_norm: T=%d N=%d", T, N);
+  B200_REQUIRE(out32 || out_split, "f32_layer_norm: no output");
+  B200_REQUIRE(!out_split || ((ld_split % 4) == 0 && (n_pad % 4) == 0), "f32_layer_norm: split pitch");
+  f32_layer_norm_kernel<<<T, 256, 0, st>>>(x, ldx, (const bf16*)w, (const bf16*)b, eps, out32, ld32,
+                                           (bf16*)out_split, ld_split, n_pad, N);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int f32_split(const float* x, long ldx, void* out, long ld_split, int n_pad, int T, int N, cudaStream_t st) {
+  B200_REQUIRE(x && out && T > 0 && N > 0 && (N % 4) == 0 && (ldx % 4) == 0 && (ld_split % 4) == 0 && (n_pad % 4) == 0,
+               "f32_split: bad shape");
+  f32_split_kernel<<<t_grid((long)T * (N / 4), 256), 256, 0, st>>>(x, ldx, (bf16*)out, ld_split, n_pad, T, N);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int clip_patchify(const float* pix, int B, int H, int W, int C, int ps, void* out, int Kp, cudaStream_t st) {
+  B200_REQUIRE(pix && out && B > 0 && H % ps == 0 && W % ps == 0 && Kp >= ps * ps * C && (Kp % 8) == 0,
+               "clip_patchify: bad shape");
+  const long total = (long)B * (H / ps) * (W / ps) * Kp;
+  clip_patchify_kernel<<<t_grid(total, 256), 256, 0, st>>>(pix, B, H, W, C, ps, (bf16*)out, Kp);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int tower_embed(const float* patch, const void* cls, const void* pos, const int* pos_ids, float* emb, int B, int P,
+                int E, int n_pos, cudaStream_t st) {
+  B200_REQUIRE(patch && pos && emb && B > 0 && P > 0 && (E % 4) == 0, "tower_embed: bad shape");
+  const long total = (long)B * (P + (cls ? 1 : 0)) * (E / 4);
+  tower_embed_kernel<<<t_grid(total, 256), 256, 0, st>>>(patch, (const bf16*)cls, (const bf16*)pos, pos_ids, emb, B, P,
+                                                         E, n_pos);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int attention_f32(const float* q, long q_ts, long q_hs, const float* k, long k_ts, long k_hs, const float* v,
+                  long v_ts, long v_hs, float* out32, long o_ts, void* out_split, long os_ts, int n_pad,
+                  int n_heads, int n_kv, int hd, int Lq, int S, int n_seg, long q_seg, long k_seg,
+                  const unsigned char* key_mask, float scale, cudaStream_t st) {
+  B200_REQUIRE(q && k && v && (out32 || out_split) && Lq > 0 && S > 0 && n_seg > 0 && n_heads % n_kv == 0,
+               "attention_f32: bad arguments");
+  B200_REQUIRE((q_ts % 4) == 0 && (k_ts % 4) == 0 && (v_ts % 4) == 0 && (q_hs % 4) == 0 && (k_hs % 4) == 0 &&
+                   (v_hs % 4) == 0 && (o_ts % 4) == 0 && (os_ts % 4) == 0 && (n_pad % 4) == 0,
+               "attention_f32: strides must be multiples of 4 elements");
+  AttnF32P p;
+  p.q = q; p.k = k; p.v = v; p.q_ts = q_ts; p.q_hs = q_hs; p.k_ts = k_ts; p.k_hs = k_hs; p.v_ts = v_ts; p.v_hs = v_hs;
+  p.out32 = out32; p.o_ts = o_ts; p.out_split = (bf16*)out_split; p.os_ts = os_ts; p.n_pad = n_pad;
+  p.n_heads = n_heads; p.n_kv = n_kv; p.Lq = Lq; p.S = S; p.q_seg = q_seg; p.k_seg = k_seg; p.key_mask = key_mask;
+  p.scale = scale;
+  const dim3 grid(cdiv(Lq, 64), n_heads, n_seg);
+  if (hd == 64) attention_f32_kernel<64><<<grid, 256, 0, st>>>(p);
+  else if (hd == 72) attention_f32_kernel<72><<<grid, 256, 0, st>>>(p);   // SigLIP-SO400M (padded: see below)
+  else if (hd == 96) attention_f32_kernel<96><<<grid, 256, 0, st>>>(p);   // Idefics2 perceiver
+  else if (hd == 16) attention_f32_kernel<16><<<grid, 256, 0, st>>>(p);   // tiny test configurations
+  else if (hd == 32) attention_f32_kernel<32><<<grid, 256, 0, st>>>(p);
+  else {
+    set_error("attention_f32: head_dim %d (16|32|64|72|96)", hd);
+    return B200_ERR_INVALID;
+  }
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+extern "C" {
+int b200_f32_layer_norm(const float* x, long ldx, const void* w, const void* b, float eps, float* out32, long ld32,
+                        void* out_split, long ld_split, int n_pad, int T, int N, void* st) {
+  return f32_layer_norm(x, ldx, w, b, eps, out32, ld32, out_split, ld_split, n_pad, T, N, (cudaStream_t)st);
+}
+int b200_f32_split(const float* x, long ldx, void* out, long ld_split, int n_pad, int T, int N, void* st) {
+  return f32_split(x, ldx, out, ld_split, n_pad, T, N, (cudaStream_t)st);
+}
+int b200_clip_patchify(const float* pix, int B, int H, int W, int C, int ps, void* out, int Kp, void* st) {
+  return clip_patchify(pix, B, H, W, C, ps, out, Kp, (cudaStream_t)st);
+}
+int b200_tower_embed(const float* patch, const void* cls, const void* pos, const int* pos_ids, float* emb, int B,
+                     int P, int E, int n_pos, void* st) {
+  return tower_embed(patch, cls, pos, pos_ids, emb, B, P, E, n_pos, (cudaStream_t)st);
+}
+int b200_attention_f32(const float* q, long q_ts, long q_hs, const float* k, long k_ts, long k_hs, const float* v,
+                       long v_ts, long v_hs, float* out32, long o_ts, void* out_split, long os_ts, int n_pad,
+                       int n_heads, int n_kv, int hd, int Lq, int S, int n_seg, long q_seg, long k_seg,
+                       const unsigned char* key_mask, float scale, void* st) {
+  return attention_f32(q, q_ts, q_hs, k, k_ts, k_hs, v, v_ts, v_hs, out32, o_ts, out_split, os_ts, n_pad, n_heads,
+                       n_kv, hd, Lq, S, n_seg, q_seg, k_seg, key_mask, scale, (cudaStream_t)st);
+}
+/* fp32-accurate Linear on the tensor cores: X = split operand [T, n_parts x Kp] (Kp = K_w rounded up to 64),
+ * W [N, K_w] bf16; mode B200_WT_F32 (C32 = act(acc + bias) + res32) or B200_WT_SPLIT (Csplit = [hi | lo]). */
+int b200_gemm_wt_f32(const void* X, long ldx, const void* W, long ldw, const void* bias, const float* res32,
+                     long ldr32, float* C32, long ldc32, void* Csplit, long ld_split, int n_pad, int T, int N,
+                     int K_w, int n_parts, int epilogue, int mode, void* stream) {
+  const int kbw = cdiv(K_w, 64);
+  WtExt ext;
+  ext.kb_w = kbw; ext.k_w = K_w; ext.ldw = ldw; ext.C32 = C32; ext.res32 = res32; ext.ldc32 = ldc32;
+  ext.ldr32 = ldr32; ext.Csplit = (bf16*)Csplit; ext.ld_split = ld_split; ext.n_pad = n_pad;
+  return gemm_wt_tuned(X, ldx, W, bias, nullptr, 0, nullptr, 0, nullptr, 0, T, N, n_parts * kbw * 64, epilogue, mode, 0,
+                       false, 148, nullptr, (cudaStream_t)stream, &ext);
+}
+}

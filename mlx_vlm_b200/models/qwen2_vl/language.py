@@ -161,8 +161,6 @@ class LanguageModel:
             self._rope_deltas = _np(rope_deltas_kw)
         if cache is None or cache[0] is None:
             cache = self.make_cache()  # stateless call: throw-away cache
-        cache_offset = int(cache[0].offset)
-
         ids_host = _np(inputs)
         if ids_host.ndim == 1:
             ids_host = ids_host[None]
@@ -170,6 +168,7 @@ class LanguageModel:
         if isinstance(cache[0], RowBatchKVCache):
             return self._call_batch(ids_host, inputs_embeds, mask, cache, rope_deltas_kw, position_ids,
                                     reserve_tokens)
+        cache_offset = int(cache[0].offset)
         if B != 1:
             raise ValueError("a batch of rows needs a batch cache: LanguageModel.make_batch_cache(rows) "
                              "(device-resident RowBatchKVCache)")

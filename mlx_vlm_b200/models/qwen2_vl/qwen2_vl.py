@@ -41,6 +41,16 @@ def weight_manifest(c: N.Qwen2VLConfig):
     E, Em, mg = c.v_embed, c.v_mlp, c.v_merge ** 2 * c.v_embed
     H, I = c.hidden, c.inter
     QKV = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim
+    out = []
+    if c.external_vision:   # decoder-only engine (LLaVA / Idefics2): the tower's weights live with the tower
+        out += [("lm.embed", (c.vocab, H)), ("lm.norm", (H,))]
+        if not c.tie_embeddings:
+            out.append(("lm.head", (c.vocab, H)))
+        for i in range(c.n_layers):
+            q = f"lm.{i}."
+            out += [(q + "ln1", (H,)), (q + "ln2", (H,)), (q + "wqkv", (QKV, H)), (q + "bqkv", (QKV,)),
+                    (q + "wo", (H, c.n_heads * c.head_dim)), (q + "wgu", (2 * I, H)), (q + "wd", (H, I))]
+        return out
     out = [("v.patch_embed.w", (E, c.v_patch_dim))]
     for i in range(c.v_depth):
         q = f"v.blk.{i}."

@@ -157,6 +157,7 @@ def test_fused_greedy_decode_hook_batched_and_cache_surgery():
         lm._rope_deltas, lm._position_ids = None, None
         lm(rid, inputs_embeds=emb.inputs_embeds, cache=rc, position_ids=emb.position_ids,
            rope_deltas=emb.rope_deltas, logits_to_keep=1, reserve_tokens=256)
+        eng.stream.synchronize()
         firsts.append(int(eng.token_log_view()[(eng.tokens_launched - 1) % eng.token_log_capacity]))
         deltas.append(int(np.asarray(emb.rope_deltas).reshape(-1)[0]))
         rows.lengths[b] = rid.shape[1]
@@ -181,6 +182,7 @@ def test_fused_greedy_decode_hook_batched_and_cache_surgery():
     lm._rope_deltas, lm._position_ids = None, None
     lm(rid, inputs_embeds=emb.inputs_embeds, cache=single, position_ids=emb.position_ids,
        rope_deltas=emb.rope_deltas, logits_to_keep=1)
+    eng.stream.synchronize()
     first3 = int(eng.token_log_view()[(eng.tokens_launched - 1) % eng.token_log_capacity])
     from mlx_vlm_b200.models.cache import RowBatchKVCache
     other = [RowBatchKVCache.merge([single[l]], engine=eng) if l == 0 else None for l in range(len(single))]
