@@ -305,6 +305,157 @@ def c5_leg(world, rank, dev, args):
     return out
 
 
+def c3_leg(dev, args):
+    """BASELINE config 3: LLaVA-1.5-7B (CLIP-ViT-L/14-336 + Llama-7B geometry) bf16, batch = 8 images,
+    prefill only: pinned-host pixel_values -> CLIP tower (23 of 24 blocks: feature layer -2) -> projector
+    -> merge -> LM prefill of the 8 requests (576 image + 32 text tokens each) incl. the first token.
+    The tower is fp32-accurate like the reference's (split-operand tcgen05 GEMMs: every Linear runs as
+    W.x_hi + W.x_lo, i.e. 2x the algorithmic MMA flops; attention / LayerNorm in fp32 on the CUDA cores)."""
+    import numpy as np
+    import torch
+    from mlx_vlm_b200.models.cache import make_prompt_cache
+    from mlx_vlm_b200.models.llava import Model
+    from mlx_vlm_b200.models.llava.config import llava_15_7b_config
+    cfg = llava_15_7b_config()
+    model = Model(cfg, device=dev).init_random(2)
+    eng, lm = model.engine, model.language_model
+    v, t = cfg.vision_config, cfg.text_config
+    B, n_text = 8, 32
+    P = (v.image_size // v.patch_size) ** 2
+    rng = np.random.default_rng(11)
+    pv_host = torch.from_numpy(rng.standard_normal((B, 3, v.image_size, v.image_size)).astype(np.float32)).pin_memory()
+    text = rng.integers(3, 31000, size=n_text)
+    ids = np.concatenate([text[:n_text // 2], np.full(P, cfg.image_token_index), text[n_text // 2:]])[None]
+    T = ids.shape[1]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step():
+        with torch.cuda.stream(eng.stream):
+            pv = pv_host.to(dev, non_blocking=True)
+        ev[0].record(eng.stream)
+        feats = model.encode_image(pv)
+        ev[1].record(eng.stream)
+        for b in range(B):
+            emb = model.get_input_embeddings(ids, pv, cached_image_features=feats[b:b + 1])
+            cache = make_prompt_cache(lm)
+            lm(ids, inputs_embeds=emb.inputs_embeds, cache=cache, logits_to_keep=1, reserve_tokens=T + 8)
+        ev[2].record(eng.stream)
+        eng.stream.synchronize()
+        return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+
+    for _ in range(3):
+        step()
+    K = max(2, min(args.steps, 5))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tw, pf = 0.0, 0.0
+    for _ in range(K):
+        a, b = step()
+        tw += a
+        pf += b
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / K
+    tw, pf = tw / K, pf / K
+    E, I, nh = v.hidden_size, v.intermediate_size, v.num_attention_heads
+    L = P + 1
+    n_blocks = v.num_hidden_layers + 1 + cfg.vision_feature_layer if cfg.vision_feature_layer < 0 else cfg.vision_feature_layer
+    H, Il = t.hidden_size, t.intermediate_size
+    hd = H // t.num_attention_heads
+    qkv = (t.num_attention_heads + 2 * t.num_key_value_heads) * hd
+    tower_gf = (n_blocks * (2 * B * L * (4 * E * E + 2 * E * I) + 4 * B * L * L * E)
+                + 2 * B * P * (3 * v.patch_size ** 2) * E + 2 * B * P * (E * H + H * H)) / 1e9
+    lm_gf = B * (t.num_hidden_layers * (2 * T * (H * qkv + H * H + 3 * H * Il) + 2 * T * T * H) + 2 * t.vocab_size * H) / 1e9
+    tpeak, tsrc = _tensor_peak()
+    out = {"workload": f"C3: LLaVA-1.5-7B bf16 (random init), batch {B} x 336x336 images, prefill only: CLIP-L/14 tower "
+                       f"({n_blocks} blocks, fp32-accurate split-operand GEMMs) + projector + merge + Llama-7B prefill "
+                       f"of {B} requests x T={T} ({P} image + {n_text} text tokens)",
+           "tower_projector_ms": tw, "lm_prefill_ms": pf, "ms_per_step": tw + pf, "wall_ms_per_step": wall * 1e3,
+           "prefill_img_tokens_per_sec": B * P / ((tw + pf) / 1e3),
+           "tower_img_tokens_per_sec": B * P / (tw / 1e3),
+           "h2d_bytes_per_step": int(pv_host.numel() * 4),
+           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": tpeak, "peak_source": tsrc,
+                        "tower": {"algorithmic_gflop": tower_gf, "achieved": tower_gf / tw, "frac": tower_gf / tw / tpeak,
+                                  "executed_mma_gflop": "2x the Linear share (hi + lo operand halves)"},
+                        "lm_prefill": {"algorithmic_gflop": lm_gf, "achieved": lm_gf / pf, "frac": lm_gf / pf / tpeak},
+                        "achieved": (tower_gf + lm_gf) / (tw + pf), "frac": (tower_gf + lm_gf) / (tw + pf) / tpeak}}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def c4_leg(dev, args):
+    """BASELINE config 4: Idefics2-8B (SigLIP-SO400M + perceiver + Mistral-7B geometry) bf16, one request with
+    4 images of 448x448 (4 x 1024 patches -> 4 x 64 latents = 256 image tokens) interleaved with 256 text
+    tokens (T = 512), 256 greedy tokens out."""
+    import numpy as np
+    import torch
+    from mlx_vlm_b200.models.cache import make_prompt_cache
+    from mlx_vlm_b200.models.idefics2 import Model
+    from mlx_vlm_b200.models.idefics2.config import idefics2_8b_config
+    cfg = idefics2_8b_config()
+    model = Model(cfg, device=dev).init_random(3)
+    model.config.eos_token_id = []
+    eng, lm = model.engine, model.language_model
+    v, t, pc = cfg.vision_config, cfg.text_config, cfg.perceiver_config
+    n_img, side, n_text, n_out = 4, 448, 256, 256
+    nl = pc.resampler_n_latents
+    rng = np.random.default_rng(13)
+    pv_host = rng.standard_normal((1, n_img, 3, side, side)).astype(np.float32)
+    text = rng.integers(3, 31000, size=n_text)
+    seg = n_text // (n_img + 1)
+    parts = []
+    for i in range(n_img):   # text / image / text / image ... (interleaved, like the processor's <image> expansion)
+        parts += [text[i * seg:(i + 1) * seg], np.full(nl, cfg.image_token_index)]
+    parts.append(text[n_img * seg:])
+    ids = np.concatenate(parts)[None]
+    T = ids.shape[1]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step():
+        ev[0].record(eng.stream)
+        feats = model.encode_image(pv_host)          # host pixels: pinned H2D inside
+        ev[1].record(eng.stream)
+        emb = model.get_input_embeddings(ids, pv_host, cached_image_features=feats)
+        cache = make_prompt_cache(lm)
+        lm(ids, inputs_embeds=emb.inputs_embeds, cache=cache, logits_to_keep=1, reserve_tokens=T + n_out + 1)
+        ev[2].record(eng.stream)
+        lm.fused_greedy_decode_n(n_out, cache, reserve_tokens=T + n_out + 1)
+        ev[3].record(eng.stream)
+        eng.stream.synchronize()
+        return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+
+    for _ in range(2):
+        step()
+    K = max(2, min(args.steps, 3))
+    l0 = eng.launch_count
+    acc = [0.0, 0.0, 0.0]
+    for _ in range(K):
+        for i, x in enumerate(step()):
+            acc[i] += x / K
+    launches = (eng.launch_count - l0) / K
+    tw, pf, dec = acc
+    H, Il = t.hidden_size, t.intermediate_size
+    hd = H // t.num_attention_heads
+    qkv = (t.num_attention_heads + 2 * t.num_key_value_heads) * hd
+    w_bytes = 2 * (t.num_hidden_layers * (H * qkv + H * H + 3 * H * Il) + t.vocab_size * H)
+    kv_pos = 2 * t.num_key_value_heads * hd * 2 * t.num_hidden_layers
+    bytes_step = w_bytes + kv_pos * (T + n_out / 2)
+    step_ms = dec / n_out
+    peak, psrc = _peaks()
+    out = {"workload": f"C4: Idefics2-8B bf16 (random init), 1 request, {n_img} x {side}x{side} images ({n_img} x "
+                       f"{(side // v.patch_size) ** 2} patches -> {n_img * nl} image tokens) interleaved with {n_text} text "
+                       f"tokens (T={T}), {n_out} greedy tokens out",
+           "tower_connector_ms": tw, "merge_prefill_ms": pf, "decode_ms": dec, "decode_ms_per_token": step_ms,
+           "decode_tokens_per_sec": n_out / (dec / 1e3), "prefill_img_tokens_per_sec": n_img * nl / ((tw + pf) / 1e3),
+           "gpu_launches_per_request": launches,
+           "roofline": {"kernel": "decode step of the Mistral-7B geometry (32 q / 8 kv heads)", "bound": "hbm",
+                        "achieved": bytes_step / (step_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": psrc,
+                        "frac": bytes_step / (step_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_step": bytes_step}}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -313,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (Qwen2-VL-7B continuous batching)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 leg (LLaVA-1.5-7B, 8 images, prefill only)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 leg (Idefics2-8B, 4 images, 256 out)")
     ap.add_argument("--c5-rows", type=int, default=8, help="concurrent requests per GPU in the C5 leg")
     ap.add_argument("--c5-out", type=int, default=512)
     ap.add_argument("--no-graph", action="store_true")
@@ -475,6 +628,11 @@ def main():
     if not args.no_c5:
         c5 = c5_leg(world, rank, dev, args)
 
+    c3 = c3_leg(dev, args) if (rank == 0 and not args.no_c3) else None
+    c4 = c4_leg(dev, args) if (rank == 0 and not args.no_c4) else None
+    if world > 1:
+        dist.barrier()
+
     stats = torch.tensor([dec_ms, pre_ms, wall, e2e_t], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -533,6 +691,10 @@ def main():
             line["weight_broadcast"] = bcast
         if c5 is not None:
             line["c5"] = c5
+        if c3 is not None:
+            line["c3"] = c3
+        if c4 is not None:
+            line["c4"] = c4
         if not args.no_cpu_baseline and world == 1:
             W = _engine_weights_to_oracle(model, __import__("oracle.qwen2vl", fromlist=["x"]).qwen2_vl_2b())
             r = cpu_reference_run(W, 6)

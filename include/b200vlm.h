@@ -197,8 +197,9 @@ int b200_engine_vision(b200_engine* e, const float* pixel_values,
 /* LanguageModel.__call__ for L>1 (language.py:404-518; Qwen2Model :170-200):
  * embeds (T, hidden) bf16, pos3 (3,T) int32 device, cache row `row` holds ctx0
  * tokens already.  Appends T tokens of K/V.  If all_logits_out != NULL it
- * receives (T, vocab) bf16 logits of every row (the reference computes them,
- * ar.py:358); the last row always goes through the fused head+sampler:
+ * receives bf16 logits of every row (the reference computes them, ar.py:358),
+ * rows round8(vocab) elements apart (= vocab for every vocabulary that is a
+ * multiple of 8; 16-byte aligned rows otherwise); the last row always goes through the fused head+sampler:
  * logits / logprobs (ar.py:368) / greedy token (sample_utils.py:63-64) land in
  * the engine's step buffers and the decode state is armed with
  * position = ctx0 + T + rope_delta. */
@@ -264,6 +265,13 @@ int b200_engine_fetch_tokens(b200_engine* e, long start, int n, int* host_out, v
 int b200_f32_layer_norm(const float* x, long ldx, const void* w, const void* b, float eps, float* out32,
                         long ld32, void* out_split, long ld_split, int n_pad, int T, int N, void* stream);
 int b200_f32_split(const float* x, long ldx, void* out_split, long ld_split, int n_pad, int T, int N, void* stream);
+/* nn.RMSNorm on fp32 rows (idefics2.py:60-90,118-143); input row t goes to output row
+ * (t / seg_in) * seg_out + seg_off + t % seg_in (seg_in == 0: row t) */
+int b200_f32_rms_norm(const float* x, long ldx, const void* w, float eps, float* out32, long ld32, void* out_split,
+                      long ld_split, int n_pad, int T, int N, int seg_in, int seg_out, int seg_off, void* stream);
+/* fp32 SwiGLU of gu = [gate | up] ([T, 2I]) -> split operand (idefics2.py:146-171) */
+int b200_f32_swiglu_split(const float* gu, long ldg, void* out_split, long ld_split, int n_pad, int T, int I,
+                          void* stream);
 /* Conv2d(kernel == stride) patch rows, (kh, kw, c) order, from NHWC fp32 pixels, as a split operand
  * [B*gh*gw, Kp | Kp] (llava/vision.py:108-127, idefics2/vision.py:123-148) */
 int b200_clip_patchify(const float* pixels_nhwc, int B, int H, int W, int C, int patch, void* out_split, int Kp,
@@ -305,8 +313,9 @@ int b200_batch_decode(b200_engine* e, int n_steps, int want_logprobs, void* stre
  * host arrays [n_steps][B] */
 int b200_batch_fetch(b200_engine* e, long first_step, int n_steps, int* tok_host, float* lp_host,
                      void* stream);
-const void* b200_batch_logits(b200_engine* e);   /* device bf16 [B][vocab] of the last step */
-const void* b200_batch_logprobs(b200_engine* e); /* device bf16 [B][vocab] (want_logprobs)   */
+/* device bf16 [B][round8(vocab)] of the last step; columns >= vocab hold -inf */
+const void* b200_batch_logits(b200_engine* e);
+const void* b200_batch_logprobs(b200_engine* e); /* same layout (want_logprobs) */
 const int* b200_batch_token_log(b200_engine* e); /* device int32 [4096 steps][16 rows]        */
 /* BatchKVCache.filter / extend / extract (cache.py:1077-1201) on device pools: copy the first
  * n_tokens positions of one row of a pool into a row of another (or the same) pool */

@@ -79,6 +79,8 @@ SIGNATURES = {
     "b200_engine_device_error": (_I, [_P, C.POINTER(_I)]),
     "b200_engine_fetch_tokens": (_I, [_P, _L, _I, _P, _P]),
     "b200_f32_layer_norm": (_I, [_P, _L, _P, _P, _F, _P, _L, _P, _L, _I, _I, _I, _P]),
+    "b200_f32_rms_norm": (_I, [_P, _L, _P, _F, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "b200_f32_swiglu_split": (_I, [_P, _L, _P, _L, _I, _I, _I, _P]),
     "b200_f32_split": (_I, [_P, _L, _P, _L, _I, _I, _I, _P]),
     "b200_clip_patchify": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "b200_tower_embed": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

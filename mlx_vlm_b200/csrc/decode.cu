@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(256) k_sample(const DecodeDims d,
   __syncthreads();
   const float lse = s_lse;
   unsigned long long best = 0ull;
-  const int nvec = d.vocab >> 3;  // vocab % 8 == 0 is checked on the host
+  const int nvec = (d.vocab + 7) >> 3;  // the tail of an odd vocabulary holds -inf (preset at creation)
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nvec; c += gridDim.x * blockDim.x) {
     float f[8];
     unpack8(*reinterpret_cast<const uint4*>(logits + (long)c * 8), f);

@@ -338,9 +338,9 @@ __device__ __forceinline__ uint32_t bd_orderable(float f) {
 }
 
 struct BdSampleP {
-  const bf16* logits;  // [B][V]
-  bf16* logprobs;      // [B][V] or nullptr
-  int V, H;
+  const bf16* logits;  // [B][ldv]
+  bf16* logprobs;      // [B][ldv] or nullptr
+  int V, ldv, H;
   int *tok, *ctx, *pos, *n_out;
   const int* active;
   int* token_log;      // [log_cap][max_b]
@@ -362,8 +362,9 @@ __global__ void __launch_bounds__(1024) bd_sample_kernel(const BdSampleP p) {
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bd_pdl_wait();
-  const bf16* lg = p.logits + (long)b * p.V;
-  const int nv = p.V >> 3;
+  // rows are ldv = round8(V) apart; the tail [V, ldv) holds -inf (preset once, never written)
+  const bf16* lg = p.logits + (long)b * p.ldv;
+  const int nv = p.ldv >> 3;
   // logsumexp over the bf16 logits (fp32), then logprobs = bf16(logit - bf16(lse)) (ar.py:368)
   float m = -INFINITY, l = 0.f;
   for (int c = threadIdx.x; c < nv; c += 1024) {
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(1024) bd_sample_kernel(const BdSampleP p) {
     if (p.logprobs) {
       uint4 ov;
       ov.x = pack2(o[0], o[1]); ov.y = pack2(o[2], o[3]); ov.z = pack2(o[4], o[5]); ov.w = pack2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(p.logprobs + (long)b * p.V + c * 8) = ov;
+      *reinterpret_cast<uint4*>(p.logprobs + (long)b * p.ldv + c * 8) = ov;
     }
   }
 #pragma unroll
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__(1024) bd_sample_kernel(const BdSampleP p) {
 struct BatchDecoder {
   int max_b = 0, B = 0;
   int log_cap = 4096;
+  int ldv = 0;  // row stride of logits / logprobs: vocab rounded up to 8
   int *tok = nullptr, *ctx = nullptr, *pos = nullptr, *active = nullptr, *n_out = nullptr;
   int* token_log = nullptr;
   float* lp_log = nullptr;
@@ -488,8 +490,14 @@ static int bd_alloc(BatchDecoder* d, const BdModel& m, int max_b) {
   B200_CUDA(cudaMalloc(&d->lp_log, (size_t)d->log_cap * max_b * 4));
   B200_CUDA(cudaMalloc(&d->h, (size_t)max_b * dd.hidden * 2)); B200_CUDA(cudaMalloc(&d->xn, (size_t)max_b * dd.hidden * 2));
   B200_CUDA(cudaMalloc(&d->att, (size_t)max_b * QH * 2)); B200_CUDA(cudaMalloc(&d->act, (size_t)max_b * dd.inter * 2));
-  B200_CUDA(cudaMalloc(&d->logits, (size_t)max_b * dd.vocab * 2));
-  B200_CUDA(cudaMalloc(&d->logprobs, (size_t)max_b * dd.vocab * 2));
+  d->ldv = (dd.vocab + 7) & ~7;
+  B200_CUDA(cudaMalloc(&d->logits, (size_t)max_b * d->ldv * 2));
+  B200_CUDA(cudaMalloc(&d->logprobs, (size_t)max_b * d->ldv * 2));
+  {
+    std::vector<uint16_t> ninf((size_t)max_b * d->ldv, (uint16_t)0xFF80);  // bf16 -inf
+    B200_CUDA(cudaMemcpy(d->logits, ninf.data(), ninf.size() * 2, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d->logprobs, ninf.data(), ninf.size() * 2, cudaMemcpyHostToDevice));
+  }
   // split-K partials: at most ~sm_count CTAs x 128 rows x 16 tokens of fp32 per GEMM, x2 margin
   d->partial_bytes = 64L << 20;
   B200_CUDA(cudaMalloc(&d->partial, d->partial_bytes));
@@ -558,11 +566,11 @@ static int bd_enqueue_step(BatchDecoder* d, const BdModel& m, cudaStream_t s, lo
       return rc;
     *launches += 7;
   }
-  if ((rc = gemm_wt_tuned(d->xn, H, m.head, nullptr, nullptr, 0, d->logits, dd.vocab, nullptr, 0, B, dd.vocab, H,
+  if ((rc = gemm_wt_tuned(d->xn, H, m.head, nullptr, nullptr, 0, d->logits, d->ldv, nullptr, 0, B, dd.vocab, H,
                           B200_EPI_NONE, B200_WT_BF16, 0, false, m.sm_count, nullptr, s)))
     return rc;
   BdSampleP sp;
-  sp.logits = d->logits; sp.logprobs = d->want_logprobs ? d->logprobs : nullptr; sp.V = dd.vocab; sp.H = H;
+  sp.logits = d->logits; sp.logprobs = d->want_logprobs ? d->logprobs : nullptr; sp.V = dd.vocab; sp.ldv = d->ldv; sp.H = H;
   sp.tok = d->tok; sp.ctx = d->ctx; sp.pos = d->pos; sp.n_out = d->n_out; sp.active = d->active;
   sp.token_log = d->token_log; sp.lp_log = d->lp_log; sp.log_cap = d->log_cap; sp.max_b = d->max_b;
   sp.embed = m.embed; sp.ln0 = m.layers[0].ln1; sp.eps = dd.eps; sp.h = d->h; sp.xn = d->xn;

@@ -353,6 +353,12 @@ static int kernels_per_step(const b200_engine* e) {
 static long align256(long x) { return (x + 255) & ~255L; }
 static const long WT_PARTIAL_BYTES = 48L << 20;  // fp32 split-K partial tiles (bounded: see gemm_wt_auto)
 static long round8(long x) { return (x + 7) & ~7L; }
+// creation-time helper: a bf16 buffer of -inf (the padding of logits rows beyond an odd vocabulary)
+static int fill_bf16_neg_inf(void* dst, long n) {
+  std::vector<uint16_t> host((size_t)n, (uint16_t)0xFF80);
+  B200_CUDA(cudaMemcpy(dst, host.data(), (size_t)n * 2, cudaMemcpyHostToDevice));
+  return B200_OK;
+}
 static float* ws_partial(b200_engine* e) {
   return reinterpret_cast<float*>(e->ws + ((e->ws_bytes - WT_PARTIAL_BYTES - 2048) & ~255L));
 }
@@ -659,7 +665,8 @@ static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ct
       return rc;
   }
   if (all_logits_out) {  // the reference computes the head on every row (ar.py:358); xn = final norm
-    if ((rc = v2_linear(e, xn, H, e->head, nullptr, (bf16*)all_logits_out, c.vocab, T, c.vocab, (int)H,
+    // rows of the caller's buffer are round8(vocab) apart (16-byte aligned rows for any vocabulary)
+    if ((rc = v2_linear(e, xn, H, e->head, nullptr, (bf16*)all_logits_out, round8(c.vocab), T, c.vocab, (int)H,
                         B200_EPI_NONE, s)))
       return rc;
   }
@@ -685,10 +692,12 @@ int b200_device_check(int device, int* sm_count) {
 
 int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine** out) {
   B200_REQUIRE(cfg && out, "engine_create: null argument");
-  B200_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0 && cfg->vocab % 8 == 0 &&
+  // the vocabulary may be any size (Idefics2: 32003): logits / logprobs rows are allocated to the next
+  // multiple of 8 with the tail preset to -inf, which the vectorised sampler passes read as "never wins"
+  B200_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0 && cfg->vocab > 0 &&
                    cfg->head_dim % 8 == 0 && cfg->n_heads % cfg->n_kv_heads == 0,
-               "engine_create: dims must be multiples of 8 (hidden=%d inter=%d vocab=%d)",
-               cfg->hidden, cfg->inter, cfg->vocab);
+               "engine_create: dims must be multiples of 8 (hidden=%d inter=%d)",
+               cfg->hidden, cfg->inter);
   int sm = 0;
   int rc = b200_device_check(device, &sm);
   if (rc) return rc;
@@ -708,8 +717,10 @@ int b200_engine_create(const b200_qwen2vl_config* cfg, int device, b200_engine**
   B200_CUDA(cudaMalloc(&e->qbuf, (size_t)c.n_heads * c.head_dim * 2));
   B200_CUDA(cudaMalloc(&e->attn, (size_t)c.n_heads * c.head_dim * 2));
   B200_CUDA(cudaMalloc(&e->act, (size_t)c.inter * 2));
-  B200_CUDA(cudaMalloc(&e->logits, (size_t)c.vocab * 2));
-  B200_CUDA(cudaMalloc(&e->logprobs, (size_t)c.vocab * 2));
+  B200_CUDA(cudaMalloc(&e->logits, (size_t)round8(c.vocab) * 2));
+  B200_CUDA(cudaMalloc(&e->logprobs, (size_t)round8(c.vocab) * 2));
+  if ((rc = fill_bf16_neg_inf(e->logits, round8(c.vocab))) || (rc = fill_bf16_neg_inf(e->logprobs, round8(c.vocab))))
+    return rc;
   B200_CUDA(cudaMalloc(&e->partials, (size_t)sm * 8 * sizeof(float2)));
   B200_CUDA(cudaMalloc(&e->token_log, (size_t)e->log_cap * 4));
   B200_CUDA(cudaMalloc(&e->force, (size_t)e->log_cap * 4));
@@ -989,6 +1000,7 @@ int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3, int
   }
   if (all_logits_out) {  // the reference computes the head on every row (ar.py:358)
     if ((rc = rms_norm(h, e->norm, xn, T, (int)H, c.rms_eps, s))) return rc;
+    B200_REQUIRE(c.vocab % 8 == 0, "prefill (round-1 kernels): all-row logits need vocab %% 8 == 0");
     if ((rc = gemm_bf16_tn(xn, H, e->head, nullptr, nullptr, 0, all_logits_out, c.vocab, T,
                            c.vocab, (int)H, B200_EPI_NONE, s)))
       return rc;

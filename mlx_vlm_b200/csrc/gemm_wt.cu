@@ -315,7 +315,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     w_ebar();
     if (!(p.flags & 4u)) {
       if (p.mode == B200_WT_BF16) {
-        const bool vec_ok = ((p.N & 7) == 0) && ((p.ldc & 7) == 0) && (!p.residual || (p.ldr & 7) == 0) &&
+        const bool vec_all = ((p.ldc & 7) == 0) && (!p.residual || (p.ldr & 7) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
 #pragma unroll
@@ -325,6 +325,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           const int t = t0 + c0 + tl, n = n0 + ch * 8;
           if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
           const uint4 sv = *reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + ch * 8) * 2);
+          const bool vec_ok = vec_all && n + 8 <= p.N;  // only the last chunk of an odd N goes element-wise
           if (vec_ok) {
             uint4 o = sv;
             if (p.residual) {
@@ -907,10 +908,17 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
       cand.push_back(model);
     }
     // ---- time them (the tuning launches never add a residual: the output stays idempotent) ----
+    // An fp32 output that is also its own residual (h += W.x in place) must not be overwritten by the
+    // measurement: those launches write a scratch buffer from the stream-ordered allocator instead.
     WtExt ext_copy;
     const WtExt* ext_t = nullptr;
+    float* scratch32 = nullptr;
     if (ext) {
       ext_copy = *ext;
+      if (mode == B200_WT_F32 && ext->res32 && ext->C32) {
+        B200_CUDA(cudaMallocAsync((void**)&scratch32, (size_t)T * (size_t)ext->ldc32 * sizeof(float), st));
+        ext_copy.C32 = scratch32;
+      }
       ext_copy.res32 = nullptr;
       ext_t = &ext_copy;
     }
@@ -956,6 +964,7 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (scratch32) cudaFreeAsync(scratch32, st);
     if (rc) {
       set_error("gemm_wt: configuration measurement failed (T=%d N=%d K=%d mode=%d)", T, N, K, mode);
       return rc;
@@ -979,7 +988,7 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
   if (cfg.TN > round16(T)) cfg.TN = round16(T);
   while (cfg.split > 1 && !fits(cfg)) cfg.split = cdiv(kb_total, cdiv(kb_total, cfg.split - 1));
   if (split_out) *split_out = cfg.split;
-  return gemm_wt(X, ldx, W, bias, residual, ldr, C, ldc, partial, T, N, K, epilogue, mode, inter, cfg, 0, st);
+  return gemm_wt(X, ldx, W, bias, residual, ldr, C, ldc, partial, T, N, K, epilogue, mode, inter, cfg, 0, st, ext);
 }
 
 int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,

@@ -664,7 +664,7 @@ __device__ __forceinline__ void mega_sample_finalize(const MegaP& p, MegaShared&
   {
     const float lse = sh.lse;
     unsigned long long best = 0ull;
-    const int nvec = d.vocab >> 3;
+    const int nvec = (d.vocab + 7) >> 3;  // the tail of an odd vocabulary holds -inf (preset at creation)
     for (int c = blockIdx.x * 256 + threadIdx.x; c < nvec; c += gridDim.x * 256) {
       float f[8], o[8];
       unpack8(ldcg16(p.logits + (long)c * 8), f);

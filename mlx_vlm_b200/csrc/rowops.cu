@@ -227,47 +227,62 @@ __global__ void swiglu_kernel(const bf16* __restrict__ gu, bf16* __restrict__ ou
 }
 
 // ---------------------------------------------------------------------------
-// embed + merge (qwen2_vl.py:48,78-148).  One CTA per batch row computes the
-// inclusive prefix count of image positions with a block scan, then all threads
-// copy rows (16-byte vectors).  feature_start of row b = number of image
-// positions in rows < b (counted redundantly by each CTA; B and T are small).
-__global__ void embed_merge_kernel(const int* __restrict__ ids, int B, int T,
+// embed + merge (qwen2_vl.py:48,78-148).  grid = (CTAs per row, B).  Every CTA of a batch row computes
+// the prefix count of image positions of that row with a block scan (each thread owns a contiguous chunk
+// of ids, chunk totals are scanned with warp shuffles: integer, order-independent), then copies ITS share
+// of the row's positions (16-byte vectors).  feature_start of row b = number of image positions in rows
+// < b (counted redundantly by each CTA; B * T ids are a few KB).
+__global__ void __launch_bounds__(512) embed_merge_kernel(const int* __restrict__ ids, int B, int T,
                                    const bf16* __restrict__ table, int hidden,
                                    const bf16* __restrict__ feats, int n_feats, int image_token,
                                    int video_token, bf16* __restrict__ out,
                                    int* __restrict__ src_out) {
   extern __shared__ int sh[];  // [T] src index per position
-  __shared__ int s_any_image, s_start;
-  const int b = blockIdx.x;
-  if (threadIdx.x == 0) {
+  __shared__ int s_any_image, s_start, s_warp[16];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
     s_any_image = 0;
     s_start = 0;
   }
   __syncthreads();
   // any image token anywhere? (reference: mx.sum(image_positions) == 0 -> video ids)
   int local = 0;
-  for (int i = threadIdx.x; i < B * T; i += blockDim.x) local |= (ids[i] == image_token);
+  for (int i = tid; i < B * T; i += blockDim.x) local |= (ids[i] == image_token);
   if (local) atomicOr(&s_any_image, 1);
   __syncthreads();
   const int tok = s_any_image ? image_token : video_token;
   // features consumed by earlier rows
   int cnt = 0;
-  for (int i = threadIdx.x; i < b * T; i += blockDim.x) cnt += (ids[i] == tok);
+  for (int i = tid; i < b * T; i += blockDim.x) cnt += (ids[i] == tok);
   if (cnt) atomicAdd(&s_start, cnt);
+  // block scan of this row: thread i owns ids [i * per, (i + 1) * per)
+  const int per = (T + blockDim.x - 1) / blockDim.x;
+  const int t0 = min(tid * per, T), t1 = min(t0 + per, T);
+  int mine = 0;
+  for (int t = t0; t < t1; ++t) mine += (ids[b * T + t] == tok);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  // serial-in-chunks scan of this row (T is at most a few thousand)
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int t = 0; t < T; ++t) {
-      const bool m = ids[b * T + t] == tok;
-      run += m;
-      sh[t] = m ? (s_start + run - 1) : -1;
-    }
+  int before = incl - mine;
+  for (int w = 0; w < warp; ++w) before += s_warp[w];
+  int run = s_start + before;
+  for (int t = t0; t < t1; ++t) {
+    const bool m = ids[b * T + t] == tok;
+    sh[t] = m ? run : -1;
+    run += m;
   }
   __syncthreads();
   const int nvec = hidden >> 3;
-  for (long idx = threadIdx.x; idx < (long)T * nvec; idx += blockDim.x) {
-    const int t = (int)(idx / nvec), c = (int)(idx % nvec);
+  const int rows_per = (T + gridDim.x - 1) / gridDim.x;
+  const int r0 = min((int)blockIdx.x * rows_per, T), r1 = min(r0 + rows_per, T);
+  for (long idx = tid; idx < (long)(r1 - r0) * nvec; idx += blockDim.x) {
+    const int t = r0 + (int)(idx / nvec), c = (int)(idx % nvec);
     const int src = sh[t];
     const bf16* row;
     if (src >= 0) {
@@ -278,8 +293,8 @@ __global__ void embed_merge_kernel(const int* __restrict__ ids, int B, int T,
     *reinterpret_cast<uint4*>(out + ((long)b * T + t) * hidden + c * 8) =
         *reinterpret_cast<const uint4*>(row + c * 8);
   }
-  if (src_out)
-    for (int t = threadIdx.x; t < T; t += blockDim.x) src_out[b * T + t] = sh[t];
+  if (src_out && blockIdx.x == 0)
+    for (int t = tid; t < T; t += blockDim.x) src_out[b * T + t] = sh[t];
 }
 
 // ---------------------------------------------------------------------------
@@ -419,7 +434,10 @@ int embed_merge(const int* ids, int B, int T, const void* table, int hidden, con
     B200_CUDA(cudaFuncSetAttribute(embed_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    T * 4));
   }
-  embed_merge_kernel<<<B, 512, (size_t)T * 4, st>>>(ids, B, T, (const bf16*)table, hidden,
+  int per_row = (T + 7) / 8;  // >= 8 positions per CTA
+  const int cap_ctas = (2 * 148 + B - 1) / B;
+  if (per_row > cap_ctas) per_row = cap_ctas;
+  embed_merge_kernel<<<dim3(per_row, B), 512, (size_t)T * 4, st>>>(ids, B, T, (const bf16*)table, hidden,
                                                    (const bf16*)feats, n_feats, image_token,
                                                    video_token, (bf16*)out, src_out);
   B200_CHECK_LAUNCH();

@@ -90,6 +90,57 @@ __global__ void __launch_bounds__(256) f32_layer_norm_kernel(const float* __rest
   }
 }
 
+// RMSNorm in fp32 (nn.RMSNorm on fp32 rows, bf16-valued weight) -> fp32 and / or split output.  Input row
+// t is written to output row (t / seg_in) * seg_out + seg_off + t % seg_in: the Idefics2 perceiver
+// normalises the context and the latents separately and attends over their concatenation
+// (idefics2.py:60-90), so both norms write into ONE [context; latents] buffer per image.
+__global__ void __launch_bounds__(256) f32_rms_norm_kernel(const float* __restrict__ x, long ldx,
+                                                           const bf16* __restrict__ w, float eps,
+                                                           float* __restrict__ out32, long ld32,
+                                                           bf16* __restrict__ out_split, long ld_split, int n_pad,
+                                                           int N, int seg_in, int seg_out, int seg_off) {
+  __shared__ float red[8];
+  const int t = blockIdx.x;
+  const long ot = seg_in > 0 ? (long)(t / seg_in) * seg_out + seg_off + t % seg_in : t;
+  const int nv = N >> 2;
+  float4 h[8];
+  float s2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nv) {
+      h[u] = *reinterpret_cast<const float4*>(x + (long)t * ldx + c * 4);
+      s2 += (h[u].x * h[u].x + h[u].y * h[u].y) + (h[u].z * h[u].z + h[u].w * h[u].w);
+    }
+  }
+  const float rs = rsqrtf(t_block_sum(s2, red) / (float)N + eps);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = threadIdx.x + 256 * u;
+    if (c < nv) {
+      float wf[4];
+      unpack4(*reinterpret_cast<const uint2*>(w + c * 4), wf);
+      const float o0 = h[u].x * rs * wf[0], o1 = h[u].y * rs * wf[1], o2 = h[u].z * rs * wf[2], o3 = h[u].w * rs * wf[3];
+      if (out32) *reinterpret_cast<float4*>(out32 + ot * ld32 + c * 4) = make_float4(o0, o1, o2, o3);
+      if (out_split) split_store4(out_split + ot * ld_split + c * 4, n_pad, o0, o1, o2, o3);
+    }
+  }
+}
+
+// SwiGLU in fp32: gu [T, 2I] = [gate | up] -> split operand of silu(gate) * up (idefics2.py:146-171, mlp)
+__global__ void f32_swiglu_split_kernel(const float* __restrict__ gu, long ldg, bf16* __restrict__ out, long ld_split,
+                                        int n_pad, int T, int I) {
+  const int nv = I >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)T * nv; i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / nv), c = (int)(i % nv);
+    const float4 g = *reinterpret_cast<const float4*>(gu + (long)t * ldg + c * 4);
+    const float4 u = *reinterpret_cast<const float4*>(gu + (long)t * ldg + I + c * 4);
+    split_store4(out + (long)t * ld_split + c * 4, n_pad, g.x * sigmoid_f(g.x) * u.x, g.y * sigmoid_f(g.y) * u.y,
+                 g.z * sigmoid_f(g.z) * u.z, g.w * sigmoid_f(g.w) * u.w);
+  }
+}
+
 // fp32 [T, N] -> split operand [T, hi | lo] (zero padding columns are the caller's: buffers are zeroed once)
 __global__ void f32_split_kernel(const float* __restrict__ x, long ldx, bf16* __restrict__ out, long ld_split,
                                  int n_pad, int T, int N) {
@@ -270,6 +321,23 @@ int f32_layer_norm(const float* x, long ldx, const void* w, const void* b, float
   return B200_OK;
 }
 
+int f32_rms_norm(const float* x, long ldx, const void* w, float eps, float* out32, long ld32, void* out_split,
+                 long ld_split, int n_pad, int T, int N, int seg_in, int seg_out, int seg_off, cudaStream_t st) {
+  B200_REQUIRE(x && w && T > 0 && N > 0 && (N % 4) == 0 && N <= 8192 && (ldx % 4) == 0 && (out32 || out_split),
+               "f32_rms_norm: T=%d N=%d", T, N);
+  f32_rms_norm_kernel<<<T, 256, 0, st>>>(x, ldx, (const bf16*)w, eps, out32, ld32, (bf16*)out_split, ld_split, n_pad, N,
+                                         seg_in, seg_out, seg_off);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int f32_swiglu_split(const float* gu, long ldg, void* out, long ld_split, int n_pad, int T, int I, cudaStream_t st) {
+  B200_REQUIRE(gu && out && T > 0 && I > 0 && (I % 4) == 0 && (ldg % 4) == 0 && (ld_split % 4) == 0, "f32_swiglu: bad shape");
+  f32_swiglu_split_kernel<<<t_grid((long)T * (I / 4), 256), 256, 0, st>>>(gu, ldg, (bf16*)out, ld_split, n_pad, T, I);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 int f32_split(const float* x, long ldx, void* out, long ld_split, int n_pad, int T, int N, cudaStream_t st) {
   B200_REQUIRE(x && out && T > 0 && N > 0 && (N % 4) == 0 && (ldx % 4) == 0 && (ld_split % 4) == 0 && (n_pad % 4) == 0,
                "f32_split: bad shape");
@@ -332,6 +400,14 @@ extern "C" {
 int b200_f32_layer_norm(const float* x, long ldx, const void* w, const void* b, float eps, float* out32, long ld32,
                         void* out_split, long ld_split, int n_pad, int T, int N, void* st) {
   return f32_layer_norm(x, ldx, w, b, eps, out32, ld32, out_split, ld_split, n_pad, T, N, (cudaStream_t)st);
+}
+int b200_f32_rms_norm(const float* x, long ldx, const void* w, float eps, float* out32, long ld32, void* out_split,
+                      long ld_split, int n_pad, int T, int N, int seg_in, int seg_out, int seg_off, void* st) {
+  return f32_rms_norm(x, ldx, w, eps, out32, ld32, out_split, ld_split, n_pad, T, N, seg_in, seg_out, seg_off,
+                      (cudaStream_t)st);
+}
+int b200_f32_swiglu_split(const float* gu, long ldg, void* out, long ld_split, int n_pad, int T, int I, void* st) {
+  return f32_swiglu_split(gu, ldg, out, ld_split, n_pad, T, I, (cudaStream_t)st);
 }
 int b200_f32_split(const float* x, long ldx, void* out, long ld_split, int n_pad, int T, int N, void* st) {
   return f32_split(x, ldx, out, ld_split, n_pad, T, N, (cudaStream_t)st);

@@ -152,7 +152,8 @@ class Engine:
 
     def batch_logits_view(self, which: str = "logits") -> torch.Tensor:
         p = (self.lib.b200_batch_logits if which == "logits" else self.lib.b200_batch_logprobs)(self.h)
-        return self._view(p, self._batch_B * self.cfg.vocab, torch.bfloat16).view(self._batch_B, self.cfg.vocab)
+        ldv = (self.cfg.vocab + 7) // 8 * 8      # rows are padded to 16-byte multiples (tail = -inf)
+        return self._view(p, self._batch_B * ldv, torch.bfloat16).view(self._batch_B, ldv)[:, :self.cfg.vocab]
 
     BATCH_LOG_STEPS, BATCH_LOG_ROWS = 4096, 16
 

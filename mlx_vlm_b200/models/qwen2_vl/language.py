@@ -194,9 +194,10 @@ class LanguageModel:
             with torch.cuda.stream(eng.stream):
                 pos3 = pos3.to(eng.device, non_blocking=False)
             keep_all = logits_to_keep is None or logits_to_keep != 1
-            all_logits = eng.empty((L, V)) if keep_all else None
+            Vp = (V + 7) // 8 * 8     # device rows are 16-byte aligned for any vocabulary
+            all_logits = eng.empty((L, Vp)) if keep_all else None
             eng.prefill(emb.contiguous(), pos3, cache_offset, delta0, all_logits)
-            logits = (all_logits.view(1, L, V) if keep_all
+            logits = (all_logits[:, :V].unsqueeze(0) if keep_all
                       else eng.snapshot("logits").view(1, 1, V))
         for c in cache:
             c.offset += L

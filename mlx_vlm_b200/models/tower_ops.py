@@ -51,6 +51,20 @@ class TowerOps:
                                              out_split.ld if out_split else 0,
                                              out_split.n_pad if out_split else 0, T, n, self.eng.s), "f32_layer_norm")
 
+    def rms_norm(self, x: torch.Tensor, w, eps: float, out32: Optional[torch.Tensor] = None,
+                 out_split: Optional[SplitBuf] = None, seg_in: int = 0, seg_out: int = 0, seg_off: int = 0):
+        T, n = x.shape
+        N.check(self.lib.b200_f32_rms_norm(x.data_ptr(), x.stride(0), w.data_ptr(), float(eps), N.ptr(out32),
+                                           out32.stride(0) if out32 is not None else 0,
+                                           N.ptr(out_split.t) if out_split else 0, out_split.ld if out_split else 0,
+                                           out_split.n_pad if out_split else 0, T, n, seg_in, seg_out, seg_off,
+                                           self.eng.s), "f32_rms_norm")
+
+    def swiglu(self, gu: torch.Tensor, out: SplitBuf):
+        T = gu.shape[0]
+        N.check(self.lib.b200_f32_swiglu_split(gu.data_ptr(), gu.stride(0), out.t.data_ptr(), out.ld, out.n_pad, T,
+                                               out.n, self.eng.s), "f32_swiglu")
+
     def split(self, x: torch.Tensor, out: SplitBuf):
         T, n = x.shape
         N.check(self.lib.b200_f32_split(x.data_ptr(), x.stride(0), out.t.data_ptr(), out.ld, out.n_pad, T, n,

@@ -51,7 +51,7 @@ def _requests(c, req, n_rows, seed=3):
     return rows
 
 
-@pytest.mark.parametrize("kind", ["tiny", "wide2", "7b"])
+@pytest.mark.parametrize("kind", ["tiny", "wide2", "7b", "oddvocab"])
 def test_lock_step_rows_equal_single_requests(kind):
     from mlx_vlm_b200.generate_batch import BatchGenerator
     from oracle import qwen2vl as O

@@ -52,6 +52,10 @@ def _mk_cfg(kind):
         c.vision.hidden_size = 2048
         c.vision.depth = 1
         return c
+    if kind == "oddvocab":  # vocabulary that is not a multiple of 8 (Idefics2's is 32003)
+        c = O.tiny_cfg()
+        c.text.vocab_size += 3
+        return c
     if kind == "full":
         return O.qwen2_vl_2b()
     raise ValueError(kind)
