@@ -208,3 +208,35 @@ def test_fused_greedy_decode_hook_batched_and_cache_surgery():
     _same_until_tie(got[1], want[1][0][:len(got[1])], want[1][1], "row 1 before the filter")
     _same_until_tie(got[2], want[2][0][:len(got[2])], want[2][1], "row 2 across filter/extend")
     _same_until_tie(got3, want[3][0][:len(got3)], want[3][1], "row admitted by extend")
+
+
+def test_server_loop_streams_concurrent_requests():
+    """mlx_vlm_b200/server.py (reference server/generation.py:1730-1918) on the real engine: the GPU thread
+    owns the lock-step BatchGenerator; three caller threads stream their own request and must see the tokens
+    the request produces alone; the vision cache is filled on a miss and used on the repeat."""
+    import threading
+    from mlx_vlm_b200.server import GenerationArguments, ResponseGenerator
+    from mlx_vlm_b200.vision_cache import VisionFeatureCache
+    c, W, model, req = _build("tiny", 10, (56, 56))
+    rows = _requests(c, req, 3)
+    want = [_alone(model, r[0], r[1], r[2]) for r in rows]
+    model.config.eos_token_id = []
+    proc = types.SimpleNamespace(tokenizer=types.SimpleNamespace(stopping_criteria=None))
+    srv = ResponseGenerator(model, proc, max_num_seqs=4, decode_slice=2, vision_cache=VisionFeatureCache())
+    got = {}
+
+    def client(i):
+        ids, kw, n = rows[i]
+        raw = {"input_ids": ids, **kw}
+        got[i] = [e.token for e in srv.generate(raw, GenerationArguments(max_tokens=n), timeout=60)]
+
+    th = [threading.Thread(target=client, args=(i,)) for i in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(120)
+    srv.stop_and_join()
+    assert srv._error is None, srv._error
+    for i in range(3):
+        _same_until_tie(got[i], want[i][0], want[i][1], f"server request {i}")
+    assert model.engine.device_error() == 0
