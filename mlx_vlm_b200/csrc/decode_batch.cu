@@ -25,7 +25,7 @@ namespace b200 {
 
 namespace {
 
-constexpr int BD_AG = 4;  // q heads per attention CTA
+constexpr int BD_AG_MAX = 4;  // q heads per attention CTA: 4, 2 or 1 — the smallest that keeps the grid within one wave
 
 __device__ __forceinline__ void bd_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void bd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -92,11 +92,11 @@ struct BdAttnP {
   float scale_bf;
 };
 
-template <int HD>
+template <int HD, int AG>
 __global__ void __launch_bounds__(256) bd_attn_kernel(const BdAttnP p) {
   bd_pdl_launch();
   extern __shared__ __align__(16) uint8_t bd_sm[];
-  constexpr int NCH = HD / 8, AG = BD_AG, half = HD / 2;
+  constexpr int NCH = HD / 8, half = HD / 2;
   constexpr int SEG = HD / 8;   // dims per lane in the P.V phase (lane = key sub-index x dim segment)
   constexpr int NV = SEG / 8;   // 16-byte vectors per lane and key
   constexpr int VU = 8;         // key trips in flight per warp in the P.V phase (32 keys)
@@ -521,8 +521,26 @@ static int bd_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   return B200_OK;
 }
 
-static size_t bd_attn_smem(const DecodeDims& d) {
-  return ((size_t)(BD_AG + 2) * d.hd + (size_t)BD_AG * d.cap + (size_t)8 * BD_AG * d.hd) * 4;
+static size_t bd_attn_smem(const DecodeDims& d, int ag) {
+  return ((size_t)(ag + 2) * d.hd + (size_t)ag * d.cap + (size_t)8 * ag * d.hd) * 4;
+}
+
+// q heads per attention CTA: the latency chain of a CTA (partials -> rope -> keys -> softmax -> values) does not
+// shrink with fewer heads, its arithmetic does; so use as many CTAs as fit one wave of the SMs
+static int bd_attn_heads_per_cta(const DecodeDims& d, int B, int sm_count) {
+  const int Gall = d.n_heads / d.n_kv;
+  for (int ag : {1, 2, 4})
+    if ((long)d.n_kv * ((Gall + ag - 1) / ag) * B <= sm_count) return ag;
+  return BD_AG_MAX;
+}
+
+template <int HD>
+static int bd_attn_launch(int ag, dim3 grid, size_t smem, cudaStream_t s, const BdAttnP& ap) {
+  switch (ag) {
+    case 1: return bd_launch(bd_attn_kernel<HD, 1>, grid, dim3(256), smem, s, ap);
+    case 2: return bd_launch(bd_attn_kernel<HD, 2>, grid, dim3(256), smem, s, ap);
+    default: return bd_launch(bd_attn_kernel<HD, 4>, grid, dim3(256), smem, s, ap);
+  }
 }
 
 // one lock-step step as plain launches on `s` (also what gets captured)
@@ -532,7 +550,8 @@ static int bd_enqueue_step(BatchDecoder* d, const BdModel& m, cudaStream_t s, lo
   const int QH = dd.n_heads * dd.hd, QKV = (dd.n_heads + 2 * dd.n_kv) * dd.hd;
   int rc;
   const int Gall = dd.n_heads / dd.n_kv;
-  const int hs = (Gall + BD_AG - 1) / BD_AG;
+  const int ag_heads = bd_attn_heads_per_cta(dd, B, m.sm_count);
+  const int hs = (Gall + ag_heads - 1) / ag_heads;
   for (int l = 0; l < m.n_layers; ++l) {
     const LayerW& lw = m.layers[l];
     int split = 1;
@@ -545,8 +564,8 @@ static int bd_enqueue_step(BatchDecoder* d, const BdModel& m, cudaStream_t s, lo
     ap.row_stride = m.row_stride; ap.out = d->att; ap.n_heads = dd.n_heads; ap.n_kv = dd.n_kv; ap.cap = dd.cap;
     ap.hsplit = hs; ap.scale_bf = dd.scale_bf;
     const dim3 ag(dd.n_kv * hs, B);
-    if (dd.hd == 128) rc = bd_launch(bd_attn_kernel<128>, ag, dim3(256), bd_attn_smem(dd), s, ap);
-    else rc = bd_launch(bd_attn_kernel<64>, ag, dim3(256), bd_attn_smem(dd), s, ap);
+    if (dd.hd == 128) rc = bd_attn_launch<128>(ag_heads, ag, bd_attn_smem(dd, ag_heads), s, ap);
+    else rc = bd_attn_launch<64>(ag_heads, ag, bd_attn_smem(dd, ag_heads), s, ap);
     if (rc) return rc;
     if ((rc = gemm_wt_tuned(d->att, QH, lw.wo, nullptr, nullptr, 0, nullptr, 0, d->partial, d->partial_bytes, B, H, QH,
                             B200_EPI_NONE, B200_WT_PARTIAL, 0, true, m.sm_count, &split, s)))
@@ -584,7 +603,7 @@ int batch_decoder_begin(void** handle, const BdModel& m, int B, const int* tok, 
   B200_REQUIRE(B >= 1 && B <= 16, "batch decode: B=%d (1..16)", B);
   B200_REQUIRE(m.d.hd == 64 || m.d.hd == 128, "batch decode: head_dim %d (64|128)", m.d.hd);
   B200_REQUIRE(B <= m.kv_batch, "batch decode: B=%d > KV pool rows %d", B, m.kv_batch);
-  B200_REQUIRE(bd_attn_smem(m.d) <= 200 * 1024, "batch decode: cache capacity %d too large for the attention kernel", m.d.cap);
+  B200_REQUIRE(bd_attn_smem(m.d, BD_AG_MAX) <= 200 * 1024, "batch decode: cache capacity %d too large for the attention kernel", m.d.cap);
   BatchDecoder* d = reinterpret_cast<BatchDecoder*>(*handle);
   if (!d) {
     d = new BatchDecoder();
@@ -596,8 +615,12 @@ int batch_decoder_begin(void** handle, const BdModel& m, int B, const int* tok, 
     *handle = d;
     static bool attr = false;
     if (!attr) {
-      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr = true;
     }
   }

@@ -821,6 +821,14 @@ struct TuneHash {
   }
 };
 
+// B200_WT_TUNE_FILE=<path>: measured choices are appended to the file and read back at the first call of a
+// later process, so a service does not re-measure at every start and a profiler run (whose serialised
+// replays distort the measurement) uses exactly the production configurations.
+static const char* tune_file() {
+  static const char* f = getenv("B200_WT_TUNE_FILE");
+  return (f && *f) ? f : nullptr;
+}
+
 static int tune_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -845,6 +853,19 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
   bool have = false;
   {
     std::lock_guard<std::mutex> g(mu);
+    static bool file_read = false;
+    if (!file_read) {
+      file_read = true;
+      if (const char* path = tune_file()) {
+        if (FILE* fp = fopen(path, "r")) {
+          int tb, n, k, md, so, tn, ks, stg, sp;
+          while (fscanf(fp, "%d %d %d %d %d %d %d %d %d", &tb, &n, &k, &md, &so, &tn, &ks, &stg, &sp) == 9)
+            if (tn >= 16 && tn <= 256 && tn % 16 == 0 && ks >= 1 && stg >= 2 && stg <= WT_MAX_STAGES && sp >= 1)
+              cache[TuneKey{tb, n, k, md, so, dev}] = WtConfig{tn, ks, stg, sp};
+          fclose(fp);
+        }
+      }
+    }
     auto it = cache.find(key);
     if (it != cache.end()) {
       cfg = it->second;
@@ -983,6 +1004,13 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
               T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, ms[pick] * 1000.f, cand.size());
     std::lock_guard<std::mutex> g(mu);
     cache[key] = cfg;
+    if (const char* path = tune_file()) {
+      if (FILE* fp = fopen(path, "a")) {
+        fprintf(fp, "%d %d %d %d %d %d %d %d %d\n", key.tb, key.N, key.K, key.mode, key.split_ok, cfg.TN, cfg.KS,
+                cfg.stages, cfg.split);
+        fclose(fp);
+      }
+    }
   }
   // a cached configuration was tuned for a token count in the same 64-bucket: re-check the bounds
   if (cfg.TN > round16(T)) cfg.TN = round16(T);

@@ -208,7 +208,15 @@ __global__ void tower_embed_kernel(const float* __restrict__ patch, const bf16* 
 }
 
 // ---- fp32 attention on the CUDA cores (exact fp32 softmax; flash-style running max / sum) -----------
-// CTA = 64 query rows of one head of one segment; 4 threads per row, each owns HD/4 dims of q and o.
+// Register-tiled: CTA = 128 query rows of one head of one segment, 256 threads as 16 (query groups of 8 rows) x
+// 16 (key groups of 4 keys / dim lanes).  Per 64-key tile:
+//   S[8 x 4] per thread = Q^T . K^T out of shared memory (both stored dim-major so that a thread's 8 queries /
+//   4 keys are one or two 16-byte loads and the 16 lanes of a key group read 256 contiguous bytes: 32 FMAs per
+//   3 shared loads), running max over the 16 lanes of a query group (4 shuffles per row), p = exp(s - m) written
+//   as P^T[key][query] (only the half-warp that owns the rows reads it back: __syncwarp), then
+//   O[8 x HDP/16] += P . V with the thread's dims interleaved (dim = e * 16 + lane: conflict-free, coalesced stores).
+// The round-1 version of this kernel (4 threads per row, 1 FMA per shared load) ran at ~6 TFLOP/s and was 88 % of the
+// CLIP tower's time; this one is bounded by the FMA pipe.
 struct AttnF32P {
   const float *q, *k, *v;
   long q_ts, q_hs, k_ts, k_hs, v_ts, v_hs;  // element strides: token, head
@@ -217,89 +225,173 @@ struct AttnF32P {
   bf16* out_split;
   long os_ts;
   int n_pad;
-  int n_heads, n_kv, Lq, S;
+  int n_heads, n_kv, Lq, S, hd;
   long q_seg, k_seg;   // tokens between consecutive segments (blockIdx.z)
   const unsigned char* key_mask;  // optional [segments][S]: 0 = key masked out
   float scale;
 };
 
-template <int HD>
+constexpr int AF_BQ = 128, AF_BK = 64, AF_PP = AF_BQ + 4;  // P^T row pitch: +4 floats -> conflict-free 16-byte stores
+
+template <int HDP>
+static constexpr size_t attn_f32_smem() {
+  return ((size_t)HDP * AF_BQ + (size_t)HDP * AF_BK + (size_t)AF_BK * HDP + (size_t)AF_BK * AF_PP) * 4 + AF_BK;
+}
+
+template <int HDP>
 __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
-  constexpr int DQ = HD / 4;     // dims per thread
-  constexpr int TK = HD > 80 ? 32 : 64;  // keys per tile (static shared memory <= 48 KB)
-  __shared__ __align__(16) float Ks[TK][HD];
-  __shared__ __align__(16) float Vs[TK][HD];
-  __shared__ unsigned char Ms[TK];
-  const int row = threadIdx.x >> 2, sub = threadIdx.x & 3;
+  constexpr int BQ = AF_BQ, BK = AF_BK, PP = AF_PP, DPT = HDP / 16;
+  extern __shared__ __align__(16) float af_sm[];
+  float* Qt = af_sm;               // [HDP][BQ]  q * scale, dim-major
+  float* Kt = Qt + HDP * BQ;       // [HDP][BK]
+  float* Vs = Kt + HDP * BK;       // [BK][HDP]
+  float* Pt = Vs + BK * HDP;       // [BK][PP]
+  unsigned char* Ms = reinterpret_cast<unsigned char*>(Pt + BK * PP);  // [BK] 1 = key takes part
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int h = blockIdx.y, kvh = h / (p.n_heads / p.n_kv), seg = blockIdx.z;
-  const int qi = blockIdx.x * 64 + row;
+  const int q0 = blockIdx.x * BQ;
+  const int hd = p.hd, hd4 = hd >> 2;
   const float* qb = p.q + (long)seg * p.q_seg * p.q_ts + (long)h * p.q_hs;
   const float* kb = p.k + (long)seg * p.k_seg * p.k_ts + (long)kvh * p.k_hs;
   const float* vb = p.v + (long)seg * p.k_seg * p.v_ts + (long)kvh * p.v_hs;
-  float q[DQ], o[DQ];
-#pragma unroll
-  for (int i = 0; i < DQ; ++i) {
-    q[i] = (qi < p.Lq) ? qb[(long)qi * p.q_ts + sub * DQ + i] * p.scale : 0.f;
-    o[i] = 0.f;
+  // Q^T: lane <-> query row (conflict-free transposed stores)
+  for (int i = tid; i < BQ * (HDP / 4); i += 256) {
+    const int r = i % BQ, c = i / BQ;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < p.Lq && c < hd4) v = *reinterpret_cast<const float4*>(qb + (long)(q0 + r) * p.q_ts + c * 4);
+    Qt[(c * 4 + 0) * BQ + r] = v.x * p.scale;
+    Qt[(c * 4 + 1) * BQ + r] = v.y * p.scale;
+    Qt[(c * 4 + 2) * BQ + r] = v.z * p.scale;
+    Qt[(c * 4 + 3) * BQ + r] = v.w * p.scale;
   }
-  float m = -INFINITY, l = 0.f;
-  for (int j0 = 0; j0 < p.S; j0 += TK) {
+  float o[8][DPT], m[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m[i] = -INFINITY;
+    l[i] = 0.f;
+#pragma unroll
+    for (int e = 0; e < DPT; ++e) o[i][e] = 0.f;
+  }
+  for (int j0 = 0; j0 < p.S; j0 += BK) {
     __syncthreads();
-    for (int i = threadIdx.x; i < TK * (HD / 4); i += 256) {
-      const int kr = i / (HD / 4), c = i % (HD / 4);
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (j0 + kr < p.S) {
-        kv = *reinterpret_cast<const float4*>(kb + (long)(j0 + kr) * p.k_ts + c * 4);
-        vv = *reinterpret_cast<const float4*>(vb + (long)(j0 + kr) * p.v_ts + c * 4);
-      }
-      *reinterpret_cast<float4*>(&Ks[kr][c * 4]) = kv;
-      *reinterpret_cast<float4*>(&Vs[kr][c * 4]) = vv;
+    for (int i = tid; i < BK * (HDP / 4); i += 256) {   // K^T: lane <-> key
+      const int r = i % BK, c = i / BK;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + r < p.S && c < hd4) v = *reinterpret_cast<const float4*>(kb + (long)(j0 + r) * p.k_ts + c * 4);
+      Kt[(c * 4 + 0) * BK + r] = v.x;
+      Kt[(c * 4 + 1) * BK + r] = v.y;
+      Kt[(c * 4 + 2) * BK + r] = v.z;
+      Kt[(c * 4 + 3) * BK + r] = v.w;
     }
-    if (threadIdx.x < TK)
-      Ms[threadIdx.x] = (j0 + threadIdx.x < p.S) &&
-                        (!p.key_mask || p.key_mask[(long)seg * p.S + j0 + threadIdx.x]);
+    for (int i = tid; i < BK * (HDP / 4); i += 256) {   // V: row-major
+      const int r = i / (HDP / 4), c = i % (HDP / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + r < p.S && c < hd4) v = *reinterpret_cast<const float4*>(vb + (long)(j0 + r) * p.v_ts + c * 4);
+      *reinterpret_cast<float4*>(Vs + r * HDP + c * 4) = v;
+    }
+    if (tid < BK) Ms[tid] = (j0 + tid < p.S) && (!p.key_mask || p.key_mask[(long)seg * p.S + j0 + tid]);
     __syncthreads();
-#pragma unroll 2
-    for (int kk = 0; kk < TK; ++kk) {
-      float s = 0.f;
+    // ---- S = Q . K^T for this thread's 8 rows x 4 keys ----
+    float s[8][4];
 #pragma unroll
-      for (int i = 0; i < DQ; ++i) s = fmaf(q[i], Ks[kk][sub * DQ + i], s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (!Ms[kk]) continue;   // uniform across the 4 threads of a row (and the warp: same key)
-      if (s > m) {             // rescale the running sum / output (rare after the first keys)
-        const float f = __expf(m - s);
-        l *= f;
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int i = 0; i < DQ; ++i) o[i] *= f;
-        m = s;
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < HDP; ++d) {
+      const float4 qa = *reinterpret_cast<const float4*>(Qt + d * BQ + ty * 8);
+      const float4 qc = *reinterpret_cast<const float4*>(Qt + d * BQ + ty * 8 + 4);
+      const float4 kk = *reinterpret_cast<const float4*>(Kt + d * BK + tx * 4);
+      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qc.x, qc.y, qc.z, qc.w};
+      const float kv[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qv[i], kv[j], s[i][j]);
+    }
+    bool on[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) on[j] = Ms[tx * 4 + j] != 0;
+    // ---- running max / sum, p -> P^T ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mx = on[j] ? fmaxf(mx, s[i][j]) : mx;
+#pragma unroll
+      for (int w = 1; w < 16; w <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, w));
+      const float mn = fmaxf(m[i], mx);
+      const float f = (mn == -INFINITY) ? 1.f : __expf(m[i] - mn);   // nothing seen yet: keep zeros
+      m[i] = mn;
+      l[i] *= f;
+#pragma unroll
+      for (int e = 0; e < DPT; ++e) o[i][e] *= f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pj = on[j] ? __expf(s[i][j] - mn) : 0.f;
+        s[i][j] = pj;
+        l[i] += pj;   // this thread's share of the row sum (reduced over the 16 lanes at the end)
       }
-      const float pj = __expf(s - m);
-      l += pj;
+    }
 #pragma unroll
-      for (int i = 0; i < DQ; ++i) o[i] = fmaf(pj, Vs[kk][sub * DQ + i], o[i]);
+    for (int j = 0; j < 4; ++j) {
+      float* dst = Pt + (tx * 4 + j) * PP + ty * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4][j], s[5][j], s[6][j], s[7][j]);
+    }
+    __syncwarp();   // rows ty*8.. of P^T are written and read by the same half-warp only
+    // ---- O += P . V ----
+#pragma unroll 4
+    for (int j = 0; j < BK; ++j) {
+      const float4 pa = *reinterpret_cast<const float4*>(Pt + j * PP + ty * 8);
+      const float4 pc = *reinterpret_cast<const float4*>(Pt + j * PP + ty * 8 + 4);
+      const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pc.x, pc.y, pc.z, pc.w};
+      float vv[DPT];
+#pragma unroll
+      for (int e = 0; e < DPT; ++e) vv[e] = Vs[j * HDP + e * 16 + tx];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int e = 0; e < DPT; ++e) o[i][e] = fmaf(pv[i], vv[e], o[i][e]);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float ls = l[i];
+#pragma unroll
+    for (int w = 1; w < 16; w <<= 1) ls += __shfl_xor_sync(0xffffffffu, ls, w);
+    const int qi = q0 + ty * 8 + i;
+    if (qi >= p.Lq) continue;
+    const float inv = 1.0f / ls;
+    const long t = (long)seg * p.q_seg + qi;
+#pragma unroll
+    for (int e = 0; e < DPT; ++e) {
+      const int d = e * 16 + tx;
+      if (d >= hd) continue;
+      const float a = o[i][e] * inv;
+      const long col = (long)h * hd + d;
+      if (p.out32) p.out32[t * p.o_ts + col] = a;
+      if (p.out_split) {
+        const float hi = rbf(a);
+        p.out_split[t * p.os_ts + col] = f2bf(hi);
+        p.out_split[t * p.os_ts + col + p.n_pad] = f2bf(a - hi);
+      }
     }
   }
-  if (qi >= p.Lq) return;
-  const float inv = 1.0f / l;
-  const long t = (long)seg * p.q_seg + qi;
-  if constexpr (DQ % 4 == 0) {
-#pragma unroll
-    for (int i = 0; i < DQ; i += 4) {
-      const float a = o[i] * inv, b = o[i + 1] * inv, c = o[i + 2] * inv, d = o[i + 3] * inv;
-      const int col = h * HD + sub * DQ + i;
-      if (p.out32) *reinterpret_cast<float4*>(p.out32 + t * p.o_ts + col) = make_float4(a, b, c, d);
-      if (p.out_split) split_store4(p.out_split + t * p.os_ts + col, p.n_pad, a, b, c, d);
-    }
-  } else {  // head_dim 72: 18 dims per thread
-#pragma unroll
-    for (int i = 0; i < DQ; i += 2) {
-      const float a = o[i] * inv, b = o[i + 1] * inv;
-      const int col = h * HD + sub * DQ + i;
-      if (p.out32) *reinterpret_cast<float2*>(p.out32 + t * p.o_ts + col) = make_float2(a, b);
-      if (p.out_split) split_store2(p.out_split + t * p.os_ts + col, p.n_pad, a, b);
-    }
+}
+
+template <int HDP>
+static int attn_f32_launch(const AttnF32P& p, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;   // one device kind per process (sm_100a only)
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(attention_f32_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)attn_f32_smem<HDP>()));
+    attr_set = true;
   }
+  attention_f32_kernel<HDP><<<grid, 256, attn_f32_smem<HDP>(), st>>>(p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
 }
 
 static inline int t_grid(long work, int block) {
@@ -379,18 +471,14 @@ int attention_f32(const float* q, long q_ts, long q_hs, const float* k, long k_t
   p.out32 = out32; p.o_ts = o_ts; p.out_split = (bf16*)out_split; p.os_ts = os_ts; p.n_pad = n_pad;
   p.n_heads = n_heads; p.n_kv = n_kv; p.Lq = Lq; p.S = S; p.q_seg = q_seg; p.k_seg = k_seg; p.key_mask = key_mask;
   p.scale = scale;
-  const dim3 grid(cdiv(Lq, 64), n_heads, n_seg);
-  if (hd == 64) attention_f32_kernel<64><<<grid, 256, 0, st>>>(p);
-  else if (hd == 72) attention_f32_kernel<72><<<grid, 256, 0, st>>>(p);   // SigLIP-SO400M (padded: see below)
-  else if (hd == 96) attention_f32_kernel<96><<<grid, 256, 0, st>>>(p);   // Idefics2 perceiver
-  else if (hd == 16) attention_f32_kernel<16><<<grid, 256, 0, st>>>(p);   // tiny test configurations
-  else if (hd == 32) attention_f32_kernel<32><<<grid, 256, 0, st>>>(p);
-  else {
-    set_error("attention_f32: head_dim %d (16|32|64|72|96)", hd);
-    return B200_ERR_INVALID;
-  }
-  B200_CHECK_LAUNCH();
-  return B200_OK;
+  p.hd = hd;
+  B200_REQUIRE((hd % 4) == 0 && hd <= 96, "attention_f32: head_dim %d (multiple of 4, <= 96)", hd);
+  const dim3 grid(cdiv(Lq, AF_BQ), n_heads, n_seg);
+  if (hd <= 16) return attn_f32_launch<16>(p, grid, st);
+  if (hd <= 32) return attn_f32_launch<32>(p, grid, st);
+  if (hd <= 64) return attn_f32_launch<64>(p, grid, st);   // CLIP-L
+  if (hd <= 80) return attn_f32_launch<80>(p, grid, st);   // SigLIP-SO400M: 72 dims, padded with zeros
+  return attn_f32_launch<96>(p, grid, st);                 // Idefics2 perceiver
 }
 
 }  // namespace b200
