@@ -81,7 +81,10 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- activation restatements (oracle/mlx_semantics.py) --------------------
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + e^-x) with the SFU exponential and reciprocal (branch-free, ~3 ulp): far below the bf16 rounding every
+// bf16 caller applies next and below the 2^-17 of the split-operand GEMMs on the fp32 paths (the libm expf + IEEE
+// division version has a slow-path branch per element and cost ~9 us per GEMM epilogue)
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // nn.silu(g) * u : three roundings
 __device__ __forceinline__ float swiglu_bf(float g, float u) {
   float s = rbf(g * rbf(sigmoid_f(g)));

@@ -159,7 +159,9 @@ int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int*
                    cudaStream_t st, float q_scale = 0.f, void* vt = nullptr, int t_ld = 0,
                    const KvRef* ref = nullptr, int layer = 0, void* kws = nullptr);
 int vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads, int hd,
-                    float scale, void* vt, int t_ld, cudaStream_t st);
+                    float scale, void* vt, int t_ld, cudaStream_t st, const void* cs = nullptr);
+// cos / sin table [n_tok][hd / 2] float2 for vision_qkv_post (computed once per tower call)
+int vision_rope_table(const int* pos_hw, const float* inv_freq, int n_tok, int hd, void* cs, cudaStream_t st);
 bool attention_fa_supported(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
                             const void* vt, long vt_hs, long vt_ds, const void* out, long o_ts, int hd);
 int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs, const void* vt,

@@ -516,12 +516,19 @@ static int vision_v2_body(b200_engine* e, const float* pixel_values, const int* 
   if ((rc = layer_norm(h, e->vblk[0].ln1w, e->vblk[0].ln1b, y, (int)N, (int)E, c.v_ln_eps, s))) return rc;
   e->launches += 2;
   const float scale = 1.0f / sqrtf((float)hd);
+  // the patch input `x` is dead after the patch-embed GEMM: its workspace holds the rotary cos / sin table
+  void* rope_cs = nullptr;
+  if ((long)N * (hd / 2) * 8 <= N * (long)c.v_patch_dim * 2) {
+    rope_cs = x;
+    if ((rc = vision_rope_table(e->pos_hw, e->v_inv_freq, (int)N, hd, rope_cs, s))) return rc;
+    e->launches += 1;
+  }
   const bool fa = attention_fa_supported(qkv, 3 * E, hd, qkv + E, 3 * E, hd, vt, (long)hd * t_ld, t_ld, att, E, hd);
   for (int i = 0; i < c.v_depth; ++i) {
     const VBlk& b = e->vblk[i];
     if ((rc = v2_linear(e, y, E, b.qkvw, b.qkvb, qkv, 3 * E, (int)N, (int)(3 * E), (int)E, B200_EPI_NONE, s))) return rc;
     if (fa) {
-      if ((rc = vision_qkv_post(qkv, e->pos_hw, e->v_inv_freq, (int)N, nh, hd, scale, vt, t_ld, s))) return rc;
+      if ((rc = vision_qkv_post(qkv, e->pos_hw, e->v_inv_freq, (int)N, nh, hd, scale, vt, t_ld, s, rope_cs))) return rc;
     } else {
       if ((rc = vision_rope(qkv, e->pos_hw, e->v_inv_freq, (int)N, nh, hd, s))) return rc;
     }

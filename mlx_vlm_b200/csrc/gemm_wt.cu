@@ -147,6 +147,37 @@ __device__ __forceinline__ void w_pdl_launch() { asm volatile("griddepcontrol.la
 __device__ __forceinline__ void w_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void w_ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// TMEM registers of one lane (weight row) -> bf16 staging tile [token][row]: + bias, one rounding, activation
+template <int EPI>
+__device__ __forceinline__ void wt_stage_bf16(const uint32_t (&a)[32], float bias_v, bf16* sb) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float v = rbf(__uint_as_float(a[j]) + bias_v);
+    if constexpr (EPI == B200_EPI_GELU_FAST) v = gelu_fast_bf(v);
+    if constexpr (EPI == B200_EPI_GELU_EXACT) v = gelu_exact_bf(v);
+    sb[j * WT_ROWS] = f2bf(v);
+  }
+}
+
+// the fp32-accurate paths: no rounding anywhere
+template <int EPI>
+__device__ __forceinline__ void wt_stage_f32(const uint32_t (&a)[32], float bias_v, float* sf) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float v = __uint_as_float(a[j]) + bias_v;
+    if constexpr (EPI == B200_EPI_GELU_FAST) v = v * sigmoid_f(1.702f * v);
+    if constexpr (EPI == B200_EPI_GELU_EXACT) v = v * (1.0f + erff(v / 1.41421356237309515f)) * 0.5f;
+    if constexpr (EPI == B200_EPI_GELU_TANH) {
+      const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+      v = 0.5f * v * (1.0f + tanhf(u));
+    }
+    sf[j * WT_ROWS] = v;
+  }
+}
+
+// TOWER = false: the bf16 paths (B200_WT_BF16 / PARTIAL / SWIGLU); TOWER = true: the fp32-accurate paths
+// (B200_WT_F32 / SPLIT).  Two instantiations keep each one's code small (tools/wt_ab_probe.py A/B-times builds).
+template <bool TOWER>
 __global__ void __launch_bounds__(256, 2)
 gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                const WtParams p) {
@@ -157,7 +188,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wt_smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool swiglu = (p.mode == B200_WT_SWIGLU);
+  const bool swiglu = !TOWER && (p.mode == B200_WT_SWIGLU);
   const int rb = blockIdx.x;
   const int n0 = rb * (swiglu ? 64 : WT_ROWS);  // first output feature (SwiGLU: channel) of the tile
   const int t0 = blockIdx.y * p.TN;
@@ -275,8 +306,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;  // weight row of the tile == TMEM lane
   float bias_v = 0.f;
-  if ((p.mode == B200_WT_BF16 || p.mode == B200_WT_F32 || p.mode == B200_WT_SPLIT) && p.bias && n0 + row < p.N)
-    bias_v = bf2f(p.bias[n0 + row]);
+  if ((TOWER || p.mode == B200_WT_BF16) && p.bias && n0 + row < p.N) bias_v = bf2f(p.bias[n0 + row]);
   uint8_t* stg = ring;  // every TMA load has landed and every MMA has retired: the ring is free
   const int tid = threadIdx.x;
   for (int c0 = 0; c0 < p.TN; c0 += WT_EPI_TOK) {
@@ -284,37 +314,28 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (cc < p.TN && !(p.flags & 1u)) {
       uint32_t a[32];
       w_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, a);
-      if (p.mode == B200_WT_PARTIAL) {
+      if (!TOWER && p.mode == B200_WT_PARTIAL) {
         float* sf = reinterpret_cast<float*>(stg);
 #pragma unroll
         for (int j = 0; j < 32; ++j) sf[(half * 32 + j) * WT_ROWS + row] = __uint_as_float(a[j]);
-      } else if (p.mode == B200_WT_F32 || p.mode == B200_WT_SPLIT) {
-        float* sf = reinterpret_cast<float*>(stg);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = __uint_as_float(a[j]) + bias_v;   // fp32 semantics: no rounding anywhere
-          if (p.epilogue == B200_EPI_GELU_FAST) v = v * sigmoid_f(1.702f * v);
-          else if (p.epilogue == B200_EPI_GELU_EXACT) v = v * (1.0f + erff(v / 1.41421356237309515f)) * 0.5f;
-          else if (p.epilogue == B200_EPI_GELU_TANH) {
-            const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
-            v = 0.5f * v * (1.0f + tanhf(u));
-          }
-          sf[(half * 32 + j) * WT_ROWS + row] = v;
-        }
+      } else if constexpr (TOWER) {
+        float* sf = reinterpret_cast<float*>(stg) + (half * 32) * WT_ROWS + row;
+        if (p.epilogue == B200_EPI_GELU_FAST) wt_stage_f32<B200_EPI_GELU_FAST>(a, bias_v, sf);
+        else if (p.epilogue == B200_EPI_GELU_EXACT) wt_stage_f32<B200_EPI_GELU_EXACT>(a, bias_v, sf);
+        else if (p.epilogue == B200_EPI_GELU_TANH) wt_stage_f32<B200_EPI_GELU_TANH>(a, bias_v, sf);
+        else wt_stage_f32<B200_EPI_NONE>(a, bias_v, sf);
       } else {
-        bf16* sb = reinterpret_cast<bf16*>(stg);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = rbf(__uint_as_float(a[j]) + bias_v);
-          if (p.epilogue == B200_EPI_GELU_FAST) v = gelu_fast_bf(v);
-          else if (p.epilogue == B200_EPI_GELU_EXACT) v = gelu_exact_bf(v);
-          sb[(half * 32 + j) * WT_ROWS + row] = f2bf(v);
-        }
+        // one unrolled loop per epilogue kind, chosen OUTSIDE the loop: left to itself the compiler merged the
+        // three kinds into one predicated body of ~90 instructions per element (6-7 us per launch, A/B measured)
+        bf16* sb = reinterpret_cast<bf16*>(stg) + (half * 32) * WT_ROWS + row;
+        if (p.epilogue == B200_EPI_GELU_FAST) wt_stage_bf16<B200_EPI_GELU_FAST>(a, bias_v, sb);
+        else if (p.epilogue == B200_EPI_GELU_EXACT) wt_stage_bf16<B200_EPI_GELU_EXACT>(a, bias_v, sb);
+        else wt_stage_bf16<B200_EPI_NONE>(a, bias_v, sb);
       }
     }
     w_ebar();
     if (!(p.flags & 4u)) {
-      if (p.mode == B200_WT_BF16) {
+      if (!TOWER && p.mode == B200_WT_BF16) {
         const bool vec_all = ((p.ldc & 7) == 0) && (!p.residual || (p.ldr & 7) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
@@ -347,7 +368,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
           }
         }
-      } else if (p.mode == B200_WT_SWIGLU) {
+      } else if (!TOWER && p.mode == B200_WT_SWIGLU) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int idx = tid + 256 * u;
@@ -363,7 +384,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           ov.x = pack2(o[0], o[1]); ov.y = pack2(o[2], o[3]); ov.z = pack2(o[4], o[5]); ov.w = pack2(o[6], o[7]);
           *reinterpret_cast<uint4*>(p.C + (long)t * p.ldc + i) = ov;
         }
-      } else if (p.mode == B200_WT_F32 || p.mode == B200_WT_SPLIT) {
+      } else if constexpr (TOWER) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int idx = tid + 256 * u;
@@ -777,8 +798,11 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   if (!(set_mask >> (dev & 63) & 1ull)) {
-    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    B200_CUDA(cudaFuncSetAttribute(gemm_wt_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
     set_mask |= 1ull << (dev & 63);
   }
@@ -793,7 +817,11 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = g_wt_pdl ? 1 : 0;
-  B200_CUDA(cudaLaunchKernelEx(&lc, gemm_wt_kernel, tw, tx, p));
+  if (mode == B200_WT_F32 || mode == B200_WT_SPLIT) {
+    B200_CUDA(cudaLaunchKernelEx(&lc, gemm_wt_kernel<true>, tw, tx, p));
+  } else {
+    B200_CUDA(cudaLaunchKernelEx(&lc, gemm_wt_kernel<false>, tw, tx, p));
+  }
   return B200_OK;
 }
 

@@ -358,32 +358,85 @@ int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int*
 // TRANSPOSED ([head][dim][token], tokens contiguous) through a shared-memory tile: the
 // pipelined attention kernel loads Q, K and V^T with TMA and touches no operand with a thread.
 // grid (ceil(T / 32), heads), 256 threads.
+__global__ void vision_rope_table_kernel(const int* __restrict__ pos_hw, const float* __restrict__ inv_freq, int T,
+                                        int half, float2* __restrict__ cs) {
+  pdl_prologue();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * half) return;
+  const int t = idx / half, j = idx % half, quarter = half >> 1;
+  const int axis = (j < quarter) ? 0 : 1;
+  const float ang = (float)pos_hw[t * 2 + axis] * inv_freq[j - axis * quarter];
+  cs[idx] = make_float2(cosf(ang), sinf(ang));
+}
+
+// `cs` (optional): cos / sin of every (token, rotary pair), computed once per tower call by
+// vision_rope_table_kernel — the angles are the same for all heads and all 32 blocks.
 __global__ void vision_qkv_post_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos_hw,
                                        const float* __restrict__ inv_freq, int T, int n_heads, int hd,
-                                       float scale_bf, bf16* __restrict__ vt, int t_ld) {
+                                       float scale_bf, bf16* __restrict__ vt, int t_ld,
+                                       const float2* __restrict__ cs) {
   pdl_prologue();
   __shared__ bf16 tile[32][136];
   const int t0 = blockIdx.x * 32, h = blockIdx.y;
   const int half = hd >> 1, quarter = hd >> 2;
   const long row = 3L * n_heads * hd;
-  for (int idx = threadIdx.x; idx < 32 * 2 * half; idx += blockDim.x) {
-    const int j = idx % half;
-    const int r = idx / half;
-    const int which = r & 1, t = t0 + (r >> 1);
-    if (t >= T) continue;
-    const int axis = (j < quarter) ? 0 : 1;
-    const float ang = (float)pos_hw[t * 2 + axis] * inv_freq[j - axis * quarter];
-    const float c = cosf(ang), sn = sinf(ang);
-    bf16* base = qkv + (long)t * row + ((long)which * n_heads + h) * hd;
-    const float x1 = bf2f(base[j]), x2 = bf2f(base[j + half]);
-    float o1 = rbf(__fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, sn)));
-    float o2 = rbf(__fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, sn)));
-    if (which == 0) {
-      o1 *= scale_bf;
-      o2 *= scale_bf;
+  if ((half & 7) == 0) {   // 8 rotary pairs per thread: two 16-byte loads, two 16-byte stores
+    const int nc = half >> 3;
+    for (int idx = threadIdx.x; idx < 32 * 2 * nc; idx += blockDim.x) {
+      const int c = idx % nc, r = idx / nc;
+      const int which = r & 1, t = t0 + (r >> 1);
+      if (t >= T) continue;
+      bf16* base = qkv + (long)t * row + ((long)which * n_heads + h) * hd;
+      float x1[8], x2[8], o1[8], o2[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + c * 8), x1);
+      unpack8(*reinterpret_cast<const uint4*>(base + half + c * 8), x2);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = c * 8 + u;
+        float cv, sv;
+        if (cs) {
+          const float2 f = __ldg(cs + (long)t * half + j);
+          cv = f.x;
+          sv = f.y;
+        } else {
+          const int axis = (j < quarter) ? 0 : 1;
+          const float ang = (float)pos_hw[t * 2 + axis] * inv_freq[j - axis * quarter];
+          cv = cosf(ang);
+          sv = sinf(ang);
+        }
+        o1[u] = rbf(__fadd_rn(__fmul_rn(x1[u], cv), __fmul_rn(-x2[u], sv)));
+        o2[u] = rbf(__fadd_rn(__fmul_rn(x2[u], cv), __fmul_rn(x1[u], sv)));
+        if (which == 0) {
+          o1[u] *= scale_bf;
+          o2[u] *= scale_bf;
+        }
+      }
+      uint4 w1, w2;
+      w1.x = pack2(o1[0], o1[1]); w1.y = pack2(o1[2], o1[3]); w1.z = pack2(o1[4], o1[5]); w1.w = pack2(o1[6], o1[7]);
+      w2.x = pack2(o2[0], o2[1]); w2.y = pack2(o2[2], o2[3]); w2.z = pack2(o2[4], o2[5]); w2.w = pack2(o2[6], o2[7]);
+      *reinterpret_cast<uint4*>(base + c * 8) = w1;
+      *reinterpret_cast<uint4*>(base + half + c * 8) = w2;
     }
-    base[j] = f2bf(o1);
-    base[j + half] = f2bf(o2);
+  } else {
+    for (int idx = threadIdx.x; idx < 32 * 2 * half; idx += blockDim.x) {
+      const int j = idx % half;
+      const int r = idx / half;
+      const int which = r & 1, t = t0 + (r >> 1);
+      if (t >= T) continue;
+      const int axis = (j < quarter) ? 0 : 1;
+      const float ang = (float)pos_hw[t * 2 + axis] * inv_freq[j - axis * quarter];
+      const float c = cosf(ang), sn = sinf(ang);
+      bf16* base = qkv + (long)t * row + ((long)which * n_heads + h) * hd;
+      const float x1 = bf2f(base[j]), x2 = bf2f(base[j + half]);
+      float o1 = rbf(__fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, sn)));
+      float o2 = rbf(__fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, sn)));
+      if (which == 0) {
+        o1 *= scale_bf;
+        o2 *= scale_bf;
+      }
+      base[j] = f2bf(o1);
+      base[j + half] = f2bf(o2);
+    }
   }
   const int nv = hd >> 3;
   for (int idx = threadIdx.x; idx < 32 * nv; idx += blockDim.x) {
@@ -407,13 +460,21 @@ __global__ void vision_qkv_post_kernel(bf16* __restrict__ qkv, const int* __rest
   }
 }
 
+int vision_rope_table(const int* pos_hw, const float* inv_freq, int n_tok, int hd, void* cs, cudaStream_t st) {
+  B200_REQUIRE(n_tok > 0 && (hd % 4) == 0 && cs, "vision_rope_table: bad shape");
+  const int total = n_tok * (hd / 2);
+  B200_CUDA(launch_pdl(vision_rope_table_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, pos_hw, inv_freq, n_tok, hd / 2,
+                       (float2*)cs));
+  return B200_OK;
+}
+
 int vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads, int hd,
-                    float scale, void* vt, int t_ld, cudaStream_t st) {
+                    float scale, void* vt, int t_ld, cudaStream_t st, const void* cs) {
   B200_REQUIRE(n_tok > 0 && n_heads > 0 && (hd % 8) == 0 && hd <= 128 && (t_ld % 8) == 0 && t_ld >= n_tok,
                "vision_qkv_post: bad shape (hd=%d t_ld=%d)", hd, t_ld);
   const float scale_bf = __bfloat162float(__float2bfloat16_rn(scale));
   B200_CUDA(launch_pdl(vision_qkv_post_kernel, dim3(cdiv(n_tok, 32), n_heads), dim3(256), 0, st, (bf16*)qkv, pos_hw,
-                       inv_freq, n_tok, n_heads, hd, scale_bf, (bf16*)vt, t_ld));
+                       inv_freq, n_tok, n_heads, hd, scale_bf, (bf16*)vt, t_ld, (const float2*)cs));
   return B200_OK;
 }
 
@@ -470,7 +531,7 @@ int b200_mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const
 }
 int b200_vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
                          int hd, float scale, void* vt, int t_ld, void* st) {
-  return vision_qkv_post(qkv, pos_hw, inv_freq, n_tok, n_heads, hd, scale, vt, t_ld, (cudaStream_t)st);
+  return vision_qkv_post(qkv, pos_hw, inv_freq, n_tok, n_heads, hd, scale, vt, t_ld, (cudaStream_t)st, nullptr);
 }
 int b200_swiglu(const void* gu, void* out, int rows, int inter, void* st) {
   return swiglu(gu, out, rows, inter, (cudaStream_t)st);

@@ -22,17 +22,18 @@ def bf(*shape, scale=1.0, seed=0):
     return (torch.randn(*shape, device=dev, generator=g) * scale).to(torch.bfloat16)
 
 
-def time_cfg(lib, T, Nn, K, mode, inter, cfg, flags, rep=24):
+def time_cfg(lib, T, Nn, K, mode, inter, cfg, flags, rep=24, bias=False, epi=0):
     X = [bf(T, K, seed=i) for i in range(2)]
     W = [bf(Nn, K, scale=0.03, seed=i) for i in range(6)]
     ncol = inter if mode == 2 else Nn
     out = torch.empty(T, ncol, device=dev, dtype=torch.bfloat16)
     part = torch.empty(max(cfg[3], 1), T, Nn, device=dev, dtype=torch.float32) if mode == 1 else None
     s = torch.cuda.Stream()
+    b = bf(Nn, scale=0.5) if bias else None
 
     def call(i):
-        rc = lib.b200_gemm_wt(X[i & 1].data_ptr(), K, W[i % 6].data_ptr(), None, None, 0, out.data_ptr(), ncol,
-                              part.data_ptr() if part is not None else None, T, Nn, K, 0, mode, inter, (I * 4)(*cfg), flags,
+        rc = lib.b200_gemm_wt(X[i & 1].data_ptr(), K, W[i % 6].data_ptr(), b.data_ptr() if bias else None, None, 0, out.data_ptr(), ncol,
+                              part.data_ptr() if part is not None else None, T, Nn, K, epi, mode, inter, (I * 4)(*cfg), flags,
                               s.cuda_stream)
         assert rc == 0, lib.b200_last_error()
     with torch.cuda.stream(s):
@@ -62,5 +63,8 @@ for rnd in range(2):
     for name, T, Nn, K, mode, inter, cfg in cases:
         for path, lib in libs:
             r = [time_cfg(lib, T, Nn, K, mode, inter, cfg, fl) for fl in (0, 1, 2, 4)]
-            print(f"{name:10s} {cfg} {path[-28:]:28s}: full {r[0]:6.2f} | loads-only {r[1]:6.2f} | mma-only {r[2]:6.2f} | no-store {r[3]:6.2f} us",
+            extra = ""
+            if mode == 0:
+                extra = f" | bias {time_cfg(lib, T, Nn, K, mode, inter, cfg, 0, bias=True):6.2f} | bias+gelu {time_cfg(lib, T, Nn, K, mode, inter, cfg, 0, bias=True, epi=1):6.2f}"
+            print(f"{name:10s} {cfg} {path[-28:]:28s}: full {r[0]:6.2f} | loads-only {r[1]:6.2f} | mma-only {r[2]:6.2f} | no-store {r[3]:6.2f}{extra} us",
                   flush=True)
