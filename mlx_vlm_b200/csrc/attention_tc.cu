@@ -381,12 +381,11 @@ bool attention_tc_supported(const void* q, long q_ts, long q_hs, const void* k, 
 int attention_tc(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
                  const void* v, long v_ts, long v_hs, void* out, long o_ts, int n_heads, int n_kv,
                  int hd, int Lq, int S, int causal, float scale, cudaStream_t st) {
-  static bool set = false;
+  static unsigned long long set_mask = 0ull;
   const size_t smem = 8 * KBLK + 1024;
-  if (!set) {
+  if (first_use_on_device(&set_mask)) {
     B200_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    set = true;
   }
   AttnTcParams p;
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.out = (bf16*)out;

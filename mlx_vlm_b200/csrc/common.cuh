@@ -105,6 +105,16 @@ __device__ __forceinline__ float gelu_exact_bf(float x) {
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// per-DEVICE one-time setup (cudaFuncSetAttribute is per device): true the first time the current device asks
+inline bool first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 // ---- programmatic dependent launch -------------------------------------------------
 // Every kernel of the prefill / vision / batched-decode sequences starts with pdl_prologue():
 // it lets the NEXT kernel of the stream begin (its barrier / TMEM set-up and the prefetch of its

@@ -613,15 +613,14 @@ int batch_decoder_begin(void** handle, const BdModel& m, int B, const int* tok, 
       return rc;
     }
     *handle = d;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_mask = 0ull;
+    if (first_use_on_device(&attr_mask)) {
       B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       B200_CUDA(cudaFuncSetAttribute(bd_attn_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
   }
   d->B = B;

@@ -362,11 +362,10 @@ static int get_tmap(const void* ptr, long ld, int rows, int k, int box_rows, CUt
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0ull;
+  if (first_use_on_device(&attr_mask)) {
     B200_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    GemmSmem<BN>::TOTAL));
-    attr_set = true;
   }
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM));
   gemm_tn_kernel<BN><<<grid, 256, GemmSmem<BN>::TOTAL, st>>>(ta, tb, p);

@@ -460,9 +460,11 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 // the NEXT block applies to h (RMSNorm / LayerNorm with the oracle's rounding points).  One CTA
 // per token row; the split-K partials are added in split order (deterministic).
 // ---------------------------------------------------------------------------------------------
-constexpr int FIN_THREADS = 256;
-constexpr int FIN_MAXV = 8;  // float4 vectors per thread: N <= 256 * 4 * 8 = 8192
+// <256 threads, 8 vectors> for sequences (one CTA per row, many rows) and <1024, 2> for the few rows of a batched
+// decode step: there the kernel is a chain of L2 round trips, and 1024 threads issue every load of a row at once
+constexpr int FIN_N_MAX = 8192;  // N <= FIN_THREADS * 4 * FIN_MAXV in both shapes
 
+template <int FIN_THREADS>
 __device__ __forceinline__ float fin_block_sum(float v, float* red) {
   v = warp_sum(v);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -475,6 +477,7 @@ __device__ __forceinline__ float fin_block_sum(float v, float* red) {
   return t;
 }
 
+template <int FIN_THREADS, int FIN_MAXV>
 __global__ void __launch_bounds__(FIN_THREADS)
 finish_rows_kernel(const float* __restrict__ P, int S, const bf16* __restrict__ bias,
                    const bf16* __restrict__ resid, long ldr, bf16* __restrict__ h_out, long ldh,
@@ -525,7 +528,7 @@ finish_rows_kernel(const float* __restrict__ P, int S, const bf16* __restrict__ 
   }
   if (norm_kind == B200_NORM_NONE) return;
   if (norm_kind == B200_NORM_RMS) {
-    const float tot = fin_block_sum(s2, red);
+    const float tot = fin_block_sum<FIN_THREADS>(s2, red);
     const float rs = 1.0f / sqrtf(tot / (float)N + eps);
 #pragma unroll
     for (int u = 0; u < FIN_MAXV; ++u) {
@@ -542,7 +545,7 @@ finish_rows_kernel(const float* __restrict__ P, int S, const bf16* __restrict__ 
     return;
   }
   // LayerNorm: fp32 mean / variance (two passes over the registers), cast, * w, + b
-  const float mu = fin_block_sum(s1, red) / (float)N;
+  const float mu = fin_block_sum<FIN_THREADS>(s1, red) / (float)N;
   float v = 0.f;
 #pragma unroll
   for (int u = 0; u < FIN_MAXV; ++u) {
@@ -553,7 +556,7 @@ finish_rows_kernel(const float* __restrict__ P, int S, const bf16* __restrict__ 
       v += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
     }
   }
-  const float var = fin_block_sum(v, red) / (float)N;
+  const float var = fin_block_sum<FIN_THREADS>(v, red) / (float)N;
   const float rstd = 1.0f / sqrtf(var + eps);
 #pragma unroll
   for (int u = 0; u < FIN_MAXV; ++u) {
@@ -1050,23 +1053,30 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
 int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
                 long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn, long ldx,
                 int T, int N, cudaStream_t st) {
-  B200_REQUIRE(P && S >= 1 && T > 0 && N > 0 && (N % 4) == 0 && N <= FIN_THREADS * 4 * FIN_MAXV,
+  B200_REQUIRE(P && S >= 1 && T > 0 && N > 0 && (N % 4) == 0 && N <= FIN_N_MAX,
                "finish_rows: T=%d N=%d S=%d", T, N, S);
   B200_REQUIRE(norm_kind == B200_NORM_NONE || (xn && (norm_kind != B200_NORM_RMS || nw)),
                "finish_rows: norm output / weight missing");
   B200_REQUIRE((ldr % 4) == 0 && (ldh % 4) == 0 && (ldx % 4) == 0, "finish_rows: strides must be multiples of 4");
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(T);
-  lc.blockDim = dim3(FIN_THREADS);
+  const bool few_rows = T <= 32;
+  lc.blockDim = dim3(few_rows ? 1024 : 256);
   lc.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at;
   lc.numAttrs = g_wt_pdl ? 1 : 0;
-  B200_CUDA(cudaLaunchKernelEx(&lc, finish_rows_kernel, P, S, (const bf16*)bias, (const bf16*)resid, ldr,
-                               (bf16*)h_out, ldh, norm_kind, (const bf16*)nw, (const bf16*)nb, eps,
-                               (bf16*)xn, ldx, T, N));
+  if (few_rows) {
+    B200_CUDA(cudaLaunchKernelEx(&lc, finish_rows_kernel<1024, 2>, P, S, (const bf16*)bias, (const bf16*)resid, ldr,
+                                 (bf16*)h_out, ldh, norm_kind, (const bf16*)nw, (const bf16*)nb, eps,
+                                 (bf16*)xn, ldx, T, N));
+  } else {
+    B200_CUDA(cudaLaunchKernelEx(&lc, finish_rows_kernel<256, 8>, P, S, (const bf16*)bias, (const bf16*)resid, ldr,
+                                 (bf16*)h_out, ldh, norm_kind, (const bf16*)nw, (const bf16*)nb, eps,
+                                 (bf16*)xn, ldx, T, N));
+  }
   return B200_OK;
 }
 

@@ -383,11 +383,10 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
 
 template <int HDP>
 static int attn_f32_launch(const AttnF32P& p, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;   // one device kind per process (sm_100a only)
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0ull;
+  if (first_use_on_device(&attr_mask)) {
     B200_CUDA(cudaFuncSetAttribute(attention_f32_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)attn_f32_smem<HDP>()));
-    attr_set = true;
   }
   attention_f32_kernel<HDP><<<grid, 256, attn_f32_smem<HDP>(), st>>>(p);
   B200_CHECK_LAUNCH();
