@@ -221,6 +221,51 @@ W_BYTES_7B = 2 * 7_070_619_136          # Qwen2-VL-7B LM weights 
 KV_BYTES_PER_POS_7B = 57_344            # 2 * 4 kv heads * 128 * 2 B * 28 layers
 
 
+def lockstep_2b(world, rank, dev, args, model, processor, ids, pvd, grid):
+    """The C2 model (Qwen2-VL-2B, already resident) with `rows` copies of the C2 request as lock-step rows of one
+    weight stream per GPU: what continuous batching buys on the small model (512 tokens out per row)."""
+    import torch
+    import torch.distributed as dist
+    from mlx_vlm_b200.generate_batch import BatchGenerator
+    rows, n_out = args.c5_rows, N_OUT
+    eng = model.engine
+    prompt = ids.reshape(-1).tolist()
+    kw = {"pixel_values": pvd, "image_grid_thw": grid}
+
+    def run():
+        g = BatchGenerator(model, processor, max_tokens=n_out, completion_batch_size=rows, prefill_batch_size=rows,
+                           decode_slice=32)
+        g.insert([prompt] * rows, [n_out] * rows, [dict(kw) for _ in range(rows)])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n = 0
+        while g.has_work:
+            n += len(g.next()[1])
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, n
+
+    run()
+    dt, n = run()
+    assert n == rows * n_out
+    step_ms = eng.last_decode_ms()
+    t = torch.tensor([dt, step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, step_ms = t.tolist()
+    peak, peak_src = _peaks()
+    bytes_step = W_BYTES_2B + rows * KV_BYTES_PER_POS * (N_TEXT + 144 + n_out / 2)
+    return {"workload": f"Qwen2-VL-2B, {rows} lock-step rows per GPU (the C2 request x {rows}), {n_out} tokens out each, "
+                        "admission + prefill of the rows inside the timed region",
+            "rows_per_gpu": rows, "seconds": dt, "tokens_per_s": world * rows * n_out / dt,
+            "decode_ms_per_step": step_ms,
+            "roofline": {"bound": "hbm", "achieved": bytes_step / (step_ms / 1e3) / 1e9 if step_ms > 0 else None,
+                         "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                         "frac": bytes_step / (step_ms / 1e3) / 1e9 / peak if step_ms > 0 else None,
+                         "algorithmic_bytes_per_step": bytes_step}}
+
+
 def c5_leg(world, rank, dev, args):
     """BASELINE config 5: Qwen2-VL-7B, `rows` concurrent image+prompt requests PER GPU (64 over 8 GPUs),
     routed by parallel.generate_sharded (request i -> rank i mod N), each replica running its own
@@ -626,7 +671,9 @@ def main():
 
     c5 = None
     if not args.no_c5:
+        rows2b = lockstep_2b(world, rank, dev, args, model, processor, ids, pvd, grid)
         c5 = c5_leg(world, rank, dev, args)
+        c5["qwen2_vl_2b_rows"] = rows2b
 
     c3 = c3_leg(dev, args) if (rank == 0 and not args.no_c3) else None
     c4 = c4_leg(dev, args) if (rank == 0 and not args.no_c4) else None

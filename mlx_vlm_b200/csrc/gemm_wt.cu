@@ -931,7 +931,11 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
     };
     WtConfig model;
     gemm_wt_auto(T, row_blocks, K, allow_split, &model, sm_count);
-    if (fits(model)) cand.push_back(model);
+    {
+      static const bool two_only = getenv("B200_WT_TWO_PER_SM") && atoi(getenv("B200_WT_TWO_PER_SM")) != 0;
+      const long model_smem = (long)model.stages * model.KS * (WT_WBLK + model.TN * 128);
+      if (fits(model) && (!two_only || model_smem <= 110 * 1024)) cand.push_back(model);
+    }
     int tns[8], n_tn = 0;
     if (T <= 96) {
       tns[n_tn++] = round16(T);
@@ -950,9 +954,13 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
         sps[1] = a < 1 ? 1 : (a > cap_k ? cap_k : a);
         sps[2] = b < 1 ? 1 : (b > cap_k ? cap_k : b);
       }
+      // B200_WT_TWO_PER_SM=1 (experiment): only configurations that leave room for a second CTA on the SM, so the
+      // NEXT kernel's prologue and weight prefetch can overlap this kernel's tail under PDL
+      static const bool two_only = getenv("B200_WT_TWO_PER_SM") && atoi(getenv("B200_WT_TWO_PER_SM")) != 0;
       for (int sp : sps) {
-        add(tn, 2, 208 * 1024, sp);  // one CTA per SM, 256-byte weight-row bursts
+        if (!two_only) add(tn, 2, 208 * 1024, sp);  // one CTA per SM, 256-byte weight-row bursts
         add(tn, 1, 110 * 1024, sp);  // two CTAs per SM
+        if (two_only) add(tn, 2, 110 * 1024, sp);
       }
     }
     if (cand.empty()) {

@@ -162,3 +162,54 @@ def test_llava_features_merge_and_generate(kind):
         if i == 0:
             cmp_noise(lp, lp_ref, lp_ex, f"{kind} llava logprobs step 0")
     assert eng.device_error() == 0
+
+
+def test_vision_feature_cache_through_the_server_loop():
+    """the GPU thread fills `VisionFeatureCache` on a miss (models with `encode_image`) and hands a
+    hit to the model as `cached_image_features` (server/generation.py:1636-1675, dispatch.py:800-809): the repeat of
+    a request produces the same tokens without running the tower again."""
+    import types
+    from oracle import llava as OL
+    from mlx_vlm_b200.server import GenerationArguments, ResponseGenerator
+    from mlx_vlm_b200.vision_cache import VisionFeatureCache
+    c = OL.LlavaCfg(vision=OL.ClipCfg(hidden_size=64, num_hidden_layers=3, intermediate_size=128,
+                                      num_attention_heads=4, image_size=42, patch_size=14),
+                    text=OL.LlamaCfg(hidden_size=256, num_hidden_layers=2, intermediate_size=512,
+                                     num_attention_heads=4, num_key_value_heads=2, vocab_size=320),
+                    image_token_index=300)
+    W, model = _build(c)
+    model.config.eos_token_id = []
+    eng = model.engine
+    req = OL.synthetic_request(c, n_text=8, seed=1)
+    ids = req["input_ids"]
+    pv = req["pixel_values"].permute(0, 3, 1, 2).contiguous().cuda()
+    proc = types.SimpleNamespace(tokenizer=types.SimpleNamespace(stopping_criteria=None))
+    cache = VisionFeatureCache()
+    srv = ResponseGenerator(model, proc, vision_cache=cache, decode_slice=2)
+    runs, launches = [], []
+    for _ in range(3):
+        l0 = eng.launch_count
+        tower_calls = {"n": 0}
+        inner = model.encode_image
+
+        def counted(x, _inner=inner):
+            tower_calls["n"] += 1
+            return _inner(x)
+        model.encode_image = counted
+        toks = [e.token for e in srv.generate({"input_ids": ids, "pixel_values": pv}, GenerationArguments(max_tokens=5),
+                                              images="image-key-1", timeout=60)]
+        model.encode_image = inner
+        runs.append(toks)
+        launches.append(tower_calls["n"])
+    srv.stop_and_join()
+    assert srv._error is None, srv._error
+    assert launches == [1, 0, 0], launches          # one miss, then hits
+    assert len(cache) == 1
+    assert runs[0] == runs[1] == runs[2] and len(runs[0]) == 5
+    ref = OL.greedy_generate(c, W, ids, req["pixel_values"], 5)
+    from oracle.mlx_semantics import Rounder
+    for i, tok in enumerate(runs[0]):
+        lp_ref = OL.Q.logprobs_from_logits(Rounder("bf16"), ref["logits"][i])[0]
+        assert _token_ok(tok, lp_ref), (i, tok, ref["tokens"][i])
+        if tok != ref["tokens"][i]:
+            break
