@@ -380,10 +380,13 @@ def c3_leg(dev, args):
         ev[0].record(eng.stream)
         feats = model.encode_image(pv)
         ev[1].record(eng.stream)
-        for b in range(B):
-            emb = model.get_input_embeddings(ids, pv, cached_image_features=feats[b:b + 1])
-            cache = make_prompt_cache(lm)
-            lm(ids, inputs_embeds=emb.inputs_embeds, cache=cache, logits_to_keep=1, reserve_tokens=T + 8)
+        embs = [model.get_input_embeddings(ids, pv, cached_image_features=feats[b:b + 1]).inputs_embeds for b in range(B)]
+        if args.c3_sequential:      # A/B: one prefill call per request
+            for b in range(B):
+                lm(ids, inputs_embeds=embs[b], cache=make_prompt_cache(lm), logits_to_keep=1, reserve_tokens=T + 8)
+        else:                       # the 8 prompts in ONE pass over the weights (reference PromptProcessingBatch)
+            rows, _ = lm.make_batch_cache(B, T + 8)
+            lm.prefill_rows([ids] * B, embs, [lm.make_cache_row(rows.pool, b) for b in range(B)], reserve_tokens=T + 8)
         ev[2].record(eng.stream)
         eng.stream.synchronize()
         return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
@@ -413,7 +416,8 @@ def c3_leg(dev, args):
     tpeak, tsrc = _tensor_peak()
     out = {"workload": f"C3: LLaVA-1.5-7B bf16 (random init), batch {B} x 336x336 images, prefill only: CLIP-L/14 tower "
                        f"({n_blocks} blocks, fp32-accurate split-operand GEMMs) + projector + merge + Llama-7B prefill "
-                       f"of {B} requests x T={T} ({P} image + {n_text} text tokens)",
+                       f"of {B} requests x T={T} ({P} image + {n_text} text tokens), "
+                       + ("one prefill call per request" if args.c3_sequential else "all requests in one batched prefill pass"),
            "tower_projector_ms": tw, "lm_prefill_ms": pf, "ms_per_step": tw + pf, "wall_ms_per_step": wall * 1e3,
            "prefill_img_tokens_per_sec": B * P / ((tw + pf) / 1e3),
            "tower_img_tokens_per_sec": B * P / (tw / 1e3),
@@ -510,6 +514,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (Qwen2-VL-7B continuous batching)")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 leg (LLaVA-1.5-7B, 8 images, prefill only)")
+    ap.add_argument("--c3-sequential", action="store_true", help="C3: prefill the 8 requests one by one (A/B)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 leg (Idefics2-8B, 4 images, 256 out)")
     ap.add_argument("--c5-rows", type=int, default=8, help="concurrent requests per GPU in the C5 leg")
     ap.add_argument("--c5-out", type=int, default=512)

@@ -207,6 +207,15 @@ int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3,
                         int T, int ctx0, int rope_delta, void* all_logits_out,
                         void* stream);
 
+/* PromptProcessingBatch (ar.py:1581-2175): n_seq FRESH prompts prefilled in one pass over the weights.
+ * embeds (sum round8(T_g), hidden) bf16 = the sequences concatenated along the token axis, each padded to a
+ * multiple of 8 tokens (finite values in the padding rows), pos3 (3, sum round8(T_g)) int32 device laid out the
+ * same way; sequence g (seq_len[g] tokens, host array) fills KV pool row rows[g] (host array) from position 0; every GEMM
+ * runs once over all tokens, attention is block-diagonal causal.  The first token of every sequence goes through
+ * the fused head + sampler, in order: n_seq new entries in the token log. */
+int b200_engine_prefill_batch(b200_engine* e, const void* embeds, const int* pos3, int n_seq,
+                              const int* seq_len, const int* rows, void* stream);
+
 /* generate_step's decode loop body (ar.py:496-515, _step :334-389) for greedy
  * sampling, n_steps times: embed(last token) -> 28 x decoder layer (L=1) -> norm
  * -> tied head -> logprobs -> argmax.  Launch-only; tokens accumulate in the

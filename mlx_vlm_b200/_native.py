@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200_engine_set_rope_tables": (_I, [_P, _P, _P]),
     "b200_engine_vision": (_I, [_P, _P, _P, _I, _P, _P]),
     "b200_engine_prefill": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "b200_engine_prefill_batch": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "b200_engine_decode": (_I, [_P, _I, _P, _P]),
     "b200_engine_set_next": (_I, [_P, _I, _I, _I, _P]),
     "b200_engine_logits": (_P, [_P]),

@@ -157,7 +157,8 @@ int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, 
 int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
                    void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
                    cudaStream_t st, float q_scale = 0.f, void* vt = nullptr, int t_ld = 0,
-                   const KvRef* ref = nullptr, int layer = 0, void* kws = nullptr);
+                   const KvRef* ref = nullptr, int layer = 0, void* kws = nullptr, const void* tok_loc = nullptr,
+                   long row_stride = 0);
 int vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads, int hd,
                     float scale, void* vt, int t_ld, cudaStream_t st, const void* cs = nullptr);
 // cos / sin table [n_tok][hd / 2] float2 for vision_qkv_post (computed once per tower call)
@@ -176,6 +177,8 @@ int gemm_bf16_tn(const void* A, long lda, const void* W, const void* bias, const
 // weight-major tcgen05 GEMM (gemm_wt.cu) + the row op that finishes its split-K partials
 struct WtConfig {
   int TN, KS, stages, split;
+  int rb = 1;   // weight row blocks (128 rows) per CTA: 2 = two accumulators share one token tile (large GEMMs:
+                // the main loop is bounded by L2 -> SM bytes per flop, and this halves the token-operand traffic)
 };
 // extension for the fp32-accurate (split bf16) GEMMs of the LLaVA / Idefics2 towers
 struct WtExt {

@@ -377,10 +377,22 @@ static int v2_linear_residual_norm(b200_engine* e, const bf16* x, long ldx, cons
                                    bf16* xn, long ldxn, int T, int N, int K, cudaStream_t s) {
   float* P = ws_partial(e);
   int split = 1;
-  int rc = gemm_wt_tuned(x, ldx, W, nullptr, nullptr, 0, nullptr, 0, P, WT_PARTIAL_BYTES, T, N, K, B200_EPI_NONE,
-                         B200_WT_PARTIAL, 0, true, e->sm_count, &split, s);
-  if (rc) return rc;
+  int rc;
   e->launches += 2;
+  if ((long)T * N * 4 > WT_PARTIAL_BYTES) {
+    // many tokens (a long chunk or a batched prefill): even one fp32 partial tile set does not fit the partial
+    // region, and with this many token tiles split-K is not needed to fill the SMs either: bias + residual fused in
+    // the bf16 epilogue (same rounding points as finish_rows), then the norm as its own row op
+    if ((rc = gemm_wt_tuned(x, ldx, W, b, h, ldh, h, ldh, nullptr, 0, T, N, K, B200_EPI_NONE, B200_WT_BF16, 0, false,
+                            e->sm_count, nullptr, s)))
+      return rc;
+    if (norm_kind == B200_NORM_RMS) return rms_norm(h, nw, xn, T, N, eps, s);
+    if (norm_kind == B200_NORM_LN) return layer_norm(h, nw, nb, xn, T, N, eps, s);
+    return B200_OK;
+  }
+  rc = gemm_wt_tuned(x, ldx, W, nullptr, nullptr, 0, nullptr, 0, P, WT_PARTIAL_BYTES, T, N, K, B200_EPI_NONE,
+                     B200_WT_PARTIAL, 0, true, e->sm_count, &split, s);
+  if (rc) return rc;
   return finish_rows(P, split, b, h, ldh, h, ldh, norm_kind, nw, nb, eps, xn, ldxn, T, N, s);
 }
 
@@ -523,7 +535,16 @@ static int vision_v2_body(b200_engine* e, const float* pixel_values, const int* 
     if ((rc = vision_rope_table(e->pos_hw, e->v_inv_freq, (int)N, hd, rope_cs, s))) return rc;
     e->launches += 1;
   }
-  const bool fa = attention_fa_supported(qkv, 3 * E, hd, qkv + E, 3 * E, hd, vt, (long)hd * t_ld, t_ld, att, E, hd);
+  bool fa = attention_fa_supported(qkv, 3 * E, hd, qkv + E, 3 * E, hd, vt, (long)hd * t_ld, t_ld, att, E, hd);
+  {  // the pipelined kernel loads V^T tiles with tokens innermost: a segment must start on a 16-byte boundary
+     // (8 tokens); frames with other offsets (e.g. a 6 x 6-patch image followed by another) take the round-1 kernel
+    long o = 0;
+    for (int im = 0; im < n_images && fa; ++im)
+      for (int tt = 0; tt < grid[im * 3]; ++tt) {
+        if (o % 8) fa = false;
+        o += (long)grid[im * 3 + 1] * grid[im * 3 + 2];
+      }
+  }
   for (int i = 0; i < c.v_depth; ++i) {
     const VBlk& b = e->vblk[i];
     if ((rc = v2_linear(e, y, E, b.qkvw, b.qkvb, qkv, 3 * E, (int)N, (int)(3 * E), (int)E, B200_EPI_NONE, s))) return rc;
@@ -573,8 +594,12 @@ static int vision_v2_body(b200_engine* e, const float* pixel_values, const int* 
   return B200_OK;
 }
 
+// one sequence of a batched prefill: tokens [off, off + T) of the concatenated batch go to KV pool row `row`
+struct PreSeg { int off, T, row; };
+
 static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ctx0, void* all_logits_out,
-                                  cudaStream_t s);
+                                  cudaStream_t s, const PreSeg* segs = nullptr, int n_seg = 0,
+                                  const void* tok_loc = nullptr);
 
 static int prefill_layers_v2(b200_engine* e, const void* embeds, const int* pos3, int T, int ctx0,
                              void* all_logits_out, bf16** h_out, cudaStream_t s) {
@@ -610,8 +635,13 @@ static int prefill_layers_v2(b200_engine* e, const void* embeds, const int* pos3
   return seq_run(e, e->pre_graphs, key, s, [&]() { return prefill_layers_v2_body(e, pos_stage, T, 0, nullptr, s); });
 }
 
+// segs == nullptr: ONE sequence bound to e->kv_row (graph-capturable: the cache is addressed through e->kvref).
+// segs != nullptr (PromptProcessingBatch, ar.py:1581-2175): several fresh sequences concatenated along the token
+// axis — every GEMM / norm / SwiGLU runs once over all T tokens (the weights are streamed once for the whole
+// batch), M-RoPE + KV append scatter each token to (its row, its position) through `tok_loc`, and attention runs
+// per sequence on its own block of the shared q / K / V^T buffers (block-diagonal causal).
 static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ctx0, void* all_logits_out,
-                                  cudaStream_t s) {
+                                  cudaStream_t s, const PreSeg* segs, int n_seg, const void* tok_loc) {
   const auto& c = e->cfg;
   const long H = c.hidden, I = c.inter, QH = (long)c.n_heads * c.head_dim;
   const long QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
@@ -642,6 +672,19 @@ static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ct
     // e->kvref: nothing about the KV pool is baked into the captured graph.
     const bool fa = ctx0 == 0 && attention_fa_supported(qkv, QKV, hd, kws, hd, (long)T * hd, vt, (long)hd * t_ld,
                                                         t_ld, att, QH, hd);
+    if (segs) {
+      B200_REQUIRE(fa, "prefill_batch: the pipelined attention kernel does not support this geometry");
+      const long row_stride = (long)c.n_kv_heads * e->kv_cap * hd;
+      if ((rc = mrope_kv_write(qkv, pos3, e->lm_inv_freq, e->axis_sel, e->kptr(l, 0), e->vptr(l, 0), T, 0, e->kv_cap,
+                               c.n_heads, c.n_kv_heads, hd, s, scale_bf, vt, t_ld, nullptr, l, kws, tok_loc, row_stride)))
+        return rc;
+      for (int g = 0; g < n_seg; ++g) {
+        if ((rc = attention_fa(qkv, QKV, hd, kws, hd, (long)T * hd, vt, (long)hd * t_ld, t_ld, att, QH, c.n_heads,
+                               c.n_kv_heads, hd, segs[g].T, segs[g].T, 1, s, segs[g].off, T, segs[g].off, T)))
+          return rc;
+      }
+      e->launches += 1 + n_seg;
+    } else {
     if ((rc = mrope_kv_write(qkv, pos3, e->lm_inv_freq, e->axis_sel, kc, vc, T, ctx0, e->kv_cap, c.n_heads,
                              c.n_kv_heads, hd, s, fa ? scale_bf : 0.f, fa ? vt : nullptr, t_ld,
                              fa ? e->kvref : nullptr, l, fa ? kws : nullptr)))
@@ -655,6 +698,7 @@ static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ct
     }
     if (rc) return rc;
     e->launches += 2;
+    }
     if ((rc = v2_linear_residual_norm(e, att, QH, lw.wo, nullptr, h, H, B200_NORM_RMS, lw.ln2, nullptr, c.rms_eps, xn,
                                       H, T, (int)H, (int)QH, s)))
       return rc;
@@ -1032,6 +1076,75 @@ int b200_engine_prefill(b200_engine* e, const void* embeds, const int* pos3, int
     return rc;
   e->launches += 3;
   e->tokens_launched += 1;
+  return B200_OK;
+}
+
+// PromptProcessingBatch (ar.py:1581-2175): n_seq FRESH prompts prefilled in one pass.  embeds = the sequences'
+// embeddings concatenated along the token axis, EACH SEQUENCE PADDED TO A MULTIPLE OF 8 TOKENS (any finite values in
+// the padding rows): [sum round8(T_g), hidden]; pos3 = (3, sum round8(T_g)) int32 device, laid out the same way;
+// sequence g has seq_len[g] real tokens and fills KV pool row rows[g] from position 0.  The first token of every sequence goes through
+// the fused head + sampler in order: token_log receives n_seq entries (tokens_launched += n_seq).
+int b200_engine_prefill_batch(b200_engine* e, const void* embeds, const int* pos3, int n_seq, const int* seq_len,
+                              const int* rows, void* stream) {
+  B200_REQUIRE(e && embeds && pos3 && n_seq > 0 && seq_len && rows, "engine_prefill_batch: bad arguments");
+  int rc = resolve(e);
+  if (rc) return rc;
+  B200_REQUIRE(e->kv && e->v2, "engine_prefill_batch: KV pool not bound / round-1 prefill kernels selected");
+  long T = 0;
+  std::vector<PreSeg> segs(n_seq);
+  for (int g = 0; g < n_seq; ++g) {
+    B200_REQUIRE(seq_len[g] > 0 && seq_len[g] <= e->kv_cap && rows[g] >= 0 && rows[g] < e->kv_batch,
+                 "engine_prefill_batch: sequence %d: %d tokens into row %d (capacity %d, %d rows)", g, seq_len[g], rows[g],
+                 e->kv_cap, e->kv_batch);
+    segs[g] = PreSeg{(int)T, seq_len[g], rows[g]};
+    T += round8(seq_len[g]);   // every sequence starts at a multiple of 8 tokens: the V^T tiles are loaded by TMA
+                               // with tokens innermost, and a box must start on a 16-byte boundary
+  }
+  B200_REQUIRE(e->ws && b200_engine_workspace_bytes(e, (int)T, 1) <= e->ws_bytes,
+               "engine_prefill_batch: workspace too small for %ld tokens", T);
+  B200_CUDA(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const auto& c = e->cfg;
+  const long H = c.hidden, I = c.inter, QH = (long)c.n_heads * c.head_dim;
+  const long QKV = (long)(c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+  uint8_t* p = e->ws;
+  bf16* h = (bf16*)p;
+  p += 2 * align256(T * H * 2) + align256(T * QKV * 2) + align256(T * QH * 2) + align256(T * 2 * I * 2) +
+       align256(T * I * 2);
+  int* pos_stage = (int*)p;   // 3 * T ints; the tokens' (row, position) table gets a stream-ordered allocation
+  B200_CUDA(cudaMemcpyAsync(h, embeds, (size_t)T * H * 2, cudaMemcpyDeviceToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(pos_stage, pos3, (size_t)3 * T * 4, cudaMemcpyDeviceToDevice, s));
+  std::vector<int> loc(2 * (size_t)T, -1);   // padding tokens: row -1 = no cache write
+  for (int g = 0; g < n_seq; ++g)
+    for (int t = 0; t < segs[g].T; ++t) {
+      loc[2 * ((size_t)segs[g].off + t)] = segs[g].row;
+      loc[2 * ((size_t)segs[g].off + t) + 1] = t;
+    }
+  int* loc_dev = nullptr;
+  B200_CUDA(cudaMallocAsync((void**)&loc_dev, loc.size() * 4, s));
+  B200_CUDA(cudaMemcpyAsync(loc_dev, loc.data(), loc.size() * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaStreamSynchronize(s));   // `loc` is pageable host memory: the copy must finish before it goes away
+  rc = prefill_layers_v2_body(e, pos_stage, (int)T, 0, nullptr, s, segs.data(), n_seq, loc_dev);
+  cudaFreeAsync(loc_dev, s);
+  if (rc) return rc;
+  const DecodeDims d = e->dims();
+  if (e->prepared_cap != e->kv_cap || e->prepared_cluster != e->attn_cluster) {
+    if ((rc = decode_prepare(d, e->attn_cluster))) return rc;
+    e->prepared_cap = e->kv_cap;
+    e->prepared_cluster = e->attn_cluster;
+  }
+  for (int g = 0; g < n_seq; ++g) {   // first token of every sequence: fused head + sampler on its last row
+    if ((rc = launch_set_state(e->st, 0, segs[g].T, segs[g].T, 0, 0, e->embed, e->h, c.hidden, s))) return rc;
+    if ((rc = launch_head(d, e->norm, e->head, h + (long)(segs[g].off + segs[g].T - 1) * H, e->logits, e->partials, s)))
+      return rc;
+    if ((rc = launch_sample(d, e->logits, e->partials, e->logprobs, e->embed, e->h, e->st, e->token_log, e->log_cap,
+                            e->force, 0, s)))
+      return rc;
+    e->launches += 3;
+    e->tokens_launched += 1;
+  }
+  e->ctx_host = segs[n_seq - 1].T;
+  e->pos_host = segs[n_seq - 1].T;
   return B200_OK;
 }
 

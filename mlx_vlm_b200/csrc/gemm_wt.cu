@@ -51,6 +51,7 @@ struct WtParams {
   long ldc, ldr;
   int T, N, K;
   int TN, KS, n_stages;
+  int RB;            // weight row blocks (128 rows each) per CTA: 1, or 2 sharing one token tile (two accumulators)
   int kb_per_split;
   int epilogue, mode;
   int inter;
@@ -190,7 +191,8 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool swiglu = !TOWER && (p.mode == B200_WT_SWIGLU);
   const int rb = blockIdx.x;
-  const int n0 = rb * (swiglu ? 64 : WT_ROWS);  // first output feature (SwiGLU: channel) of the tile
+  const int rows_blk = swiglu ? 64 : WT_ROWS;   // output features (SwiGLU: channels) of one row block
+  const int n0 = rb * rows_blk * p.RB;          // first output feature (SwiGLU: channel) of the tile
   const int t0 = blockIdx.y * p.TN;
   const int split = blockIdx.z;
   const int kb_total = (p.K + WT_BK - 1) / WT_BK;
@@ -198,10 +200,10 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int kb1 = min(kb_total, kb0 + p.kb_per_split);
   const int n_it = (kb1 - kb0 + p.KS - 1) / p.KS;
   const int xblk = p.TN * 128;                      // bytes of one token k-block tile
-  const int stage_bytes = p.KS * (WT_WBLK + xblk);
+  const int stage_bytes = p.KS * (p.RB * WT_WBLK + xblk);
   const int NS = p.n_stages;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.TN) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.RB * p.TN) tmem_cols <<= 1;
 
   w_pdl_launch();  // the next kernel may start its prologue / weight prefetch as SM resources free up
 
@@ -212,22 +214,25 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       w_mbar_arrive(&full_bar[s]);
       return;
     }
-    w_mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (WT_WBLK + xblk));
+    w_mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (p.RB * WT_WBLK + xblk));
     for (int j = 0; j < cnt; ++j) {
       int kbw = kb0 + it * p.KS + j;
       if (p.kb_w > 0) kbw %= p.kb_w;
       const int kc = kbw * WT_BK;
-      if (swiglu) {
-        w_tma_2d(sW + j * WT_WBLK, &tmW, &full_bar[s], kc, n0);
-        w_tma_2d(sW + j * WT_WBLK + 64 * 128, &tmW, &full_bar[s], kc, p.inter + n0);
-      } else {
-        w_tma_2d(sW + j * WT_WBLK, &tmW, &full_bar[s], kc, n0);
+      for (int r = 0; r < p.RB; ++r) {   // rows beyond N are zero-filled by the tensor map
+        uint8_t* dst = sW + (j * p.RB + r) * WT_WBLK;
+        if (swiglu) {
+          w_tma_2d(dst, &tmW, &full_bar[s], kc, n0 + r * 64);
+          w_tma_2d(dst + 64 * 128, &tmW, &full_bar[s], kc, p.inter + n0 + r * 64);
+        } else {
+          w_tma_2d(dst, &tmW, &full_bar[s], kc, n0 + r * WT_ROWS);
+        }
       }
     }
   };
   auto issue_x = [&](int it, int s) {
     if (p.flags & 2u) return;
-    uint8_t* sX = ring + (long)s * stage_bytes + p.KS * WT_WBLK;
+    uint8_t* sX = ring + (long)s * stage_bytes + p.KS * p.RB * WT_WBLK;
     const int cnt = min(p.KS, kb1 - kb0 - it * p.KS);
     for (int j = 0; j < cnt; ++j)
       w_tma_2d(sX + j * xblk, &tmX, &full_bar[s], (kb0 + it * p.KS + j) * WT_BK, t0);
@@ -282,13 +287,14 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         w_fence_after();
         if (!(p.flags & 1u)) {
           const uint32_t w_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes));
-          const uint32_t x_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes + p.KS * WT_WBLK));
+          const uint32_t x_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes + p.KS * p.RB * WT_WBLK));
           const int cnt = min(p.KS, kb1 - kb0 - it * p.KS);
           for (int j = 0; j < cnt; ++j) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              w_umma(tmem_base, w_lo + (uint32_t)(j * (WT_WBLK >> 4) + kk * 2),
-                     x_lo + (uint32_t)(j * (xblk >> 4) + kk * 2), W_DESC_HI, idesc, acc);
+              for (int r = 0; r < p.RB; ++r)   // the row blocks of the CTA share the token operand
+                w_umma(tmem_base + (uint32_t)(r * p.TN), w_lo + (uint32_t)((j * p.RB + r) * (WT_WBLK >> 4) + kk * 2),
+                       x_lo + (uint32_t)(j * (xblk >> 4) + kk * 2), W_DESC_HI, idesc, acc);
               acc = 1;
             }
           }
@@ -305,15 +311,18 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   w_fence_after();
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;  // weight row of the tile == TMEM lane
-  float bias_v = 0.f;
-  if ((TOWER || p.mode == B200_WT_BF16) && p.bias && n0 + row < p.N) bias_v = bf2f(p.bias[n0 + row]);
   uint8_t* stg = ring;  // every TMA load has landed and every MMA has retired: the ring is free
   const int tid = threadIdx.x;
+  for (int rbi = 0; rbi < p.RB; ++rbi) {   // the row blocks of this CTA, one after the other
+  const int n0r = n0 + rbi * rows_blk;
+  const uint32_t tmem_r = tmem_base + (uint32_t)(rbi * p.TN);
+  float bias_v = 0.f;
+  if ((TOWER || p.mode == B200_WT_BF16) && p.bias && n0r + row < p.N) bias_v = bf2f(p.bias[n0r + row]);
   for (int c0 = 0; c0 < p.TN; c0 += WT_EPI_TOK) {
     const int cc = c0 + half * 32;
     if (cc < p.TN && !(p.flags & 1u)) {
       uint32_t a[32];
-      w_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, a);
+      w_tmem_ld32(tmem_r + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, a);
       if (!TOWER && p.mode == B200_WT_PARTIAL) {
         float* sf = reinterpret_cast<float*>(stg);
 #pragma unroll
@@ -343,7 +352,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 4; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 4, ch = idx & 15;
-          const int t = t0 + c0 + tl, n = n0 + ch * 8;
+          const int t = t0 + c0 + tl, n = n0r + ch * 8;
           if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
           const uint4 sv = *reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + ch * 8) * 2);
           const bool vec_ok = vec_all && n + 8 <= p.N;  // only the last chunk of an odd N goes element-wise
@@ -373,7 +382,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 2; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 3, ch = idx & 7;
-          const int t = t0 + c0 + tl, i = n0 + ch * 8;
+          const int t = t0 + c0 + tl, i = n0r + ch * 8;
           if (c0 + tl >= p.TN || t >= p.T || i >= p.inter) continue;
           float g[8], uu[8], o[8];
           unpack8(*reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + ch * 8) * 2), g);
@@ -389,7 +398,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 8; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 5, ch = idx & 31;
-          const int t = t0 + c0 + tl, n = n0 + ch * 4;
+          const int t = t0 + c0 + tl, n = n0r + ch * 4;
           if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
           float4 v = *reinterpret_cast<const float4*>(stg + (tl * WT_ROWS + ch * 4) * 4);
           if (p.mode == B200_WT_F32) {
@@ -430,7 +439,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 8; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 5, ch = idx & 31;
-          const int t = t0 + c0 + tl, n = n0 + ch * 4;
+          const int t = t0 + c0 + tl, n = n0r + ch * 4;
           if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
           const float4 v = *reinterpret_cast<const float4*>(stg + (tl * WT_ROWS + ch * 4) * 4);
           float* dst = p.partial + ((long)split * p.T + t) * p.N + n;
@@ -444,6 +453,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       }
     }
     w_ebar();
+  }
   }
   w_fence_before();
   __syncthreads();
@@ -789,7 +799,9 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
     p.Csplit = ext->Csplit; p.ld_split = ext->ld_split; p.n_pad = ext->n_pad;
     if (ext->kb_w > 0) k_w = ext->k_w;
   }
-  const int stage = cfg.KS * (WT_WBLK + cfg.TN * 128);
+  B200_REQUIRE((cfg.rb == 1 || cfg.rb == 2) && cfg.rb * cfg.TN <= 512, "gemm_wt: rb=%d TN=%d", cfg.rb, cfg.TN);
+  p.RB = cfg.rb;
+  const int stage = cfg.KS * (cfg.rb * WT_WBLK + cfg.TN * 128);
   const size_t smem = (size_t)cfg.stages * stage + 1024;
   B200_REQUIRE(smem <= 227 * 1024 - 1024, "gemm_wt: %zu B of shared memory", smem);
   B200_REQUIRE((size_t)cfg.stages * stage >= (size_t)WT_EPI_TOK * WT_ROWS * 4, "gemm_wt: ring smaller than the epilogue staging tile");
@@ -811,7 +823,7 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
   }
   const int row_blocks = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, WT_ROWS);
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(row_blocks, cdiv(T, cfg.TN), splits);
+  lc.gridDim = dim3(cdiv(row_blocks, cfg.rb), cdiv(T, cfg.TN), splits);
   lc.blockDim = dim3(256);
   lc.dynamicSmemBytes = smem;
   lc.stream = st;
@@ -889,10 +901,11 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
       file_read = true;
       if (const char* path = tune_file()) {
         if (FILE* fp = fopen(path, "r")) {
-          int tb, n, k, md, so, tn, ks, stg, sp;
-          while (fscanf(fp, "%d %d %d %d %d %d %d %d %d", &tb, &n, &k, &md, &so, &tn, &ks, &stg, &sp) == 9)
-            if (tn >= 16 && tn <= 256 && tn % 16 == 0 && ks >= 1 && stg >= 2 && stg <= WT_MAX_STAGES && sp >= 1)
-              cache[TuneKey{tb, n, k, md, so, dev}] = WtConfig{tn, ks, stg, sp};
+          int tb, n, k, md, so, tn, ks, stg, sp, rb;
+          while (fscanf(fp, "%d %d %d %d %d %d %d %d %d %d", &tb, &n, &k, &md, &so, &tn, &ks, &stg, &sp, &rb) == 10)
+            if (tn >= 16 && tn <= 256 && tn % 16 == 0 && ks >= 1 && stg >= 2 && stg <= WT_MAX_STAGES && sp >= 1 &&
+                (rb == 1 || rb == 2))
+              cache[TuneKey{tb, n, k, md, so, dev}] = WtConfig{tn, ks, stg, sp, rb};
           fclose(fp);
         }
       }
@@ -915,27 +928,23 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
   } else if (!have) {
     // ---- candidate list ----
     std::vector<WtConfig> cand;
-    auto add = [&](int tn, int ks, int budget, int split) {
+    auto add = [&](int tn, int ks, int budget, int split, int rb = 1) {
       if (tn > round16(T)) tn = round16(T);
       if (tn > 256) tn = 256;
-      const int stage = ks * (WT_WBLK + tn * 128);
+      const int stage = ks * (rb * WT_WBLK + tn * 128);
       int stg = budget / stage;
       if (stg > 6) stg = 6;
       if (stg < 2 || (long)stg * stage < (long)WT_EPI_TOK * WT_ROWS * 4) return;
       split = cdiv(kb_total, cdiv(kb_total, split < 1 ? 1 : split));
-      WtConfig c{tn, ks, stg, split};
+      WtConfig c{tn, ks, stg, split, rb};
       if (!fits(c)) return;
       for (const auto& o : cand)
-        if (o.TN == c.TN && o.KS == c.KS && o.stages == c.stages && o.split == c.split) return;
+        if (o.TN == c.TN && o.KS == c.KS && o.stages == c.stages && o.split == c.split && o.rb == c.rb) return;
       cand.push_back(c);
     };
     WtConfig model;
     gemm_wt_auto(T, row_blocks, K, allow_split, &model, sm_count);
-    {
-      static const bool two_only = getenv("B200_WT_TWO_PER_SM") && atoi(getenv("B200_WT_TWO_PER_SM")) != 0;
-      const long model_smem = (long)model.stages * model.KS * (WT_WBLK + model.TN * 128);
-      if (fits(model) && (!two_only || model_smem <= 110 * 1024)) cand.push_back(model);
-    }
+    if (fits(model)) cand.push_back(model);
     int tns[8], n_tn = 0;
     if (T <= 96) {
       tns[n_tn++] = round16(T);
@@ -954,17 +963,21 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
         sps[1] = a < 1 ? 1 : (a > cap_k ? cap_k : a);
         sps[2] = b < 1 ? 1 : (b > cap_k ? cap_k : b);
       }
-      // B200_WT_TWO_PER_SM=1 (experiment): only configurations that leave room for a second CTA on the SM, so the
-      // NEXT kernel's prologue and weight prefetch can overlap this kernel's tail under PDL
-      static const bool two_only = getenv("B200_WT_TWO_PER_SM") && atoi(getenv("B200_WT_TWO_PER_SM")) != 0;
+      // (measured and discarded: restricting the list to <= 110 KB configurations so that the NEXT kernel's prologue
+      // can always co-reside under PDL made the C2 prefill 2-5 % slower)
       for (int sp : sps) {
-        if (!two_only) add(tn, 2, 208 * 1024, sp);  // one CTA per SM, 256-byte weight-row bursts
+        add(tn, 2, 208 * 1024, sp);  // one CTA per SM, 256-byte weight-row bursts
         add(tn, 1, 110 * 1024, sp);  // two CTAs per SM
-        if (two_only) add(tn, 2, 110 * 1024, sp);
+      }
+      // large GEMMs (more CTAs than two waves even with 256-row CTAs): two row blocks per CTA share the token tile
+      if (row_blocks >= 2 && (long)(row_blocks / 2) * cdiv(T, tn) >= 2L * sm_count) {
+        add(tn, 1, 208 * 1024, 1, 2);
+        add(tn, 1, 110 * 1024, 1, 2);
       }
     }
     if (cand.empty()) {
       gemm_wt_auto(T, row_blocks, K, false, &model, sm_count);
+      B200_REQUIRE(fits(model), "gemm_wt: the partial-tile buffer (%ld B) is too small for T=%d N=%d", partial_bytes, T, N);
       cand.push_back(model);
     }
     // ---- time them (the tuning launches never add a residual: the output stays idempotent) ----
@@ -1039,14 +1052,14 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
       }
     cfg = cand[pick];
     if (getenv("B200_WT_TUNE_LOG"))
-      fprintf(stderr, "[gemm_wt tune] T=%d N=%d K=%d mode=%d -> TN=%d KS=%d stages=%d split=%d (%.1f us, %zu candidates)\n",
-              T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, ms[pick] * 1000.f, cand.size());
+      fprintf(stderr, "[gemm_wt tune] T=%d N=%d K=%d mode=%d -> TN=%d KS=%d stages=%d split=%d rb=%d (%.1f us, %zu candidates)\n",
+              T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, cfg.rb, ms[pick] * 1000.f, cand.size());
     std::lock_guard<std::mutex> g(mu);
     cache[key] = cfg;
     if (const char* path = tune_file()) {
       if (FILE* fp = fopen(path, "a")) {
-        fprintf(fp, "%d %d %d %d %d %d %d %d %d\n", key.tb, key.N, key.K, key.mode, key.split_ok, cfg.TN, cfg.KS,
-                cfg.stages, cfg.split);
+        fprintf(fp, "%d %d %d %d %d %d %d %d %d %d\n", key.tb, key.N, key.K, key.mode, key.split_ok, cfg.TN, cfg.KS,
+                cfg.stages, cfg.split, cfg.rb);
         fclose(fp);
       }
     }
@@ -1054,6 +1067,7 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
   // a cached configuration was tuned for a token count in the same 64-bucket: re-check the bounds
   if (cfg.TN > round16(T)) cfg.TN = round16(T);
   while (cfg.split > 1 && !fits(cfg)) cfg.split = cdiv(kb_total, cdiv(kb_total, cfg.split - 1));
+  B200_REQUIRE(fits(cfg), "gemm_wt: the partial-tile buffer (%ld B) is too small for T=%d N=%d", partial_bytes, T, N);
   if (split_out) *split_out = cfg.split;
   return gemm_wt(X, ldx, W, bias, residual, ldr, C, ldc, partial, T, N, K, epilogue, mode, inter, cfg, 0, st, ext);
 }
@@ -1101,7 +1115,8 @@ int b200_gemm_wt(const void* X, long ldx, const void* W, const void* bias, const
                  int mode, int inter, const int* cfg4, unsigned flags, void* stream) {
   WtConfig c;
   if (cfg4 && cfg4[0] > 0) {
-    c.TN = cfg4[0]; c.KS = cfg4[1]; c.stages = cfg4[2]; c.split = cfg4[3];
+    c.TN = cfg4[0]; c.KS = cfg4[1] % 100; c.stages = cfg4[2]; c.split = cfg4[3];
+    c.rb = cfg4[1] >= 100 ? 2 : 1;   // (tests / probes: KS + 100 selects two row blocks per CTA)
   } else {
     const int rbs = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, 128);
     gemm_wt_auto(T, rbs, K, mode == B200_WT_PARTIAL, &c, 148);

@@ -151,7 +151,10 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
                                       bf16* __restrict__ vc, int T, int ctx0, int cap, int n_heads,
                                       int n_kv, int hd, float q_scale, bf16* __restrict__ vt,
                                       int t_ld, const KvRef* __restrict__ ref, int layer,
-                                      bf16* __restrict__ kws) {
+                                      bf16* __restrict__ kws, const int2* __restrict__ tok_loc,
+                                      long row_stride) {
+  // tok_loc (batched prefill of several sequences in one pass): token t belongs to pool row tok_loc[t].x and
+  // lands at cache position tok_loc[t].y; kc / vc then point at row 0 and rows are row_stride elements apart
   pdl_prologue();
   if (ref) {  // cache location read from device memory: a captured graph stays valid when the pool moves
     kc = ref->k0 + (long)layer * ref->layer_stride;
@@ -172,9 +175,12 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
     const float x1 = bf2f(base[j]), x2 = bf2f(base[j + half]);
     if (slot >= n_heads + n_kv) {  // V: copy into the cache
       const int kvh = slot - n_heads - n_kv;
-      bf16* dst = vc + ((long)kvh * cap + ctx0 + t) * hd;
-      dst[j] = base[j];
-      dst[j + half] = base[j + half];
+      const int2 loc = tok_loc ? tok_loc[t] : make_int2(0, ctx0 + t);
+      if (loc.x >= 0) {   // (row -1: a padding token of a batched prefill)
+        bf16* dst = vc + (long)loc.x * row_stride + ((long)kvh * cap + loc.y) * hd;
+        dst[j] = base[j];
+        dst[j + half] = base[j + half];
+      }
       if (vt) {  // V^T [kv head][dim][token] for the pipelined attention kernel (attention_fa.cu)
         vt[((long)kvh * hd + j) * t_ld + t] = base[j];
         vt[((long)kvh * hd + j + half) * t_ld + t] = base[j + half];
@@ -191,9 +197,12 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
       base[j + half] = f2bf(q_scale != 0.f ? o2 * q_scale : o2);
     } else {
       const int kvh = slot - n_heads;
-      bf16* dst = kc + ((long)kvh * cap + ctx0 + t) * hd;
-      dst[j] = f2bf(o1);
-      dst[j + half] = f2bf(o2);
+      const int2 loc = tok_loc ? tok_loc[t] : make_int2(0, ctx0 + t);
+      if (loc.x >= 0) {
+        bf16* dst = kc + (long)loc.x * row_stride + ((long)kvh * cap + loc.y) * hd;
+        dst[j] = f2bf(o1);
+        dst[j + half] = f2bf(o2);
+      }
       if (kws) {  // the prompt chunk's rotated keys [kv head][token][dim] for the pipelined attention
         bf16* d2 = kws + ((long)kvh * T + t) * hd;
         d2[j] = f2bf(o1);
@@ -341,14 +350,15 @@ int vision_rope(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, 
 
 int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int* axis_sel,
                    void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv, int hd,
-                   cudaStream_t st, float q_scale, void* vt, int t_ld, const KvRef* ref, int layer, void* kws) {
-  B200_REQUIRE(T > 0 && ctx0 >= 0 && (ref || ctx0 + T <= cap), "mrope_kv_write: T=%d ctx0=%d cap=%d", T,
+                   cudaStream_t st, float q_scale, void* vt, int t_ld, const KvRef* ref, int layer, void* kws,
+                   const void* tok_loc, long row_stride) {
+  B200_REQUIRE(T > 0 && ctx0 >= 0 && (ref || tok_loc || ctx0 + T <= cap), "mrope_kv_write: T=%d ctx0=%d cap=%d", T,
                ctx0, cap);
   B200_REQUIRE(!vt || t_ld >= T, "mrope_kv_write: V^T pitch %d < T %d", t_ld, T);
   const long total = (long)T * (n_heads + 2 * n_kv) * (hd / 2);
   B200_CUDA(launch_pdl(mrope_kv_write_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, (bf16*)qkv, pos3, inv_freq,
                        axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd, q_scale, (bf16*)vt, t_ld, ref,
-                       layer, (bf16*)kws));
+                       layer, (bf16*)kws, (const int2*)tok_loc, row_stride));
   return B200_OK;
 }
 
@@ -527,7 +537,7 @@ int b200_mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const
                         void* kc, void* vc, int T, int ctx0, int cap, int n_heads, int n_kv,
                         int hd, void* st) {
   return mrope_kv_write(qkv, pos3, inv_freq, axis_sel, kc, vc, T, ctx0, cap, n_heads, n_kv, hd,
-                        (cudaStream_t)st, 0.f, nullptr, 0, nullptr, 0, nullptr);
+                        (cudaStream_t)st, 0.f, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
 }
 int b200_vision_qkv_post(void* qkv, const int* pos_hw, const float* inv_freq, int n_tok, int n_heads,
                          int hd, float scale, void* vt, int t_ld, void* st) {

@@ -208,8 +208,9 @@ __global__ void tower_embed_kernel(const float* __restrict__ patch, const bf16* 
 }
 
 // ---- fp32 attention on the CUDA cores (exact fp32 softmax; flash-style running max / sum) -----------
-// Register-tiled: CTA = 128 query rows of one head of one segment, 256 threads as 16 (query groups of 8 rows) x
-// 16 (key groups of 4 keys / dim lanes).  Per 64-key tile:
+// Register-tiled: CTA = 64 query rows of one head of one segment, 128 threads as 8 (query groups of 8 rows) x
+// 16 (key groups of 4 keys / dim lanes); 65 KB of shared memory -> three CTAs per SM, and CLIP's 8 x 16 x 10 = 1280
+// CTAs fill 2.9 of 3 waves (128-row CTAs at two per SM wasted 28 % of the third wave).  Per 64-key tile:
 //   S[8 x 4] per thread = Q^T . K^T out of shared memory (both stored dim-major so that a thread's 8 queries /
 //   4 keys are one or two 16-byte loads and the 16 lanes of a key group read 256 contiguous bytes: 32 FMAs per
 //   3 shared loads), running max over the 16 lanes of a query group (4 shuffles per row), p = exp(s - m) written
@@ -231,7 +232,9 @@ struct AttnF32P {
   float scale;
 };
 
-constexpr int AF_BQ = 128, AF_BK = 64, AF_PP = AF_BQ + 4;  // P^T row pitch: +4 floats -> conflict-free 16-byte stores
+constexpr int AF_BQ = 64, AF_BK = 64, AF_THREADS = AF_BQ * 2;
+constexpr int AF_PP = AF_BQ + 4;  // P^T row pitch: +4 floats; with rows stored as (key % 4) * 16 + key / 4 the 16 lanes of
+                                  // a key group write consecutive rows -> conflict-free 16-byte stores
 
 template <int HDP>
 static constexpr size_t attn_f32_smem() {
@@ -239,8 +242,8 @@ static constexpr size_t attn_f32_smem() {
 }
 
 template <int HDP>
-__global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
-  constexpr int BQ = AF_BQ, BK = AF_BK, PP = AF_PP, DPT = HDP / 16;
+__global__ void __launch_bounds__(AF_THREADS) attention_f32_kernel(const AttnF32P p) {
+  constexpr int BQ = AF_BQ, BK = AF_BK, PP = AF_PP, DPT = HDP / 16, NT = AF_THREADS;
   extern __shared__ __align__(16) float af_sm[];
   float* Qt = af_sm;               // [HDP][BQ]  q * scale, dim-major
   float* Kt = Qt + HDP * BQ;       // [HDP][BK]
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
   const float* kb = p.k + (long)seg * p.k_seg * p.k_ts + (long)kvh * p.k_hs;
   const float* vb = p.v + (long)seg * p.k_seg * p.v_ts + (long)kvh * p.v_hs;
   // Q^T: lane <-> query row (conflict-free transposed stores)
-  for (int i = tid; i < BQ * (HDP / 4); i += 256) {
+  for (int i = tid; i < BQ * (HDP / 4); i += NT) {
     const int r = i % BQ, c = i / BQ;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q0 + r < p.Lq && c < hd4) v = *reinterpret_cast<const float4*>(qb + (long)(q0 + r) * p.q_ts + c * 4);
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
   }
   for (int j0 = 0; j0 < p.S; j0 += BK) {
     __syncthreads();
-    for (int i = tid; i < BK * (HDP / 4); i += 256) {   // K^T: lane <-> key
+    for (int i = tid; i < BK * (HDP / 4); i += NT) {   // K^T: lane <-> key
       const int r = i % BK, c = i / BK;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j0 + r < p.S && c < hd4) v = *reinterpret_cast<const float4*>(kb + (long)(j0 + r) * p.k_ts + c * 4);
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
       Kt[(c * 4 + 2) * BK + r] = v.z;
       Kt[(c * 4 + 3) * BK + r] = v.w;
     }
-    for (int i = tid; i < BK * (HDP / 4); i += 256) {   // V: row-major
+    for (int i = tid; i < BK * (HDP / 4); i += NT) {   // V: row-major
       const int r = i / (HDP / 4), c = i % (HDP / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j0 + r < p.S && c < hd4) v = *reinterpret_cast<const float4*>(vb + (long)(j0 + r) * p.v_ts + c * 4);
@@ -334,17 +337,18 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32P p) {
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float* dst = Pt + (tx * 4 + j) * PP + ty * 8;
+    for (int j = 0; j < 4; ++j) {   // key tx * 4 + j lives in P^T row j * 16 + tx
+      float* dst = Pt + (j * 16 + tx) * PP + ty * 8;
       *reinterpret_cast<float4*>(dst) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4][j], s[5][j], s[6][j], s[7][j]);
     }
     __syncwarp();   // rows ty*8.. of P^T are written and read by the same half-warp only
     // ---- O += P . V ----
 #pragma unroll 4
-    for (int j = 0; j < BK; ++j) {
-      const float4 pa = *reinterpret_cast<const float4*>(Pt + j * PP + ty * 8);
-      const float4 pc = *reinterpret_cast<const float4*>(Pt + j * PP + ty * 8 + 4);
+    for (int r = 0; r < BK; ++r) {
+      const int j = (r & 15) * 4 + (r >> 4);   // the key stored in P^T row r
+      const float4 pa = *reinterpret_cast<const float4*>(Pt + r * PP + ty * 8);
+      const float4 pc = *reinterpret_cast<const float4*>(Pt + r * PP + ty * 8 + 4);
       const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pc.x, pc.y, pc.z, pc.w};
       float vv[DPT];
 #pragma unroll
@@ -388,7 +392,7 @@ static int attn_f32_launch(const AttnF32P& p, dim3 grid, cudaStream_t st) {
     B200_CUDA(cudaFuncSetAttribute(attention_f32_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)attn_f32_smem<HDP>()));
   }
-  attention_f32_kernel<HDP><<<grid, 256, attn_f32_smem<HDP>(), st>>>(p);
+  attention_f32_kernel<HDP><<<grid, AF_THREADS, attn_f32_smem<HDP>(), st>>>(p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -120,6 +120,19 @@ class Engine:
                                              rope_delta, N.ptr(all_logits), self.s),
                 "engine_prefill")
 
+    def prefill_batch(self, embeds: torch.Tensor, pos3: torch.Tensor, seq_len, rows):
+        """several FRESH prompts in one pass over the weights (reference `PromptProcessingBatch`): embeds
+        (sum round8(T_g), hidden) bf16 concatenated along the token axis with every sequence padded to a multiple
+        of 8 tokens, pos3 (3, sum round8(T_g)) int32 device, sequence g fills pool row rows[g]; the first tokens land
+        in the token log in order"""
+        seq_len = np.ascontiguousarray(np.asarray(seq_len, dtype=np.int32))
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int32))
+        T = int(((seq_len + 7) // 8 * 8).sum())     # every sequence padded to a multiple of 8 tokens
+        assert embeds.shape[0] == T and pos3.shape[-1] == T and len(rows) == len(seq_len)
+        self.ensure_workspace(tokens=T)
+        N.check(self.lib.b200_engine_prefill_batch(self.h, embeds.data_ptr(), pos3.data_ptr(), len(seq_len),
+                                                   seq_len.ctypes.data, rows.ctypes.data, self.s), "engine_prefill_batch")
+
     def decode(self, n_steps: int, force_tokens: Optional[np.ndarray] = None):
         fp = 0
         if force_tokens is not None:

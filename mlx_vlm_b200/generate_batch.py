@@ -172,7 +172,7 @@ class BatchGenerator:
                  prefill_batch_size: int = DEFAULT_PREFILL_BATCH_SIZE,
                  prefill_step_size: Optional[int] = None, compute_logprobs: bool = False,
                  top_logprobs_k: int = 0, logits_processors=None, greedy_sampling: bool = False,
-                 decode_slice: int = 16, **unsupported):
+                 decode_slice: int = 16, batched_prefill: bool = True, **unsupported):
         for k in ("kv_bits", "kv_key_bits", "kv_value_bits", "draft_model", "apc_manager", "prompt_cache"):
             if unsupported.pop(k, None) is not None:
                 raise NotImplementedError(f"BatchGenerator: `{k}` is outside the B200 hot-path scope")
@@ -189,6 +189,7 @@ class BatchGenerator:
         self.prefill_batch_size = prefill_batch_size
         self.prefill_step_size = prefill_step_size
         self.decode_slice = max(1, int(decode_slice))
+        self.batched_prefill = bool(batched_prefill)
         self.tokenizer = processor.tokenizer if hasattr(processor, "tokenizer") else processor
         from .utils import StoppingCriteria
         if getattr(self.tokenizer, "stopping_criteria", None) is None:
@@ -333,6 +334,42 @@ class BatchGenerator:
         self._prompt_time_counter += dt
         return PromptProgress(uid=row.uid, prompt_tokens=len(row.ids), prompt_time=dt,
                               prompt_tps=len(row.ids) / dt if dt > 0 else 0.0)
+
+    def _prefill_group(self, rows: List[_Row]) -> List[PromptProgress]:
+        """`PromptProcessingBatch` (ar.py:1581-2175): the rows admitted together are prefilled in ONE pass over the
+        weights (tokens concatenated, block-diagonal causal attention, every token scattered to its own pool row);
+        embeddings (vision tower + merge) are still produced per request."""
+        model, lm, eng = self.model, self.model.language_model, self.model.engine
+        tic = time.perf_counter()
+        ids_l, emb_l, pos_l, del_l = [], [], [], []
+        for row in rows:
+            kw = dict(row.kwargs)
+            ids = np.asarray([row.ids])
+            emb = kw.pop("inputs_embeds", None)
+            pos, deltas = kw.pop("position_ids", None), kw.pop("rope_deltas", None)
+            if emb is None:
+                out = model.get_input_embeddings(ids, kw.pop("pixel_values", None), mask=kw.pop("mask", None), **kw)
+                emb, pos, deltas = out.inputs_embeds, out.position_ids, out.rope_deltas
+            row.reserve = emb.shape[1] + row.max_tokens + 1
+            row.delta = int(np.asarray(deltas).reshape(-1)[0]) if deltas is not None else 0
+            ids_l.append(ids); emb_l.append(emb); pos_l.append(pos); del_l.append(deltas)
+        pool = self._pool_for(max(r.reserve for r in rows))
+        base = len(self._active)
+        for i, row in enumerate(rows):
+            row.cache = lm.make_cache_row(pool, base + i)
+        toks = lm.prefill_rows(ids_l, emb_l, [r.cache for r in rows], pos_l, del_l,
+                               reserve_tokens=max(r.reserve for r in rows))
+        dt = time.perf_counter() - tic
+        out = []
+        for row, tok in zip(rows, toks):
+            row.last_token, row.n_decoded = tok, 1
+            row.ctx = int(row.cache[0].offset)
+            row.buffer.append((tok, 0.0))
+            self._prompt_tokens_counter += len(row.ids)
+            out.append(PromptProgress(uid=row.uid, prompt_tokens=len(row.ids), prompt_time=dt / len(rows),
+                                      prompt_tps=len(row.ids) * len(rows) / dt if dt > 0 else 0.0))
+        self._prompt_time_counter += dt
+        return out
 
     def _sample(self, logits: torch.Tensor) -> Tuple[int, float]:
         # torch ops on the engine's stream: ordered after the step that wrote `logits`
@@ -490,7 +527,14 @@ class BatchGenerator:
         n_admit = min(room, self.prefill_batch_size, len(self._unprocessed_sequences))
         admitted = []
         self._admitting = 0
-        for _ in range(max(0, n_admit)):
+        group = (self._lockstep and n_admit >= 2 and self.greedy_sampling and not self.compute_logprobs
+                 and hasattr(self.model.language_model, "prefill_rows") and self.batched_prefill
+                 and (self.prefill_step_size is None
+                      or all(len(r.ids) <= self.prefill_step_size + 1 for r in self._unprocessed_sequences[:n_admit])))
+        if group:
+            admitted = [self._unprocessed_sequences.pop(0) for _ in range(n_admit)]
+            prompt_responses.extend(self._prefill_group(admitted))
+        for _ in range(0 if group else max(0, n_admit)):
             row = self._unprocessed_sequences.pop(0)
             prompt_responses.append(self._prefill(row))
             admitted.append(row)

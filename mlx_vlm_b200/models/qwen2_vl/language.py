@@ -203,6 +203,62 @@ class LanguageModel:
             c.offset += L
         return LanguageModelOutput(logits=logits)
 
+    def prefill_rows(self, ids_list, embeds_list, caches, position_ids_list=None, rope_deltas_list=None,
+                     reserve_tokens: int = 0) -> List[int]:
+        """The reference's `PromptProcessingBatch` (ar.py:1581-2175) for FRESH prompts that live in rows of ONE
+        batched pool: all prompts are prefilled in one pass over the weights (tokens concatenated, block-diagonal
+        causal attention, every token scattered to its own row / position of the pool).  `caches[g]` are the
+        per-layer row caches of prompt g (`make_cache_row`); returns the first greedy token of every prompt
+        (host ints; one device->host fetch for the whole group)."""
+        eng = self._engine()
+        n = len(ids_list)
+        assert n == len(embeds_list) == len(caches) and n > 0
+        pools = {id(c[0]._pool) for c in caches}
+        if len(pools) != 1 or any(int(c[0].offset) != 0 for c in caches):
+            raise ValueError("prefill_rows: fresh prompts in rows of one pool only")
+        lens, pos, embs, deltas = [], [], [], []
+        for g in range(n):
+            ids = _np(ids_list[g])
+            if ids.ndim == 1:
+                ids = ids[None]
+            L = ids.shape[1]
+            self._rope_deltas, self._position_ids = None, None
+            p3, d0 = self.resolve_position_ids(
+                ids, 0, None if position_ids_list is None else position_ids_list[g], None, None, None,
+                None if rope_deltas_list is None else rope_deltas_list[g])
+            if rope_deltas_list is not None and rope_deltas_list[g] is not None:
+                d0 = int(np.asarray(rope_deltas_list[g]).reshape(-1)[0])
+            e = embeds_list[g].reshape(-1, embeds_list[g].shape[-1])
+            assert e.shape[0] == L and e.dtype == torch.bfloat16 and e.is_cuda
+            pad = (-L) % 8            # sequences start at multiples of 8 tokens in the concatenated batch
+            p3 = np.asarray(p3)[:, 0, :].astype(np.int32)
+            lens.append(L)
+            pos.append(np.ascontiguousarray(np.pad(p3, ((0, 0), (0, pad)))))
+            embs.append((e, pad))
+            deltas.append(d0)
+        need = max(max(lens), reserve_tokens)
+        self._bind(caches[0], need)
+        pos3 = torch.from_numpy(np.ascontiguousarray(np.concatenate(pos, axis=1)))
+        with torch.cuda.stream(eng.stream):
+            pos3 = pos3.to(eng.device)
+            parts = []
+            for e, pad in embs:
+                parts.append(e)
+                if pad:
+                    parts.append(torch.zeros(pad, e.shape[1], dtype=e.dtype, device=e.device))
+            emb = torch.cat(parts, 0) if len(parts) > 1 else parts[0].contiguous()
+        start = eng.tokens_launched
+        eng.prefill_batch(emb, pos3, lens, [int(c[0]._row or 0) for c in caches])
+        for g in range(n):
+            for c in caches[g]:
+                c.offset += lens[g]
+        host = torch.empty(n, dtype=torch.int32).pin_memory()
+        eng.fetch_tokens(start, n, host)
+        eng.stream.synchronize()
+        self._rope_deltas, self._position_ids = None, None
+        self.last_prefill_deltas = deltas
+        return [int(t) for t in host]
+
     def resolve_position_ids(self, ids_host: np.ndarray, cache_offset: int, position_ids=None, mask=None,
                              image_grid_thw=None, video_grid_thw=None, rope_deltas_kw=None):
         """Position bookkeeping of `LanguageModel.__call__` (reference language.py:404-518), pure host

@@ -240,3 +240,40 @@ def test_server_loop_streams_concurrent_requests():
     for i in range(3):
         _same_until_tie(got[i], want[i][0], want[i][1], f"server request {i}")
     assert model.engine.device_error() == 0
+
+
+def test_batched_prefill_equals_single_prefills():
+    """`b200_engine_prefill_batch` (reference PromptProcessingBatch, ar.py:1581-2175): four prompts of different
+    lengths (two with an image) prefilled in ONE pass land in their pool rows exactly like four single prefills:
+    K/V rows to the per-op bar, first tokens equal up to a near-tie; the following lock-step steps run on them."""
+    c, W, model, req = _build("wide2", 10, (56, 56))
+    lm, eng = model.language_model, model.engine
+    rows_req = _requests(c, req, 4)
+    # reference: every prompt alone in a single-row cache
+    singles, firsts = [], []
+    for ids, kw, _ in rows_req:
+        emb = model.get_input_embeddings(ids, kw.get("pixel_values"), image_grid_thw=kw.get("image_grid_thw"))
+        cache = lm.make_cache()
+        lm._rope_deltas, lm._position_ids = None, None
+        lm(ids, inputs_embeds=emb.inputs_embeds, cache=cache, position_ids=emb.position_ids,
+           rope_deltas=emb.rope_deltas, logits_to_keep=1)
+        eng.stream.synchronize()
+        firsts.append(int(eng.token_log_view()[(eng.tokens_launched - 1) % eng.token_log_capacity]))
+        lp = eng.logprobs_view().float().cpu().clone()
+        singles.append((cache, emb, lp))
+    rows, caches = lm.make_batch_cache(4, 256)
+    row_caches = [lm.make_cache_row(rows.pool, b) for b in range(4)]
+    toks = lm.prefill_rows([r[0] for r in rows_req], [s[1].inputs_embeds for s in singles], row_caches,
+                           [s[1].position_ids for s in singles], [s[1].rope_deltas for s in singles], reserve_tokens=256)
+    eng.stream.synchronize()
+    for b, (ids, _, _) in enumerate(rows_req):
+        L = ids.shape[1]
+        assert row_caches[b][0].offset == L
+        for layer in (0, 1):
+            k1 = singles[b][0][layer].keys[0, :, :L].float().cpu()
+            v1 = singles[b][0][layer].values[0, :, :L].float().cpu()
+            k2 = row_caches[b][layer].keys[0, :, :L].float().cpu()
+            v2 = row_caches[b][layer].values[0, :, :L].float().cpu()
+            assert rl2(k2, k1) <= 1e-3 and rl2(v2, v1) <= 1e-3, (b, layer, rl2(k2, k1), rl2(v2, v1))
+        assert _token_ok(toks[b], singles[b][2]), (b, toks[b], firsts[b])
+    print("batched prefill first tokens", toks, "single", firsts)

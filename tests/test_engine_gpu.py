@@ -307,17 +307,20 @@ def test_batch_generator_rows_equal_single_requests():
             assert got[u] == w, (slice_, u, got[u], w)
 
 
-def test_two_images_of_different_size_in_one_prompt():
+@pytest.mark.parametrize("sizes", [((56, 84), (84, 56)), ((84, 84), (56, 56))])
+def test_two_images_of_different_size_in_one_prompt(sizes):
     """Multi-image request (the case of the reference's TestMultiImageMRoPE, test_models.py:11866):
     two images with different grids -> per-image (block-diagonal) vision attention, features
-    concatenated, merge by cumsum(mask)-1, position ids / delta bit-exact, prefill logits in noise."""
+    concatenated, merge by cumsum(mask)-1, position ids / delta bit-exact, prefill logits in noise.
+    The second case starts its second image at patch 36 (not a multiple of 8): the pipelined attention
+    kernel cannot load V^T tiles there and the tower must take the fallback kernel."""
     from mlx_vlm_b200.models.cache import make_prompt_cache
     from oracle import qwen2vl as O
     c, W, model, _ = _build("tiny", 8, (56, 56))
     eng = model.engine
     rng = np.random.default_rng(7)
-    imgs = [rng.integers(0, 256, size=(3, 56, 84), dtype=np.uint8),
-            rng.integers(0, 256, size=(3, 84, 56), dtype=np.uint8)]
+    imgs = [rng.integers(0, 256, size=(3,) + sizes[0], dtype=np.uint8),
+            rng.integers(0, 256, size=(3,) + sizes[1], dtype=np.uint8)]
     pvs, grids = zip(*[O.preprocess_image(im, c.vision) for im in imgs])
     pv = np.concatenate(pvs, axis=0)
     grid = np.asarray(grids, dtype=np.int64)
