@@ -177,8 +177,6 @@ int gemm_bf16_tn(const void* A, long lda, const void* W, const void* bias, const
 // weight-major tcgen05 GEMM (gemm_wt.cu) + the row op that finishes its split-K partials
 struct WtConfig {
   int TN, KS, stages, split;
-  int rb = 1;   // weight row blocks (128 rows) per CTA: 2 = two accumulators share one token tile (large GEMMs:
-                // the main loop is bounded by L2 -> SM bytes per flop, and this halves the token-operand traffic)
 };
 // extension for the fp32-accurate (split bf16) GEMMs of the LLaVA / Idefics2 towers
 struct WtExt {

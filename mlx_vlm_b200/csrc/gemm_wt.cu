@@ -51,7 +51,6 @@ struct WtParams {
   long ldc, ldr;
   int T, N, K;
   int TN, KS, n_stages;
-  int RB;            // weight row blocks (128 rows each) per CTA: 1, or 2 sharing one token tile (two accumulators)
   int kb_per_split;
   int epilogue, mode;
   int inter;
@@ -191,8 +190,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool swiglu = !TOWER && (p.mode == B200_WT_SWIGLU);
   const int rb = blockIdx.x;
-  const int rows_blk = swiglu ? 64 : WT_ROWS;   // output features (SwiGLU: channels) of one row block
-  const int n0 = rb * rows_blk * p.RB;          // first output feature (SwiGLU: channel) of the tile
+  const int n0 = rb * (swiglu ? 64 : WT_ROWS);  // first output feature (SwiGLU: channel) of the tile
   const int t0 = blockIdx.y * p.TN;
   const int split = blockIdx.z;
   const int kb_total = (p.K + WT_BK - 1) / WT_BK;
@@ -200,10 +198,10 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   const int kb1 = min(kb_total, kb0 + p.kb_per_split);
   const int n_it = (kb1 - kb0 + p.KS - 1) / p.KS;
   const int xblk = p.TN * 128;                      // bytes of one token k-block tile
-  const int stage_bytes = p.KS * (p.RB * WT_WBLK + xblk);
+  const int stage_bytes = p.KS * (WT_WBLK + xblk);
   const int NS = p.n_stages;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.RB * p.TN) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.TN) tmem_cols <<= 1;
 
   w_pdl_launch();  // the next kernel may start its prologue / weight prefetch as SM resources free up
 
@@ -214,25 +212,22 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       w_mbar_arrive(&full_bar[s]);
       return;
     }
-    w_mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (p.RB * WT_WBLK + xblk));
+    w_mbar_expect_tx(&full_bar[s], (uint32_t)cnt * (WT_WBLK + xblk));
     for (int j = 0; j < cnt; ++j) {
       int kbw = kb0 + it * p.KS + j;
       if (p.kb_w > 0) kbw %= p.kb_w;
       const int kc = kbw * WT_BK;
-      for (int r = 0; r < p.RB; ++r) {   // rows beyond N are zero-filled by the tensor map
-        uint8_t* dst = sW + (j * p.RB + r) * WT_WBLK;
-        if (swiglu) {
-          w_tma_2d(dst, &tmW, &full_bar[s], kc, n0 + r * 64);
-          w_tma_2d(dst + 64 * 128, &tmW, &full_bar[s], kc, p.inter + n0 + r * 64);
-        } else {
-          w_tma_2d(dst, &tmW, &full_bar[s], kc, n0 + r * WT_ROWS);
-        }
+      if (swiglu) {
+        w_tma_2d(sW + j * WT_WBLK, &tmW, &full_bar[s], kc, n0);
+        w_tma_2d(sW + j * WT_WBLK + 64 * 128, &tmW, &full_bar[s], kc, p.inter + n0);
+      } else {
+        w_tma_2d(sW + j * WT_WBLK, &tmW, &full_bar[s], kc, n0);
       }
     }
   };
   auto issue_x = [&](int it, int s) {
     if (p.flags & 2u) return;
-    uint8_t* sX = ring + (long)s * stage_bytes + p.KS * p.RB * WT_WBLK;
+    uint8_t* sX = ring + (long)s * stage_bytes + p.KS * WT_WBLK;
     const int cnt = min(p.KS, kb1 - kb0 - it * p.KS);
     for (int j = 0; j < cnt; ++j)
       w_tma_2d(sX + j * xblk, &tmX, &full_bar[s], (kb0 + it * p.KS + j) * WT_BK, t0);
@@ -287,14 +282,13 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         w_fence_after();
         if (!(p.flags & 1u)) {
           const uint32_t w_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes));
-          const uint32_t x_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes + p.KS * p.RB * WT_WBLK));
+          const uint32_t x_lo = w_desc_lo(w_smem_u32(ring + (long)s * stage_bytes + p.KS * WT_WBLK));
           const int cnt = min(p.KS, kb1 - kb0 - it * p.KS);
           for (int j = 0; j < cnt; ++j) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              for (int r = 0; r < p.RB; ++r)   // the row blocks of the CTA share the token operand
-                w_umma(tmem_base + (uint32_t)(r * p.TN), w_lo + (uint32_t)((j * p.RB + r) * (WT_WBLK >> 4) + kk * 2),
-                       x_lo + (uint32_t)(j * (xblk >> 4) + kk * 2), W_DESC_HI, idesc, acc);
+              w_umma(tmem_base, w_lo + (uint32_t)(j * (WT_WBLK >> 4) + kk * 2),
+                     x_lo + (uint32_t)(j * (xblk >> 4) + kk * 2), W_DESC_HI, idesc, acc);
               acc = 1;
             }
           }
@@ -311,18 +305,15 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   w_fence_after();
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;  // weight row of the tile == TMEM lane
+  float bias_v = 0.f;
+  if ((TOWER || p.mode == B200_WT_BF16) && p.bias && n0 + row < p.N) bias_v = bf2f(p.bias[n0 + row]);
   uint8_t* stg = ring;  // every TMA load has landed and every MMA has retired: the ring is free
   const int tid = threadIdx.x;
-  for (int rbi = 0; rbi < p.RB; ++rbi) {   // the row blocks of this CTA, one after the other
-  const int n0r = n0 + rbi * rows_blk;
-  const uint32_t tmem_r = tmem_base + (uint32_t)(rbi * p.TN);
-  float bias_v = 0.f;
-  if ((TOWER || p.mode == B200_WT_BF16) && p.bias && n0r + row < p.N) bias_v = bf2f(p.bias[n0r + row]);
   for (int c0 = 0; c0 < p.TN; c0 += WT_EPI_TOK) {
     const int cc = c0 + half * 32;
     if (cc < p.TN && !(p.flags & 1u)) {
       uint32_t a[32];
-      w_tmem_ld32(tmem_r + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, a);
+      w_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, a);
       if (!TOWER && p.mode == B200_WT_PARTIAL) {
         float* sf = reinterpret_cast<float*>(stg);
 #pragma unroll
@@ -352,7 +343,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 4; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 4, ch = idx & 15;
-          const int t = t0 + c0 + tl, n = n0r + ch * 8;
+          const int t = t0 + c0 + tl, n = n0 + ch * 8;
           if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
           const uint4 sv = *reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + ch * 8) * 2);
           const bool vec_ok = vec_all && n + 8 <= p.N;  // only the last chunk of an odd N goes element-wise
@@ -382,7 +373,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 2; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 3, ch = idx & 7;
-          const int t = t0 + c0 + tl, i = n0r + ch * 8;
+          const int t = t0 + c0 + tl, i = n0 + ch * 8;
           if (c0 + tl >= p.TN || t >= p.T || i >= p.inter) continue;
           float g[8], uu[8], o[8];
           unpack8(*reinterpret_cast<const uint4*>(stg + (tl * WT_ROWS + ch * 8) * 2), g);
@@ -398,7 +389,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 8; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 5, ch = idx & 31;
-          const int t = t0 + c0 + tl, n = n0r + ch * 4;
+          const int t = t0 + c0 + tl, n = n0 + ch * 4;
           if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
           float4 v = *reinterpret_cast<const float4*>(stg + (tl * WT_ROWS + ch * 4) * 4);
           if (p.mode == B200_WT_F32) {
@@ -439,7 +430,7 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int u = 0; u < 8; ++u) {
           const int idx = tid + 256 * u;
           const int tl = idx >> 5, ch = idx & 31;
-          const int t = t0 + c0 + tl, n = n0r + ch * 4;
+          const int t = t0 + c0 + tl, n = n0 + ch * 4;
           if (c0 + tl >= p.TN || t >= p.T || n >= p.N) continue;
           const float4 v = *reinterpret_cast<const float4*>(stg + (tl * WT_ROWS + ch * 4) * 4);
           float* dst = p.partial + ((long)split * p.T + t) * p.N + n;
@@ -453,7 +444,6 @@ gemm_wt_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       }
     }
     w_ebar();
-  }
   }
   w_fence_before();
   __syncthreads();
@@ -799,9 +789,7 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
     p.Csplit = ext->Csplit; p.ld_split = ext->ld_split; p.n_pad = ext->n_pad;
     if (ext->kb_w > 0) k_w = ext->k_w;
   }
-  B200_REQUIRE((cfg.rb == 1 || cfg.rb == 2) && cfg.rb * cfg.TN <= 512, "gemm_wt: rb=%d TN=%d", cfg.rb, cfg.TN);
-  p.RB = cfg.rb;
-  const int stage = cfg.KS * (cfg.rb * WT_WBLK + cfg.TN * 128);
+  const int stage = cfg.KS * (WT_WBLK + cfg.TN * 128);
   const size_t smem = (size_t)cfg.stages * stage + 1024;
   B200_REQUIRE(smem <= 227 * 1024 - 1024, "gemm_wt: %zu B of shared memory", smem);
   B200_REQUIRE((size_t)cfg.stages * stage >= (size_t)WT_EPI_TOK * WT_ROWS * 4, "gemm_wt: ring smaller than the epilogue staging tile");
@@ -823,7 +811,7 @@ int gemm_wt(const void* X, long ldx, const void* W, const void* bias, const void
   }
   const int row_blocks = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, WT_ROWS);
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(cdiv(row_blocks, cfg.rb), cdiv(T, cfg.TN), splits);
+  lc.gridDim = dim3(row_blocks, cdiv(T, cfg.TN), splits);
   lc.blockDim = dim3(256);
   lc.dynamicSmemBytes = smem;
   lc.stream = st;
@@ -901,11 +889,10 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
       file_read = true;
       if (const char* path = tune_file()) {
         if (FILE* fp = fopen(path, "r")) {
-          int tb, n, k, md, so, tn, ks, stg, sp, rb;
-          while (fscanf(fp, "%d %d %d %d %d %d %d %d %d %d", &tb, &n, &k, &md, &so, &tn, &ks, &stg, &sp, &rb) == 10)
-            if (tn >= 16 && tn <= 256 && tn % 16 == 0 && ks >= 1 && stg >= 2 && stg <= WT_MAX_STAGES && sp >= 1 &&
-                (rb == 1 || rb == 2))
-              cache[TuneKey{tb, n, k, md, so, dev}] = WtConfig{tn, ks, stg, sp, rb};
+          int tb, n, k, md, so, tn, ks, stg, sp;
+          while (fscanf(fp, "%d %d %d %d %d %d %d %d %d", &tb, &n, &k, &md, &so, &tn, &ks, &stg, &sp) == 9)
+            if (tn >= 16 && tn <= 256 && tn % 16 == 0 && ks >= 1 && stg >= 2 && stg <= WT_MAX_STAGES && sp >= 1)
+              cache[TuneKey{tb, n, k, md, so, dev}] = WtConfig{tn, ks, stg, sp};
           fclose(fp);
         }
       }
@@ -928,18 +915,18 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
   } else if (!have) {
     // ---- candidate list ----
     std::vector<WtConfig> cand;
-    auto add = [&](int tn, int ks, int budget, int split, int rb = 1) {
+    auto add = [&](int tn, int ks, int budget, int split) {
       if (tn > round16(T)) tn = round16(T);
       if (tn > 256) tn = 256;
-      const int stage = ks * (rb * WT_WBLK + tn * 128);
+      const int stage = ks * (WT_WBLK + tn * 128);
       int stg = budget / stage;
       if (stg > 6) stg = 6;
       if (stg < 2 || (long)stg * stage < (long)WT_EPI_TOK * WT_ROWS * 4) return;
       split = cdiv(kb_total, cdiv(kb_total, split < 1 ? 1 : split));
-      WtConfig c{tn, ks, stg, split, rb};
+      WtConfig c{tn, ks, stg, split};
       if (!fits(c)) return;
       for (const auto& o : cand)
-        if (o.TN == c.TN && o.KS == c.KS && o.stages == c.stages && o.split == c.split && o.rb == c.rb) return;
+        if (o.TN == c.TN && o.KS == c.KS && o.stages == c.stages && o.split == c.split) return;
       cand.push_back(c);
     };
     WtConfig model;
@@ -968,11 +955,6 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
       for (int sp : sps) {
         add(tn, 2, 208 * 1024, sp);  // one CTA per SM, 256-byte weight-row bursts
         add(tn, 1, 110 * 1024, sp);  // two CTAs per SM
-      }
-      // large GEMMs (more CTAs than two waves even with 256-row CTAs): two row blocks per CTA share the token tile
-      if (row_blocks >= 2 && (long)(row_blocks / 2) * cdiv(T, tn) >= 2L * sm_count) {
-        add(tn, 1, 208 * 1024, 1, 2);
-        add(tn, 1, 110 * 1024, 1, 2);
       }
     }
     if (cand.empty()) {
@@ -1052,14 +1034,14 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
       }
     cfg = cand[pick];
     if (getenv("B200_WT_TUNE_LOG"))
-      fprintf(stderr, "[gemm_wt tune] T=%d N=%d K=%d mode=%d -> TN=%d KS=%d stages=%d split=%d rb=%d (%.1f us, %zu candidates)\n",
-              T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, cfg.rb, ms[pick] * 1000.f, cand.size());
+      fprintf(stderr, "[gemm_wt tune] T=%d N=%d K=%d mode=%d -> TN=%d KS=%d stages=%d split=%d (%.1f us, %zu candidates)\n",
+              T, N, K, mode, cfg.TN, cfg.KS, cfg.stages, cfg.split, ms[pick] * 1000.f, cand.size());
     std::lock_guard<std::mutex> g(mu);
     cache[key] = cfg;
     if (const char* path = tune_file()) {
       if (FILE* fp = fopen(path, "a")) {
-        fprintf(fp, "%d %d %d %d %d %d %d %d %d %d\n", key.tb, key.N, key.K, key.mode, key.split_ok, cfg.TN, cfg.KS,
-                cfg.stages, cfg.split, cfg.rb);
+        fprintf(fp, "%d %d %d %d %d %d %d %d %d\n", key.tb, key.N, key.K, key.mode, key.split_ok, cfg.TN, cfg.KS,
+                cfg.stages, cfg.split);
         fclose(fp);
       }
     }
@@ -1115,8 +1097,7 @@ int b200_gemm_wt(const void* X, long ldx, const void* W, const void* bias, const
                  int mode, int inter, const int* cfg4, unsigned flags, void* stream) {
   WtConfig c;
   if (cfg4 && cfg4[0] > 0) {
-    c.TN = cfg4[0]; c.KS = cfg4[1] % 100; c.stages = cfg4[2]; c.split = cfg4[3];
-    c.rb = cfg4[1] >= 100 ? 2 : 1;   // (tests / probes: KS + 100 selects two row blocks per CTA)
+    c.TN = cfg4[0]; c.KS = cfg4[1]; c.stages = cfg4[2]; c.split = cfg4[3];
   } else {
     const int rbs = mode == B200_WT_SWIGLU ? cdiv(inter, 64) : cdiv(N, 128);
     gemm_wt_auto(T, rbs, K, mode == B200_WT_PARTIAL, &c, 148);
