@@ -39,6 +39,12 @@ def _cfg(kind):
             perceiver=OI.PerceiverCfg(num_key_value_heads=2, resampler_depth=2, resampler_head_dim=16,
                                       resampler_n_heads=4, resampler_n_latents=6),
             image_token_index=300)
+    if kind == "siglip_full_depth":   # all 27 SigLIP-SO400M layers + the 3-layer perceiver of Idefics2-8B
+        return OI.Idefics2Cfg(
+            vision=OI.SiglipCfg(image_size=980),
+            text=OI.MistralCfg(hidden_size=512, num_hidden_layers=2, intermediate_size=1024, num_attention_heads=4,
+                               num_key_value_heads=2, vocab_size=32003),
+            perceiver=OI.PerceiverCfg(), image_token_index=32001)
     # SigLIP-SO400M widths (1152 / 16 heads = head_dim 72, mlp 4304), 2 layers, 154 px images (11 x 11 patches on
     # a 70 x 70 position grid); the real perceiver geometry (16 heads of 96 over 4 kv heads, 64 latents)
     return OI.Idefics2Cfg(
@@ -48,7 +54,7 @@ def _cfg(kind):
         perceiver=OI.PerceiverCfg(resampler_depth=2), image_token_index=32001)
 
 
-@pytest.mark.parametrize("kind", ["tiny", "siglip_widths"])
+@pytest.mark.parametrize("kind", ["tiny", "siglip_widths", "siglip_full_depth"])
 def test_idefics2_features_merge_and_generate(kind):
     from oracle import idefics2 as OI
     from oracle.mlx_semantics import Rounder

@@ -108,7 +108,7 @@ def test_tower_ops_against_fp32_torch():
             assert e < 2e-5
 
 
-@pytest.mark.parametrize("kind", ["tiny", "clip_l_2layers"])
+@pytest.mark.parametrize("kind", ["tiny", "clip_l_2layers", "clip_l_full_depth"])
 def test_llava_features_merge_and_generate(kind):
     from oracle import llava as OL
     from oracle.mlx_semantics import Rounder
@@ -119,6 +119,11 @@ def test_llava_features_merge_and_generate(kind):
                     text=OL.LlamaCfg(hidden_size=256, num_hidden_layers=2, intermediate_size=512,
                                      num_attention_heads=4, num_key_value_heads=2, vocab_size=320),
                     image_token_index=300)
+    if kind == "clip_l_full_depth":   # the real CLIP-L/14-336 tower: 24 layers, 577 tokens (feature layer -2 = 23 run)
+        c = OL.LlavaCfg(vision=OL.ClipCfg(),
+                        text=OL.LlamaCfg(hidden_size=512, num_hidden_layers=2, intermediate_size=1024,
+                                         num_attention_heads=4, num_key_value_heads=4, vocab_size=33000),
+                        image_token_index=32000)
     if kind == "clip_l_2layers":   # CLIP-L/14-336 widths, 3 encoder layers (feature layer -2 = after layer 1)
         c = OL.LlavaCfg(vision=OL.ClipCfg(num_hidden_layers=3),
                         text=OL.LlamaCfg(hidden_size=512, num_hidden_layers=2, intermediate_size=1024,
