@@ -9,8 +9,9 @@ CPU restatement of the reference's LLaVA-1.5 generate path (SURVEY §8 row a16, 
   models/llava/llava.py:90-116     merge: inputs_embeds[:, positions of <image>, :] = features
   models/llava/language.py:16-150  Llama decoder with nn.RoPE(traditional=False) and KVCache
 
-PARITY STATUS: oracle only — the product kernels for this row are not built yet (round 2).
-The structure is pinned two ways (tests/test_oracle_llava.py): the merge against the
+PARITY STATUS: floating-point rounding points unpinned at the mlx boundary (mlx is not installable offline; see
+oracle/mlx_semantics.py).  The product path (mlx_vlm_b200/models/llava/) is checked against this file on the GPU
+(tests/test_llava_gpu.py).  The structure is pinned two ways (tests/test_oracle_llava.py): the merge against the
 reference's own function source (tests/golden/), and the whole model in fp32 against
 HuggingFace transformers' LlavaForConditionalGeneration with the same weights.
 
