@@ -59,7 +59,8 @@ struct MegaP {
   int attn_ctas, hsplit;
   unsigned long long* bar;  // monotonic grid-barrier counter
   int advance;
-  int l2_prefetch;
+  int l2_prefetch;   // 1: producer-issued (round 1), 2: consumer-issued gate/up, 3: + down
+  int l2_skip;       // gate/up tiles per CTA the consumer-issued prefetch leaves to the ring
   int max_inflight;   // k_mega: weight tiles requested but not landed per SM (0: no limit)
   int flow;           // k_mega dataflow mode: 3 of the 5 per-layer grid barriers become polled words
   int scratch_bytes;  // attention scratch / activation vector region after the ring

@@ -67,9 +67,9 @@ __device__ __forceinline__ void produce_phase(const MegaPhase& g, const bf16* W,
 
 template <int MODE>
 __device__ __forceinline__ void l2_prefetch_phase(const MegaPhase& g, const bf16* W,
-                                                  const bf16* W2) {
+                                                  const bf16* W2, int skip = 0) {
   const int rows_unit = g.K * 2;
-  for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+  for (int t = blockIdx.x + skip * gridDim.x; t < g.tiles; t += gridDim.x) {
     const int rows = min(g.R, g.N - t * g.R);
     const uint32_t bytes = (uint32_t)rows * rows_unit;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(W + (long)t * g.R * g.K),
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
         // fits the 126 MB L2) into L2, so the ring later refills at L2 speed.
         // (measured, round 1: no gain — gate/up is consumer-bound at 8 warps — and a
         // straggler CTA in the down phase; kept behind a switch for round 2)
-        if (p.l2_prefetch) {
+        if (p.l2_prefetch == 1) {
           l2_prefetch_phase<PH_GATEUP>(p.ph[PH_GATEUP], lw.wgu, lw.wgu + (long)d.inter * d.hidden);
           l2_prefetch_phase<PH_DRES>(p.ph[PH_DRES], lw.wd, nullptr);
         }
@@ -435,6 +435,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) k_mega(const MegaP p) {
     bf16* vc = kc + p.kv_v_offset;
     (void)plane;
     const uint32_t ep = (uint32_t)(sh.att_base + (unsigned long long)l + 1ull);  // tag of this layer
+    // B200_L2_PREFETCH >= 2: the CONSUMER side, entering the latency-bound qkv -> attention -> o_proj chain of this
+    // layer (~16 us during which HBM is idle once the ring is full), asks the L2 for this CTA's share of the layer's
+    // MLP weights; the first `l2_skip` gate/up tiles are already on their way into the ring.  (The producer-issued
+    // variant of round 1 fired while the PREVIOUS layer's MLP was still streaming: no gain.)
+    if (p.l2_prefetch >= 2 && threadIdx.x == 0) {
+      l2_prefetch_phase<PH_GATEUP>(p.ph[PH_GATEUP], lw.wgu, lw.wgu + (long)d.inter * d.hidden, p.l2_skip);
+      if (p.l2_prefetch >= 3) l2_prefetch_phase<PH_DRES>(p.ph[PH_DRES], lw.wd, nullptr);
+    }
     {
       PhaseIO io = {p.h, lw.ln1, lw.bqkv, p.qbuf, kc, vc, nullptr, nullptr,
                     (FLOW && l > 0) ? p.hout_w : nullptr, nullptr, p.qkv_w, hraw, ep, ep - 1u};

@@ -108,7 +108,7 @@ struct b200_engine {
   long tc_acc_rows = 0;
   int tc_alias = 1;
   int tc_inflight = 2;
-  int fma_inflight = 0, l2_prefetch = 0;
+  int fma_inflight = 0, l2_prefetch = 0, l2_skip = 2;
   int flow = 0;  // k_mega dataflow mode (set_mega(4) / B200_MEGA_FLOW=1): measured slower, see DESIGN.md
   unsigned long long* flow_words = nullptr;
   float* att_part = nullptr;
@@ -251,6 +251,7 @@ static int mega_prepare(b200_engine* e, cudaStream_t s) {
     p.qkv_w = e->flow_words + 2 * nh;
   }
   p.l2_prefetch = e->l2_prefetch;
+  p.l2_skip = e->l2_skip;
   int rc;
   if (e->use_mega == 2) {
     // ---- tensor-core variant: tile images of the weights + split-K partial buffers ----
@@ -1250,6 +1251,7 @@ int b200_engine_set_mega(b200_engine* e, int enabled) {
   if (const char* v = getenv("B200_FMA_INFLIGHT")) e->fma_inflight = atoi(v);
 
   if (const char* v = getenv("B200_L2_PREFETCH")) e->l2_prefetch = atoi(v);
+  if (const char* v = getenv("B200_L2_SKIP")) e->l2_skip = atoi(v);
   invalidate_graph(e);
   return B200_OK;
 }
