@@ -177,9 +177,18 @@ def prepare_inputs(processor, images=None, audio=None, prompts=None, image_token
     if inputs.get("pixel_values", None) is not None:
         out["pixel_values"] = _to_device(np.asarray(inputs["pixel_values"], dtype=np.float32), dev,
                                          stream, torch.float32)
+    if "pixel_values" not in inputs and inputs.get("images", None) is not None:   # utils.py:2113-2115
+        out["pixel_values"] = _to_device(np.asarray(inputs["images"], dtype=np.float32), dev, stream, torch.float32)
     for k in ("image_grid_thw", "video_grid_thw"):
         if inputs.get(k, None) is not None:
             out[k] = np.asarray(inputs[k], dtype=np.int64)
+    # every other key the processor produced travels on to the model as a kwarg (utils.py:2124-2134), as host
+    # arrays: Idefics2's `pixel_attention_mask`, LLaVA-Next's `image_sizes`, ...
+    for k in inputs.keys():
+        if k in out or k in ("input_ids", "attention_mask", "pixel_values", "images"):
+            continue
+        v = inputs[k]
+        out[k] = v if v is None or isinstance(v, (str, list)) else np.asarray(v)
     return out
 
 

@@ -45,3 +45,17 @@ def test_config_defaults_and_sanitize():
     out = m.sanitize({"model.text_model.layers.0.x": 1, "lm_head.weight": 2, "model.vision_model.a": 3,
                       "model.connector.b": 4})
     assert set(out) == {"language_model.layers.0.x", "language_model.lm_head.weight", "vision_model.a", "connector.b"}
+
+
+def test_prepare_inputs_passes_processor_extras_through():
+    """utils.py:2124-2134: keys the processor adds (Idefics2: `pixel_attention_mask`, LLaVA-Next: `image_sizes`)
+    reach the model as kwargs; `images` is an alias of `pixel_values` (utils.py:2113-2115)."""
+    from mlx_vlm_b200.utils import prepare_inputs
+
+    def proc(text=None, images=None, **kw):
+        return {"input_ids": [[1, 2, 3]], "attention_mask": [[1, 1, 1]], "images": np.zeros((1, 2, 3, 4, 4), np.float32),
+                "pixel_attention_mask": np.ones((1, 2, 4, 4), bool), "image_sizes": [[4, 4]], "note": "x"}
+    out = prepare_inputs(proc, images=[np.zeros((4, 4, 3), np.uint8)], prompts="hi", device="cpu")
+    assert out["input_ids"].tolist() == [[1, 2, 3]] and out["pixel_values"].shape == (1, 2, 3, 4, 4)
+    assert out["pixel_attention_mask"].dtype == bool and out["pixel_attention_mask"].shape == (1, 2, 4, 4)
+    assert out["image_sizes"] == [[4, 4]] and out["note"] == "x" and "images" not in out
