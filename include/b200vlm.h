@@ -281,6 +281,11 @@ int b200_f32_rms_norm(const float* x, long ldx, const void* w, float eps, float*
 /* fp32 SwiGLU of gu = [gate | up] ([T, 2I]) -> split operand (idefics2.py:146-171) */
 int b200_f32_swiglu_split(const float* gu, long ldg, void* out_split, long ld_split, int n_pad, int T, int I,
                           void* stream);
+/* Idefics3 / SmolVLM pixel shuffle (idefics3.py:47-62) written as the split operand of the connector's Linear:
+ * x fp32 [n_img, side, side, E] -> [n_img (side/s)^2, E s^2], row (yg, xg), column (dy s + dx) E + e =
+ * x[yg s + dy, xg s + dx, e]; round_in rounds the values to bf16 first (the reference's bf16 tower output) */
+int b200_pixel_shuffle_split(const float* x, int n_img, int side, int E, int s, int round_in, void* out_split,
+                             long ld_split, int n_pad, void* stream);
 /* Conv2d(kernel == stride) patch rows, (kh, kw, c) order, from NHWC fp32 pixels, as a split operand
  * [B*gh*gw, Kp | Kp] (llava/vision.py:108-127, idefics2/vision.py:123-148) */
 int b200_clip_patchify(const float* pixels_nhwc, int B, int H, int W, int C, int patch, void* out_split, int Kp,

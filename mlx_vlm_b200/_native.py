@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200_f32_rms_norm": (_I, [_P, _L, _P, _F, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
     "b200_f32_swiglu_split": (_I, [_P, _L, _P, _L, _I, _I, _I, _P]),
     "b200_f32_split": (_I, [_P, _L, _P, _L, _I, _I, _I, _P]),
+    "b200_pixel_shuffle_split": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _I, _P]),
     "b200_clip_patchify": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "b200_tower_embed": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_attention_f32": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _L, _L,

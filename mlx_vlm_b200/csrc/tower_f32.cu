@@ -152,6 +152,25 @@ __global__ void f32_split_kernel(const float* __restrict__ x, long ldx, bf16* __
   }
 }
 
+// Idefics3 / SmolVLM pixel shuffle (reference idefics3.py:47-62) fused with the operand split of the connector's
+// Linear: x fp32 [n_img, side, side, E] -> split operand [n_img * (side / s)^2, E s^2]; output row (yg, xg), column
+// (dy s + dx) E + e = x[yg s + dy, xg s + dx, e].  round_in: the values are rounded to bf16 first (the reference's
+// tower output is bf16), which makes the lo half zero.
+__global__ void pixel_shuffle_split_kernel(const float* __restrict__ x, int n_img, int side, int E, int s, int round_in,
+                                           bf16* __restrict__ out, long ld_split, int n_pad) {
+  const int g = side / s, ev = E >> 2, cols = s * s * ev;
+  const long total = (long)n_img * g * g * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long r = i / cols;
+    const int e4 = c % ev, d = c / ev, dx = d % s, dy = d / s;
+    const int xg = (int)(r % g), yg = (int)((r / g) % g), b = (int)(r / ((long)g * g));
+    float4 v = *reinterpret_cast<const float4*>(x + (((long)b * side + yg * s + dy) * side + xg * s + dx) * E + e4 * 4);
+    if (round_in) v = make_float4(rbf(v.x), rbf(v.y), rbf(v.z), rbf(v.w));
+    split_store4(out + r * ld_split + (long)d * E + e4 * 4, n_pad, v.x, v.y, v.z, v.w);
+  }
+}
+
 // Conv2d(kernel == stride) as a Linear: NHWC fp32 pixels -> rows of (kh, kw, c)-ordered patches, written
 // as a split operand [B * gh * gw, Kp | Kp] (K = ps * ps * C, zero padded to Kp).  (llava/vision.py:108-127)
 __global__ void clip_patchify_kernel(const float* __restrict__ pix, int B, int H, int W, int C, int ps,
@@ -441,6 +460,17 @@ int f32_split(const float* x, long ldx, void* out, long ld_split, int n_pad, int
   return B200_OK;
 }
 
+int pixel_shuffle_split(const float* x, int n_img, int side, int E, int s, int round_in, void* out, long ld_split,
+                        int n_pad, cudaStream_t st) {
+  B200_REQUIRE(x && out && n_img > 0 && s > 0 && side > 0 && side % s == 0 && (E % 4) == 0 && n_pad >= E * s * s &&
+                   (ld_split % 4) == 0 && (n_pad % 4) == 0, "pixel_shuffle_split: bad shape");
+  const long total = (long)n_img * (side / s) * (side / s) * s * s * (E / 4);
+  pixel_shuffle_split_kernel<<<t_grid(total, 256), 256, 0, st>>>(x, n_img, side, E, s, round_in, (bf16*)out, ld_split,
+                                                                 n_pad);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 int clip_patchify(const float* pix, int B, int H, int W, int C, int ps, void* out, int Kp, cudaStream_t st) {
   B200_REQUIRE(pix && out && B > 0 && H % ps == 0 && W % ps == 0 && Kp >= ps * ps * C && (Kp % 8) == 0,
                "clip_patchify: bad shape");
@@ -502,6 +532,10 @@ int b200_f32_swiglu_split(const float* gu, long ldg, void* out, long ld_split, i
 }
 int b200_f32_split(const float* x, long ldx, void* out, long ld_split, int n_pad, int T, int N, void* st) {
   return f32_split(x, ldx, out, ld_split, n_pad, T, N, (cudaStream_t)st);
+}
+int b200_pixel_shuffle_split(const float* x, int n_img, int side, int E, int s, int round_in, void* out_split,
+                             long ld_split, int n_pad, void* st) {
+  return pixel_shuffle_split(x, n_img, side, E, s, round_in, out_split, ld_split, n_pad, (cudaStream_t)st);
 }
 int b200_clip_patchify(const float* pix, int B, int H, int W, int C, int ps, void* out, int Kp, void* st) {
   return clip_patchify(pix, B, H, W, C, ps, out, Kp, (cudaStream_t)st);

@@ -95,6 +95,11 @@ class TowerOps:
             out_split.ld if out_split else 0, out_split.n_pad if out_split else 0, n_heads, n_kv, hd, Lq, S, n_seg,
             q_seg, k_seg, N.ptr(key_mask), float(scale), self.eng.s), "attention_f32")
 
+    def pixel_shuffle(self, x: torch.Tensor, n_img: int, side: int, s: int, out: SplitBuf, round_in: bool = True):
+        E = x.shape[-1]
+        N.check(self.lib.b200_pixel_shuffle_split(x.data_ptr(), n_img, side, E, s, int(round_in), out.t.data_ptr(), out.ld,
+                                                  out.n_pad, self.eng.s), "pixel_shuffle_split")
+
     def patchify(self, pix_nhwc: torch.Tensor, ps: int, out: SplitBuf):
         B, H, W, C = pix_nhwc.shape
         N.check(self.lib.b200_clip_patchify(pix_nhwc.data_ptr(), B, H, W, C, ps, out.t.data_ptr(), out.n_pad,

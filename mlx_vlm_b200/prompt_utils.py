@@ -1,7 +1,7 @@
 """Chat-template helpers of the reference's public surface (mlx_vlm/prompt_utils.py:
 `get_message_json` :555-591, `get_chat_template` :594-826, `apply_chat_template` :829-995) for the
-model families on the B200 generate path — qwen2_vl, llava, idefics2 (all "list with image"
-messages, prompt_utils.py:37,45,77) — plus the reference's text-only fallback for unknown types.
+model families on the B200 generate path — qwen2_vl, llava, llava_next, idefics2 ("list with image"
+messages, prompt_utils.py:37,45,77,78) and idefics3 / smolvlm ("list with image first", :38,76) — plus the reference's text-only fallback for unknown types.
 Behaviour is pinned against the reference's own module, executed, in tests/golden
 (`chat_template_cases`).  Video / audio message kinds are outside the hot-path scope.
 """
@@ -12,7 +12,9 @@ import json
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 # model_type -> image entries come before the text entry?
-_LIST_WITH_IMAGE: Dict[str, bool] = {"qwen2_vl": False, "llava": False, "idefics2": False}
+_LIST_WITH_IMAGE: Dict[str, bool] = {"qwen2_vl": False, "llava": False, "llava_next": False, "idefics2": False,
+                                     "idefics3": True, "smolvlm": True}
+_SINGLE_IMAGE_ONLY = {"llava_next"}     # prompt_utils.py:119-127
 _IMAGE_KINDS = ("image", "image_url", "input_image")
 
 
@@ -70,6 +72,8 @@ def get_message_json(model_name: str, prompt: str, role: str = "user", skip_imag
     name = model_name.lower()
     if name not in _LIST_WITH_IMAGE:
         raise ValueError(f"Unsupported model: {model_name}")
+    if num_images > 1 and name in _SINGLE_IMAGE_ONLY:
+        raise ValueError(f"Model {name} does not support multi-image chat. Please only use 1 image.")
     if kwargs.get("video"):
         raise NotImplementedError("video messages are outside the B200 hot-path scope")
     entries: List[Dict[str, Any]] = [{"type": "text", "text": prompt, "content": prompt}]

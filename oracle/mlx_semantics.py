@@ -118,6 +118,16 @@ def gelu_exact(R: Rounder, x):
     return R.r(d / 2.0)
 
 
+def gelu_tanh(R: Rounder, x):
+    """nn.GELU(approx="precise") = 0.5 * x * (1 + tanh(sqrt(2 / pi) * (x + 0.044715 * x ** 3))) (mlx nn.gelu_approx);
+    every primitive rounds to the activation dtype, python scalars are weak-typed to it."""
+    c0, c1 = R.scalar(0.044715), R.scalar(math.sqrt(2.0 / math.pi))
+    x3 = R.r(torch.pow(x, 3))     # mx.power(x, 3): one primitive, one rounding
+    t = R.r(x + R.r(c0 * x3))
+    t = R.r(torch.tanh(R.r(c1 * t)))
+    return R.r(R.r(0.5 * x) * R.r(1.0 + t))
+
+
 # ---------------------------------------------------------------------------
 # mx.fast.scaled_dot_product_attention on the CPU device = fallback graph
 # (mlx/fast.cpp): q = q * array(scale, q.dtype); GQA by reshaping q to

@@ -45,7 +45,7 @@ PROMPTS = {
 }
 
 cases = []
-for model_type in ("qwen2_vl", "llava", "idefics2", "some_text_model"):
+for model_type in ("qwen2_vl", "llava", "llava_next", "idefics2", "idefics3", "smolvlm", "some_text_model"):
     for pname, prompt in PROMPTS.items():
         for n_img in (0, 1, 3):
             for proc in ("template", "none", "null"):
@@ -61,12 +61,15 @@ for model_type in ("qwen2_vl", "llava", "idefics2", "some_text_model"):
                         except Exception as e:  # noqa
                             cases.append({**args, "error": type(e).__name__})
 msgs = []
-for m in ("qwen2_vl", "llava", "idefics2"):
+for m in ("qwen2_vl", "llava", "llava_next", "idefics2", "idefics3", "smolvlm"):
     for role in ("user", "assistant", "system"):
         for n in (0, 2):
             for skip in (False, True):
-                msgs.append({"model": m, "role": role, "n": n, "skip": skip,
-                             "out": ref.get_message_json(m, "p", role, skip_image_token=skip, num_images=n, num_audios=1)})
+                try:
+                    msgs.append({"model": m, "role": role, "n": n, "skip": skip,
+                                 "out": ref.get_message_json(m, "p", role, skip_image_token=skip, num_images=n, num_audios=1)})
+                except Exception as e:  # noqa
+                    msgs.append({"model": m, "role": role, "n": n, "skip": skip, "error": type(e).__name__})
 here = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(here, "chat_template_golden.json"), "w") as f:
     json.dump({"prompts": PROMPTS, "cases": cases, "messages": msgs}, f, sort_keys=True)

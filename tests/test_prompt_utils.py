@@ -42,6 +42,9 @@ def test_chat_template_matches_reference_module():
         n_ok += 1
     assert n_ok == len(G["cases"]) >= 1000
     for m in G["messages"]:
-        out = get_message_json(m["model"], "p", m["role"], skip_image_token=m["skip"], num_images=m["n"],
-                               num_audios=1)
-        assert json.loads(json.dumps(out)) == m["out"], m
+        try:
+            got = {"out": json.loads(json.dumps(get_message_json(m["model"], "p", m["role"], skip_image_token=m["skip"],
+                                                                 num_images=m["n"], num_audios=1)))}
+        except Exception as e:  # noqa
+            got = {"error": type(e).__name__}
+        assert got == {k: m[k] for k in ("out", "error") if k in m}, m
