@@ -300,6 +300,21 @@ int b200_attention_f32(const float* q, long q_ts, long q_hs, const float* k, lon
                        long v_ts, long v_hs, float* out32, long o_ts, void* out_split, long os_ts, int n_pad,
                        int n_heads, int n_kv, int hd, int Lq, int S, int n_seg, long q_seg, long k_seg,
                        const unsigned char* key_mask, float scale, void* stream);
+/* the same attention over RAGGED self-attention segments: segment z = tokens [cu_seqlens[z], cu_seqlens[z+1]) of q, k and
+ * v (device int array of n_seg + 1 entries); max_len = the longest segment.  Qwen2.5-VL's windowed blocks
+ * (qwen2_5_vl/vision.py:147-160: one SDPA per split of cu_seqlens). */
+int b200_attention_f32_varlen(const float* q, long q_ts, long q_hs, const float* k, long k_ts, long k_hs, const float* v,
+                              long v_ts, long v_hs, float* out32, long o_ts, void* out_split, long os_ts, int n_pad,
+                              int n_heads, int n_kv, int hd, const int* cu_seqlens, int n_seg, int max_len, float scale,
+                              void* stream);
+/* 2-D rotary embedding on fp32 q and k in place (qwen2_5_vl/vision.py:35-50; qwen2_vl/vision.py:35-50): qkv [T, >= 3 *
+ * n_heads * hd] = (q | k | v), pos_hw [T][2] (row, column) per patch, inv_freq [hd / 4] */
+int b200_f32_vision_rope(float* qkv, long ld, const int* pos_hw, const float* inv_freq, int T, int n_heads, int hd,
+                         void* stream);
+/* out[i * unit + u] = in[idx[i] * unit + u] for rows of n fp32 values: the window permutation of merge units and its
+ * inverse (qwen2_5_vl/vision.py:343-347,386-388) */
+int b200_f32_gather_rows(const float* in, long ld_in, const int* idx, int n_idx, int unit, int n, float* out,
+                         long ld_out, void* stream);
 /* nn.Linear on fp32 activations: X split operand [T, n_parts x Kp], W [N, K_w] bf16 (row pitch ldw);
  * mode B200_WT_F32: C32 = act(acc + bias) + res32; mode B200_WT_SPLIT: Csplit = [hi | lo] of act(acc + bias) */
 int b200_gemm_wt_f32(const void* X, long ldx, const void* W, long ldw, const void* bias, const float* res32,

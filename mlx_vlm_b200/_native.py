@@ -88,6 +88,9 @@ SIGNATURES = {
     "b200_tower_embed": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_attention_f32": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _L, _L,
                                 _P, _F, _P]),
+    "b200_attention_f32_varlen": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _I, _F, _P]),
+    "b200_f32_vision_rope": (_I, [_P, _L, _P, _P, _I, _I, _I, _P]),
+    "b200_f32_gather_rows": (_I, [_P, _L, _P, _I, _I, _I, _P, _L, _P]),
     "b200_gemm_wt_f32": (_I, [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_engine_set_kv_row": (_I, [_P, _I]),
     "b200_batch_begin": (_I, [_P, _I, _P, _P, _P, _P, _P]),

@@ -171,6 +171,46 @@ __global__ void pixel_shuffle_split_kernel(const float* __restrict__ x, int n_im
   }
 }
 
+// 2-D rotary embedding of the Qwen2-VL / Qwen2.5-VL vision towers on fp32 q and k in place (reference
+// qwen2_5_vl/vision.py:35-50: x * cos + rotate_half(x) * sin in fp32 with cos / sin tiled twice along the head):
+// qkv [T, 3 * n_heads * hd] fp32 (q | k | v), pos_hw [T][2] the (row, column) of each patch, inv_freq [hd / 4];
+// pair j < hd / 2 turns by pos[j < hd / 4 ? row : column] * inv_freq[j mod hd / 4].
+__global__ void f32_vision_rope_kernel(float* __restrict__ qkv, long ld, const int* __restrict__ pos_hw,
+                                       const float* __restrict__ inv_freq, int T, int n_heads, int hd) {
+  const int half = hd >> 1, quarter = hd >> 2;
+  const long total = (long)T * 2 * n_heads * half;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % half);
+    long r = i / half;
+    const int h = (int)(r % n_heads);
+    r /= n_heads;
+    const int which = (int)(r & 1), t = (int)(r >> 1);
+    const int axis = j < quarter ? 0 : 1;
+    const float ang = (float)pos_hw[t * 2 + axis] * inv_freq[j - axis * quarter];
+    const float c = cosf(ang), sn = sinf(ang);
+    float* base = qkv + (long)t * ld + ((long)which * n_heads + h) * hd;
+    const float x1 = base[j], x2 = base[j + half];
+    base[j] = __fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, sn));
+    base[j + half] = __fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, sn));
+  }
+}
+
+// out[(i * unit + u), :] = in[(idx[i] * unit + u), :]  — the window permutation of Qwen2.5-VL's merge units and its
+// inverse (qwen2_5_vl/vision.py:343-347,386-388); rows of n fp32 values (n % 4 == 0)
+__global__ void f32_gather_rows_kernel(const float* __restrict__ in, long ld_in, const int* __restrict__ idx, int n_idx,
+                                       int unit, int n, float* __restrict__ out, long ld_out) {
+  const int nv = n >> 2;
+  const long total = (long)n_idx * unit * nv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nv);
+    const long r = i / nv;
+    const int u = (int)(r % unit);
+    const long g = r / unit;
+    *reinterpret_cast<float4*>(out + r * ld_out + c * 4) =
+        *reinterpret_cast<const float4*>(in + ((long)idx[g] * unit + u) * ld_in + c * 4);
+  }
+}
+
 // Conv2d(kernel == stride) as a Linear: NHWC fp32 pixels -> rows of (kh, kw, c)-ordered patches, written
 // as a split operand [B * gh * gw, Kp | Kp] (K = ps * ps * C, zero padded to Kp).  (llava/vision.py:108-127)
 __global__ void clip_patchify_kernel(const float* __restrict__ pix, int B, int H, int W, int C, int ps,
@@ -248,6 +288,8 @@ struct AttnF32P {
   int n_heads, n_kv, Lq, S, hd;
   long q_seg, k_seg;   // tokens between consecutive segments (blockIdx.z)
   const unsigned char* key_mask;  // optional [segments][S]: 0 = key masked out
+  const int* cu;                  // optional [segments + 1]: segment z = tokens [cu[z], cu[z+1]) of q, k and v (self-attention
+                                  // over ragged segments, e.g. Qwen2.5-VL's windows); Lq is then the longest segment
   float scale;
 };
 
@@ -273,14 +315,21 @@ __global__ void __launch_bounds__(AF_THREADS) attention_f32_kernel(const AttnF32
   const int h = blockIdx.y, kvh = h / (p.n_heads / p.n_kv), seg = blockIdx.z;
   const int q0 = blockIdx.x * BQ;
   const int hd = p.hd, hd4 = hd >> 2;
-  const float* qb = p.q + (long)seg * p.q_seg * p.q_ts + (long)h * p.q_hs;
-  const float* kb = p.k + (long)seg * p.k_seg * p.k_ts + (long)kvh * p.k_hs;
-  const float* vb = p.v + (long)seg * p.k_seg * p.v_ts + (long)kvh * p.v_hs;
+  long q_first = (long)seg * p.q_seg, k_first = (long)seg * p.k_seg;
+  int Lq = p.Lq, S = p.S;
+  if (p.cu) {
+    q_first = k_first = p.cu[seg];
+    Lq = S = p.cu[seg + 1] - p.cu[seg];
+    if (q0 >= Lq) return;   // uniform per CTA
+  }
+  const float* qb = p.q + q_first * p.q_ts + (long)h * p.q_hs;
+  const float* kb = p.k + k_first * p.k_ts + (long)kvh * p.k_hs;
+  const float* vb = p.v + k_first * p.v_ts + (long)kvh * p.v_hs;
   // Q^T: lane <-> query row (conflict-free transposed stores)
   for (int i = tid; i < BQ * (HDP / 4); i += NT) {
     const int r = i % BQ, c = i / BQ;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < p.Lq && c < hd4) v = *reinterpret_cast<const float4*>(qb + (long)(q0 + r) * p.q_ts + c * 4);
+    if (q0 + r < Lq && c < hd4) v = *reinterpret_cast<const float4*>(qb + (long)(q0 + r) * p.q_ts + c * 4);
     Qt[(c * 4 + 0) * BQ + r] = v.x * p.scale;
     Qt[(c * 4 + 1) * BQ + r] = v.y * p.scale;
     Qt[(c * 4 + 2) * BQ + r] = v.z * p.scale;
@@ -294,12 +343,12 @@ __global__ void __launch_bounds__(AF_THREADS) attention_f32_kernel(const AttnF32
 #pragma unroll
     for (int e = 0; e < DPT; ++e) o[i][e] = 0.f;
   }
-  for (int j0 = 0; j0 < p.S; j0 += BK) {
+  for (int j0 = 0; j0 < S; j0 += BK) {
     __syncthreads();
     for (int i = tid; i < BK * (HDP / 4); i += NT) {   // K^T: lane <-> key
       const int r = i % BK, c = i / BK;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + r < p.S && c < hd4) v = *reinterpret_cast<const float4*>(kb + (long)(j0 + r) * p.k_ts + c * 4);
+      if (j0 + r < S && c < hd4) v = *reinterpret_cast<const float4*>(kb + (long)(j0 + r) * p.k_ts + c * 4);
       Kt[(c * 4 + 0) * BK + r] = v.x;
       Kt[(c * 4 + 1) * BK + r] = v.y;
       Kt[(c * 4 + 2) * BK + r] = v.z;
@@ -308,10 +357,10 @@ __global__ void __launch_bounds__(AF_THREADS) attention_f32_kernel(const AttnF32
     for (int i = tid; i < BK * (HDP / 4); i += NT) {   // V: row-major
       const int r = i / (HDP / 4), c = i % (HDP / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + r < p.S && c < hd4) v = *reinterpret_cast<const float4*>(vb + (long)(j0 + r) * p.v_ts + c * 4);
+      if (j0 + r < S && c < hd4) v = *reinterpret_cast<const float4*>(vb + (long)(j0 + r) * p.v_ts + c * 4);
       *reinterpret_cast<float4*>(Vs + r * HDP + c * 4) = v;
     }
-    if (tid < BK) Ms[tid] = (j0 + tid < p.S) && (!p.key_mask || p.key_mask[(long)seg * p.S + j0 + tid]);
+    if (tid < BK) Ms[tid] = (j0 + tid < S) && (!p.key_mask || p.key_mask[(long)seg * S + j0 + tid]);
     __syncthreads();
     // ---- S = Q . K^T for this thread's 8 rows x 4 keys ----
     float s[8][4];
@@ -385,9 +434,9 @@ __global__ void __launch_bounds__(AF_THREADS) attention_f32_kernel(const AttnF32
 #pragma unroll
     for (int w = 1; w < 16; w <<= 1) ls += __shfl_xor_sync(0xffffffffu, ls, w);
     const int qi = q0 + ty * 8 + i;
-    if (qi >= p.Lq) continue;
+    if (qi >= Lq) continue;
     const float inv = 1.0f / ls;
-    const long t = (long)seg * p.q_seg + qi;
+    const long t = q_first + qi;
 #pragma unroll
     for (int e = 0; e < DPT; ++e) {
       const int d = e * 16 + tx;
@@ -490,12 +539,32 @@ int tower_embed(const float* patch, const void* cls, const void* pos, const int*
   return B200_OK;
 }
 
+int f32_vision_rope(float* qkv, long ld, const int* pos_hw, const float* inv_freq, int T, int n_heads, int hd,
+                    cudaStream_t st) {
+  B200_REQUIRE(qkv && pos_hw && inv_freq && T > 0 && n_heads > 0 && (hd % 4) == 0 && ld >= 3L * n_heads * hd,
+               "f32_vision_rope: bad shape");
+  f32_vision_rope_kernel<<<t_grid((long)T * n_heads * hd, 256), 256, 0, st>>>(qkv, ld, pos_hw, inv_freq, T, n_heads, hd);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int f32_gather_rows(const float* in, long ld_in, const int* idx, int n_idx, int unit, int n, float* out, long ld_out,
+                    cudaStream_t st) {
+  B200_REQUIRE(in && idx && out && n_idx > 0 && unit > 0 && n > 0 && (n % 4) == 0 && (ld_in % 4) == 0 && (ld_out % 4) == 0,
+               "f32_gather_rows: bad shape");
+  f32_gather_rows_kernel<<<t_grid((long)n_idx * unit * (n / 4), 256), 256, 0, st>>>(in, ld_in, idx, n_idx, unit, n, out,
+                                                                                   ld_out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 int attention_f32(const float* q, long q_ts, long q_hs, const float* k, long k_ts, long k_hs, const float* v,
                   long v_ts, long v_hs, float* out32, long o_ts, void* out_split, long os_ts, int n_pad,
                   int n_heads, int n_kv, int hd, int Lq, int S, int n_seg, long q_seg, long k_seg,
-                  const unsigned char* key_mask, float scale, cudaStream_t st) {
+                  const unsigned char* key_mask, float scale, cudaStream_t st, const int* cu = nullptr) {
   B200_REQUIRE(q && k && v && (out32 || out_split) && Lq > 0 && S > 0 && n_seg > 0 && n_heads % n_kv == 0,
                "attention_f32: bad arguments");
+  B200_REQUIRE(!cu || !key_mask, "attention_f32: ragged segments take no key mask");
   B200_REQUIRE((q_ts % 4) == 0 && (k_ts % 4) == 0 && (v_ts % 4) == 0 && (q_hs % 4) == 0 && (k_hs % 4) == 0 &&
                    (v_hs % 4) == 0 && (o_ts % 4) == 0 && (os_ts % 4) == 0 && (n_pad % 4) == 0,
                "attention_f32: strides must be multiples of 4 elements");
@@ -504,6 +573,7 @@ int attention_f32(const float* q, long q_ts, long q_hs, const float* k, long k_t
   p.out32 = out32; p.o_ts = o_ts; p.out_split = (bf16*)out_split; p.os_ts = os_ts; p.n_pad = n_pad;
   p.n_heads = n_heads; p.n_kv = n_kv; p.Lq = Lq; p.S = S; p.q_seg = q_seg; p.k_seg = k_seg; p.key_mask = key_mask;
   p.scale = scale;
+  p.cu = cu;
   p.hd = hd;
   B200_REQUIRE((hd % 4) == 0 && hd <= 96, "attention_f32: head_dim %d (multiple of 4, <= 96)", hd);
   const dim3 grid(cdiv(Lq, AF_BQ), n_heads, n_seg);
@@ -550,6 +620,22 @@ int b200_attention_f32(const float* q, long q_ts, long q_hs, const float* k, lon
                        const unsigned char* key_mask, float scale, void* st) {
   return attention_f32(q, q_ts, q_hs, k, k_ts, k_hs, v, v_ts, v_hs, out32, o_ts, out_split, os_ts, n_pad, n_heads,
                        n_kv, hd, Lq, S, n_seg, q_seg, k_seg, key_mask, scale, (cudaStream_t)st);
+}
+int b200_attention_f32_varlen(const float* q, long q_ts, long q_hs, const float* k, long k_ts, long k_hs, const float* v,
+                              long v_ts, long v_hs, float* out32, long o_ts, void* out_split, long os_ts, int n_pad,
+                              int n_heads, int n_kv, int hd, const int* cu_seqlens, int n_seg, int max_len, float scale,
+                              void* st) {
+  B200_REQUIRE(cu_seqlens && max_len > 0, "attention_f32_varlen: needs cu_seqlens and the longest segment");
+  return attention_f32(q, q_ts, q_hs, k, k_ts, k_hs, v, v_ts, v_hs, out32, o_ts, out_split, os_ts, n_pad, n_heads,
+                       n_kv, hd, max_len, max_len, n_seg, 0, 0, nullptr, scale, (cudaStream_t)st, cu_seqlens);
+}
+int b200_f32_vision_rope(float* qkv, long ld, const int* pos_hw, const float* inv_freq, int T, int n_heads, int hd,
+                         void* st) {
+  return f32_vision_rope(qkv, ld, pos_hw, inv_freq, T, n_heads, hd, (cudaStream_t)st);
+}
+int b200_f32_gather_rows(const float* in, long ld_in, const int* idx, int n_idx, int unit, int n, float* out,
+                         long ld_out, void* st) {
+  return f32_gather_rows(in, ld_in, idx, n_idx, unit, n, out, ld_out, (cudaStream_t)st);
 }
 /* fp32-accurate Linear on the tensor cores: X = split operand [T, n_parts x Kp] (Kp = K_w rounded up to 64),
  * W [N, K_w] bf16; mode B200_WT_F32 (C32 = act(acc + bias) + res32) or B200_WT_SPLIT (Csplit = [hi | lo]). */

@@ -72,9 +72,10 @@ class TowerOps:
 
     def linear(self, x: SplitBuf, w: torch.Tensor, bias, *, out32: Optional[torch.Tensor] = None,
                res32: Optional[torch.Tensor] = None, out_split: Optional[SplitBuf] = None, epi: int = EPI_NONE,
-               k_w: Optional[int] = None):
+               k_w: Optional[int] = None, n_parts: int = 2):
         """y = act(W . x + bias) (+ res32): fp32 into `out32` or as a split operand into `out_split`.
-        w: [N, ldw] bf16 with k_w valid columns (k_w defaults to x.n)."""
+        w: [N, ldw] bf16 with k_w valid columns (k_w defaults to x.n); n_parts = 1 reads only the hi half of x, i.e. the
+        input rounded to bf16."""
         n_out = w.shape[0]
         k_w = x.n if k_w is None else k_w
         mode = F32 if out32 is not None else SPLIT
@@ -82,7 +83,7 @@ class TowerOps:
             x.t.data_ptr(), x.ld, w.data_ptr(), w.stride(0), N.ptr(bias), N.ptr(res32),
             res32.stride(0) if res32 is not None else 0, N.ptr(out32), out32.stride(0) if out32 is not None else 0,
             N.ptr(out_split.t) if out_split else 0, out_split.ld if out_split else 0,
-            out_split.n_pad if out_split else 0, x.T, n_out, k_w, 2, epi, mode, self.eng.s), "gemm_wt_f32")
+            out_split.n_pad if out_split else 0, x.T, n_out, k_w, n_parts, epi, mode, self.eng.s), "gemm_wt_f32")
 
     def attention(self, q, k, v, *, n_heads: int, n_kv: int, hd: int, Lq: int, S: int, n_seg: int, q_seg: int,
                   k_seg: int, scale: float, out32: Optional[torch.Tensor] = None, out_split: Optional[SplitBuf] = None,
@@ -94,6 +95,24 @@ class TowerOps:
             out32.stride(0) if out32 is not None else 0, N.ptr(out_split.t) if out_split else 0,
             out_split.ld if out_split else 0, out_split.n_pad if out_split else 0, n_heads, n_kv, hd, Lq, S, n_seg,
             q_seg, k_seg, N.ptr(key_mask), float(scale), self.eng.s), "attention_f32")
+
+    def attention_varlen(self, q, k, v, *, n_heads: int, n_kv: int, hd: int, cu: torch.Tensor, n_seg: int, max_len: int,
+                         scale: float, out32: Optional[torch.Tensor] = None, out_split: Optional[SplitBuf] = None):
+        """self-attention inside each ragged segment [cu[z], cu[z+1]) (cu: device int32)"""
+        (qt, q_ts, q_hs), (kt, k_ts, k_hs), (vt, v_ts, v_hs) = q, k, v
+        N.check(self.lib.b200_attention_f32_varlen(
+            qt.data_ptr(), q_ts, q_hs, kt.data_ptr(), k_ts, k_hs, vt.data_ptr(), v_ts, v_hs, N.ptr(out32),
+            out32.stride(0) if out32 is not None else 0, N.ptr(out_split.t) if out_split else 0,
+            out_split.ld if out_split else 0, out_split.n_pad if out_split else 0, n_heads, n_kv, hd, cu.data_ptr(),
+            n_seg, max_len, float(scale), self.eng.s), "attention_f32_varlen")
+
+    def vision_rope(self, qkv: torch.Tensor, pos_hw: torch.Tensor, inv_freq: torch.Tensor, n_heads: int, hd: int):
+        N.check(self.lib.b200_f32_vision_rope(qkv.data_ptr(), qkv.stride(0), pos_hw.data_ptr(), inv_freq.data_ptr(),
+                                              qkv.shape[0], n_heads, hd, self.eng.s), "f32_vision_rope")
+
+    def gather_rows(self, x: torch.Tensor, idx: torch.Tensor, unit: int, out: torch.Tensor):
+        N.check(self.lib.b200_f32_gather_rows(x.data_ptr(), x.stride(0), idx.data_ptr(), idx.numel(), unit, x.shape[1],
+                                              out.data_ptr(), out.stride(0), self.eng.s), "f32_gather_rows")
 
     def pixel_shuffle(self, x: torch.Tensor, n_img: int, side: int, s: int, out: SplitBuf, round_in: bool = True):
         E = x.shape[-1]

@@ -1,7 +1,7 @@
 """Chat-template helpers of the reference's public surface (mlx_vlm/prompt_utils.py:
 `get_message_json` :555-591, `get_chat_template` :594-826, `apply_chat_template` :829-995) for the
 model families on the B200 generate path — qwen2_vl, llava, llava_next, idefics2 ("list with image"
-messages, prompt_utils.py:37,45,77,78) and idefics3 / smolvlm ("list with image first", :38,76) — plus the reference's text-only fallback for unknown types.
+messages, prompt_utils.py:37,45,77,78) and qwen2_5_vl / idefics3 / smolvlm ("list with image first", :46,38,76) — plus the reference's text-only fallback for unknown types.
 Behaviour is pinned against the reference's own module, executed, in tests/golden
 (`chat_template_cases`).  Video / audio message kinds are outside the hot-path scope.
 """
@@ -12,7 +12,7 @@ import json
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 # model_type -> image entries come before the text entry?
-_LIST_WITH_IMAGE: Dict[str, bool] = {"qwen2_vl": False, "llava": False, "llava_next": False, "idefics2": False,
+_LIST_WITH_IMAGE: Dict[str, bool] = {"qwen2_vl": False, "qwen2_5_vl": True, "llava": False, "llava_next": False, "idefics2": False,
                                      "idefics3": True, "smolvlm": True}
 _SINGLE_IMAGE_ONLY = {"llava_next"}     # prompt_utils.py:119-127
 _IMAGE_KINDS = ("image", "image_url", "input_image")

@@ -45,7 +45,7 @@ PROMPTS = {
 }
 
 cases = []
-for model_type in ("qwen2_vl", "llava", "llava_next", "idefics2", "idefics3", "smolvlm", "some_text_model"):
+for model_type in ("qwen2_vl", "qwen2_5_vl", "llava", "llava_next", "idefics2", "idefics3", "smolvlm", "some_text_model"):
     for pname, prompt in PROMPTS.items():
         for n_img in (0, 1, 3):
             for proc in ("template", "none", "null"):
@@ -61,7 +61,7 @@ for model_type in ("qwen2_vl", "llava", "llava_next", "idefics2", "idefics3", "s
                         except Exception as e:  # noqa
                             cases.append({**args, "error": type(e).__name__})
 msgs = []
-for m in ("qwen2_vl", "llava", "llava_next", "idefics2", "idefics3", "smolvlm"):
+for m in ("qwen2_vl", "qwen2_5_vl", "llava", "llava_next", "idefics2", "idefics3", "smolvlm"):
     for role in ("user", "assistant", "system"):
         for n in (0, 2):
             for skip in (False, True):
