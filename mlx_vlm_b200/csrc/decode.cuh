@@ -201,7 +201,7 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
                   const WtExt* ext = nullptr);
 int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
                 long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn, long ldx,
-                int T, int N, cudaStream_t st);
+                int T, int N, cudaStream_t st, const void* l2_prefetch = nullptr, long l2_prefetch_bytes = 0);
 void gemm_wt_set_pdl(bool on);
 int attention(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs,
               const void* v, long v_ts, long v_hs, void* out, long o_ts, int n_heads, int n_kv,

@@ -90,11 +90,21 @@ struct BdAttnP {
   bf16* out;          // [B][n_heads*hd]
   int n_heads, n_kv, cap, hsplit;
   float scale_bf;
+  // weights of the GEMMs that follow (o_proj, gate/up, down): this kernel is a chain of dependent round trips that
+  // leaves HBM idle, so its CTAs ask the L2 for them up front (l2_prefetch_span; weights are static during a step)
+  const void* pf[3];
+  long pf_bytes[3];
 };
 
 template <int HD, int AG>
 __global__ void __launch_bounds__(256) bd_attn_kernel(const BdAttnP p) {
   bd_pdl_launch();
+  if (threadIdx.x == 0) {
+    const int n = gridDim.x * gridDim.y, id = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (p.pf_bytes[i] > 0) l2_prefetch_span(p.pf[i], p.pf_bytes[i], id, n);
+  }
   extern __shared__ __align__(16) uint8_t bd_sm[];
   constexpr int NCH = HD / 8, half = HD / 2;
   constexpr int SEG = HD / 8;   // dims per lane in the P.V phase (lane = key sub-index x dim segment)
@@ -543,6 +553,22 @@ static int bd_attn_launch(int ag, dim3 grid, size_t smem, cudaStream_t s, const 
   }
 }
 
+// L2 prefetch budget of the latency-bound kernels of a step, in bytes (B200_BD_PREFETCH_MB).  DEFAULT 0 = off: measured on
+// C5 (Qwen2-VL-7B, 8 rows) the step got SLOWER with it — 3.672 ms off, 3.745 ms at 60 MB, 3.804 ms at 96 MB
+// (profiles/r2_bd_l2_prefetch_ab.txt): the prefetch traffic lengthens the attention kernel's dependent round trips by
+// more than the L2-resident weights save the GEMMs.  Kept as a tuning knob.
+static long bd_prefetch_budget() {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_BD_PREFETCH_MB");
+    long mb = e ? atol(e) : 0;
+    if (mb < 0) mb = 0;
+    if (mb > 120) mb = 120;
+    v = mb << 20;
+  }
+  return v;
+}
+
 // one lock-step step as plain launches on `s` (also what gets captured)
 static int bd_enqueue_step(BatchDecoder* d, const BdModel& m, cudaStream_t s, long* launches) {
   const DecodeDims& dd = m.d;
@@ -563,6 +589,16 @@ static int bd_enqueue_step(BatchDecoder* d, const BdModel& m, cudaStream_t s, lo
     ap.ctx = d->ctx; ap.pos = d->pos; ap.kv = m.kv + (long)l * m.layer_stride; ap.v_off = m.v_off;
     ap.row_stride = m.row_stride; ap.out = d->att; ap.n_heads = dd.n_heads; ap.n_kv = dd.n_kv; ap.cap = dd.cap;
     ap.hsplit = hs; ap.scale_bf = dd.scale_bf;
+    {  // o_proj, then gate/up, then down, as far as the budget goes
+      long left = bd_prefetch_budget();
+      const void* w[3] = {lw.wo, lw.wgu, lw.wd};
+      const long bytes[3] = {(long)H * QH * 2, 2L * I * H * 2, (long)H * I * 2};
+      for (int i = 0; i < 3; ++i) {
+        ap.pf[i] = w[i];
+        ap.pf_bytes[i] = bytes[i] < left ? bytes[i] : left;
+        left -= ap.pf_bytes[i];
+      }
+    }
     const dim3 ag(dd.n_kv * hs, B);
     if (dd.hd == 128) rc = bd_attn_launch<128>(ag_heads, ag, bd_attn_smem(dd, ag_heads), s, ap);
     else rc = bd_attn_launch<64>(ag_heads, ag, bd_attn_smem(dd, ag_heads), s, ap);
@@ -580,8 +616,11 @@ static int bd_enqueue_step(BatchDecoder* d, const BdModel& m, cudaStream_t s, lo
                             B200_EPI_NONE, B200_WT_PARTIAL, 0, true, m.sm_count, &split, s)))
       return rc;
     const bf16* nw = (l + 1 == m.n_layers) ? m.final_norm : m.layers[l + 1].ln1;
+    // the finish of `down` is the other HBM-idle spot: it asks for the next layer's qkv weights
+    const void* nq = (l + 1 == m.n_layers) ? nullptr : (const void*)m.layers[l + 1].wqkv;
+    const long nq_bytes = nq ? ((long)QKV * H * 2 < bd_prefetch_budget() ? (long)QKV * H * 2 : bd_prefetch_budget()) : 0;
     if ((rc = finish_rows(d->partial, split, nullptr, d->h, H, d->h, H, B200_NORM_RMS, nw, nullptr, dd.eps, d->xn, H, B,
-                          H, s)))
+                          H, s, nq, nq_bytes)))
       return rc;
     *launches += 7;
   }

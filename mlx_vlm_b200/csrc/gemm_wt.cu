@@ -482,9 +482,10 @@ __global__ void __launch_bounds__(FIN_THREADS)
 finish_rows_kernel(const float* __restrict__ P, int S, const bf16* __restrict__ bias,
                    const bf16* __restrict__ resid, long ldr, bf16* __restrict__ h_out, long ldh,
                    int norm_kind, const bf16* __restrict__ nw, const bf16* __restrict__ nb, float eps,
-                   bf16* __restrict__ xn, long ldx, int T, int N) {
+                   bf16* __restrict__ xn, long ldx, int T, int N, const void* pf, long pf_bytes) {
   __shared__ float red[FIN_THREADS / 32];
   w_pdl_launch();
+  if (pf_bytes > 0 && threadIdx.x == 0) l2_prefetch_span(pf, pf_bytes, blockIdx.x, gridDim.x);
   w_pdl_wait();
   const int t = blockIdx.x;
   const int nv = N >> 2;
@@ -1056,7 +1057,7 @@ int gemm_wt_tuned(const void* X, long ldx, const void* W, const void* bias, cons
 
 int finish_rows(const float* P, int S, const void* bias, const void* resid, long ldr, void* h_out,
                 long ldh, int norm_kind, const void* nw, const void* nb, float eps, void* xn, long ldx,
-                int T, int N, cudaStream_t st) {
+                int T, int N, cudaStream_t st, const void* pf, long pf_bytes) {
   B200_REQUIRE(P && S >= 1 && T > 0 && N > 0 && (N % 4) == 0 && N <= FIN_N_MAX,
                "finish_rows: T=%d N=%d S=%d", T, N, S);
   B200_REQUIRE(norm_kind == B200_NORM_NONE || (xn && (norm_kind != B200_NORM_RMS || nw)),
@@ -1075,11 +1076,11 @@ int finish_rows(const float* P, int S, const void* bias, const void* resid, long
   if (few_rows) {
     B200_CUDA(cudaLaunchKernelEx(&lc, finish_rows_kernel<1024, 2>, P, S, (const bf16*)bias, (const bf16*)resid, ldr,
                                  (bf16*)h_out, ldh, norm_kind, (const bf16*)nw, (const bf16*)nb, eps,
-                                 (bf16*)xn, ldx, T, N));
+                                 (bf16*)xn, ldx, T, N, pf, pf_bytes));
   } else {
     B200_CUDA(cudaLaunchKernelEx(&lc, finish_rows_kernel<256, 8>, P, S, (const bf16*)bias, (const bf16*)resid, ldr,
                                  (bf16*)h_out, ldh, norm_kind, (const bf16*)nw, (const bf16*)nb, eps,
-                                 (bf16*)xn, ldx, T, N));
+                                 (bf16*)xn, ldx, T, N, pf, pf_bytes));
   }
   return B200_OK;
 }
