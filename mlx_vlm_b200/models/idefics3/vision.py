@@ -21,15 +21,26 @@ from ..idefics2.vision import VisionModel as _SiglipTower
 from ..tower_ops import EPI_GELU_TANH, SplitBuf, TowerOps
 
 
+def _arange_f32(start: float, stop: float, step: float) -> np.ndarray:
+    """`mx.arange` on python floats: float32, element i = start + i * step with the product rounded to float32 (the Metal
+    kernel of the device the reference runs on).  The buckets below are decided by `>=` between float32 values and an image
+    that fills the grid makes every comparison a tie, so this rounding is part of the reference's behaviour."""
+    n = max(int(np.ceil((stop - start) / step)), 0)
+    first = np.float32(start)
+    inc = np.float32(np.float32(start + step) - first)
+    return np.array([np.float32(first + np.float32(np.float32(i) * inc)) for i in range(n)], dtype=np.float32)
+
+
 def position_ids(patch_mask: np.ndarray, side: int, seq: int) -> np.ndarray:
     """vision.py:95-137.  patch_mask (B, ph, pw) bool -> (B, seq) int64"""
     m = np.asarray(patch_mask).astype(bool)
-    edges = np.arange(1 / side, 1.0, 1 / side)
+    edges = _arange_f32(1 / side, 1.0, 1 / side)
+    top = np.float32(1.0 - 1e-6)
     ids = np.zeros((m.shape[0], seq), dtype=np.int64)
     for b in range(m.shape[0]):
         rows, cols = max(int(m[b, :, 0].sum()), 1), max(int(m[b, 0, :].sum()), 1)
-        fr = np.clip(np.arange(rows, dtype=np.float32) / rows, 0.0, 1.0 - 1e-6)
-        fc = np.clip(np.arange(cols, dtype=np.float32) / cols, 0.0, 1.0 - 1e-6)
+        fr = np.minimum(np.arange(rows, dtype=np.float32) / np.float32(rows), top)
+        fc = np.minimum(np.arange(cols, dtype=np.float32) / np.float32(cols), top)
         br = (fr[:, None] >= edges[None, :]).sum(axis=1)
         bc = (fc[:, None] >= edges[None, :]).sum(axis=1)
         flat = (br[:, None] * side + bc[None, :]).reshape(-1)

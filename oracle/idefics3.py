@@ -50,6 +50,20 @@ def pixel_shuffle(x: torch.Tensor, s: int) -> torch.Tensor:
     return x.reshape(B, seq // (s * s), E * s * s)
 
 
+def mlx_arange_f32(start: float, stop: float, step: float) -> np.ndarray:
+    """mx.arange(start, stop, step) with python floats: a float32 array of ceil((stop - start) / step) elements, element i
+    = start + i * step evaluated in float32 with the product rounded (mlx's Metal kernel `out[i] = start + i * step`, the
+    device the reference runs on; scalars are the float32 casts of start and of (start + step) - start).  PARITY NOTE: the
+    position buckets below compare k / n against these boundaries with `>=`, and for an image that fills the grid every
+    coordinate is a TIE, so the ids depend on this rounding (float64 boundaries, an FMA, or the CPU backend's running sum
+    each move a few ids by one); which one a given mlx build produces is unpinned — HF's torch.bucketize gives the
+    identity there."""
+    n = max(int(np.ceil((stop - start) / step)), 0)
+    s0 = np.float32(start)
+    st = np.float32(np.float32(start + step) - s0)
+    return np.array([np.float32(s0 + np.float32(np.float32(i) * st)) for i in range(n)], dtype=np.float32)
+
+
 def position_ids_and_mask(patch_mask: Optional[np.ndarray], gh: int, gw: int, side: int):
     """vision.py:95-141 -> (ids (B, gh*gw) int64, mask (B, gh*gw) bool or None)"""
     if patch_mask is None:
@@ -57,13 +71,14 @@ def position_ids_and_mask(patch_mask: Optional[np.ndarray], gh: int, gw: int, si
     m = np.asarray(patch_mask).astype(bool)
     B = m.shape[0]
     seq = gh * gw
-    bounds = np.arange(1 / side, 1.0, 1 / side)
+    bounds = mlx_arange_f32(1 / side, 1.0, 1 / side)
+    hi = np.float32(1.0 - 1e-6)
     ids = np.zeros((B, seq), dtype=np.int64)
     for b in range(B):
         nh = max(int(m[b, :, 0].sum()), 1)
         nw = max(int(m[b, 0, :].sum()), 1)
-        fh = np.clip(np.arange(nh, dtype=np.float32) / nh, 0.0, 1.0 - 1e-6)
-        fw = np.clip(np.arange(nw, dtype=np.float32) / nw, 0.0, 1.0 - 1e-6)
+        fh = np.clip(np.arange(nh, dtype=np.float32) / np.float32(nh), np.float32(0.0), hi)
+        fw = np.clip(np.arange(nw, dtype=np.float32) / np.float32(nw), np.float32(0.0), hi)
         bh = (fh[:, None] >= bounds[None, :]).sum(axis=1)
         bw = (fw[:, None] >= bounds[None, :]).sum(axis=1)
         p = (bh[:, None] * side + bw[None, :]).reshape(-1)

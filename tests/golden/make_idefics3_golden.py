@@ -20,11 +20,22 @@ OUT = os.path.join(HERE, "idefics3_golden.json")
 
 def main():
     mx = make_mx()
-    mx.clip = lambda a, a_min=None, a_max=None: np.clip(a, a_min, a_max)
     mx.tile = np.tile
     mx.flatten = lambda a, start_axis=0, end_axis=-1: np.reshape(
         a, a.shape[:start_axis] + (-1,) + (a.shape[end_axis + 1:] if end_axis != -1 and end_axis + 1 < a.ndim else ()))
-    mx.arange = lambda *a, dtype=None: np.arange(*a, dtype=dtype)
+    def arange(*a, dtype=None):
+        """integers: numpy; python floats: float32 with element i = start + i * step, product rounded to float32 — mlx's
+        Metal `arange` kernel (numpy would compute the boundaries in float64 and break the ties of the `>=` below
+        differently; see oracle/idefics3.py::mlx_arange_f32)"""
+        if dtype is None and any(isinstance(x, float) for x in a):
+            start, stop, step = a
+            n = max(int(np.ceil((stop - start) / step)), 0)
+            s0 = np.float32(start)
+            st = np.float32(np.float32(start + step) - s0)
+            return np.array([np.float32(s0 + np.float32(np.float32(i) * st)) for i in range(n)], dtype=np.float32)
+        return np.arange(*a, dtype=dtype)
+    mx.arange = arange
+    mx.clip = lambda a, a_min=None, a_max=None: np.clip(a, np.float32(a_min), np.float32(a_max)).astype(np.float32)
     mx.zeros = lambda shape, dtype=None: np.zeros(shape, dtype=dtype)
     ns = {"mx": mx, "np": np}
     shuffle, w1 = load(ns, "models/idefics3/idefics3.py", "pixel_shuffle", "Idefics3Connector")
@@ -51,6 +62,18 @@ def main():
         out = embed(self, mx.array(x), mx.array(mask))
         golden["embeddings"].append({"grid": [gh, gw], "valid": [vh, vw], "side": side, "E": E, "table": tolist(table),
                                      "patch_mask": mask[0].astype(int).tolist(), "out": tolist(out[0])})
+    # grids where the float32 rounding of the boundaries decides ties: the Idefics3 (26) and SmolVLM (27) position grids
+    golden["position_ids"] = []
+    for side, vh, vw in ((26, 26, 26), (26, 13, 26), (27, 27, 27), (27, 27, 9), (6, 6, 6)):
+        ids_table = np.arange(side * side, dtype=np.float32)[:, None]
+        mask = np.zeros((1, side, side), dtype=bool)
+        mask[0, :vh, :vw] = True
+        self = types.SimpleNamespace(
+            patch_embedding=lambda x, side=side: np.zeros((x.shape[0], side, side, 1), dtype=np.float32),
+            position_embedding=lambda ids: ids_table[np.asarray(ids)], num_patches_per_side=side)
+        out = embed(self, mx.array(np.zeros((1, side * 14, side * 14, 3), dtype=np.float32)), mx.array(mask))
+        golden["position_ids"].append({"side": side, "valid": [vh, vw],
+                                       "ids_times_mask": np.asarray(out[0, :, 0]).astype(np.int64).tolist()})
     x = np.zeros((1, 3 * 14, 4 * 14, 3), dtype=np.float32)
     self = types.SimpleNamespace(patch_embedding=lambda x: np.zeros((1, 3, 4, E), dtype=np.float32),
                                  position_embedding=lambda ids: table[np.asarray(ids)], num_patches_per_side=side)

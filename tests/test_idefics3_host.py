@@ -46,6 +46,26 @@ def test_position_embeddings_match_reference():
         assert np.array_equal(table0[pid[0]], want)
 
 
+def test_position_ids_where_float32_rounding_decides():
+    """An image that fills the position grid makes every `k / n >= boundary` a tie: the ids then follow the float32
+    arithmetic of `mx.arange` (oracle/idefics3.py::mlx_arange_f32).  Goldens: the reference's source over a stand-in whose
+    float `arange` follows mlx's Metal kernel; oracle and product must agree with them and with each other."""
+    from oracle import idefics3 as O3
+    from mlx_vlm_b200.models.idefics3.vision import position_ids
+    assert len(GOLD["position_ids"]) >= 5
+    for c in GOLD["position_ids"]:
+        side = c["side"]
+        vh, vw = c["valid"]
+        m = np.zeros((1, side, side), dtype=bool)
+        m[0, :vh, :vw] = True
+        ids, mask = O3.position_ids_and_mask(m, side, side, side)
+        assert np.array_equal(ids[0] * mask[0], np.asarray(c["ids_times_mask"]))
+        assert np.array_equal(position_ids(m, side, side * side), ids)
+    # not the identity on a full 26 x 26 grid (HF's torch.bucketize gives the identity there): reproduced, not repaired
+    full = np.ones((1, 26, 26), dtype=bool)
+    assert not np.array_equal(O3.position_ids_and_mask(full, 26, 26, 26)[0][0], np.arange(676))
+
+
 def test_configs_and_alias():
     from mlx_vlm_b200.models import idefics3, smolvlm
     from mlx_vlm_b200.models.idefics3.config import idefics3_8b_config
