@@ -395,14 +395,18 @@ def c3_leg(dev, args):
         step()
     K = max(2, min(args.steps, 5))
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)     # this leg is the power-hungry one (dense tcgen05 work for ~0.1 s per step)
+    sampler.start()
     t0 = time.perf_counter()
-    tw, pf = 0.0, 0.0
+    tw, pf, per_step = 0.0, 0.0, []
     for _ in range(K):
         a, b = step()
         tw += a
         pf += b
+        per_step.append(round(b, 2))
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / K
+    clocks = sampler.stop()
     tw, pf = tw / K, pf / K
     E, I, nh = v.hidden_size, v.intermediate_size, v.num_attention_heads
     L = P + 1
@@ -419,6 +423,7 @@ def c3_leg(dev, args):
                        f"of {B} requests x T={T} ({P} image + {n_text} text tokens), "
                        + ("one prefill call per request" if args.c3_sequential else "all requests in one batched prefill pass"),
            "tower_projector_ms": tw, "lm_prefill_ms": pf, "ms_per_step": tw + pf, "wall_ms_per_step": wall * 1e3,
+           "lm_prefill_ms_per_step": per_step, "clocks": clocks,
            "prefill_img_tokens_per_sec": B * P / ((tw + pf) / 1e3),
            "tower_img_tokens_per_sec": B * P / (tw / 1e3),
            "h2d_bytes_per_step": int(pv_host.numel() * 4),
