@@ -68,6 +68,14 @@ struct b200_engine {
   int* pos_hw_host = nullptr;   // pinned staging of the rot_pos_emb ids (no stream sync per call)
   long pos_hw_host_cap = 0;
   cudaEvent_t pos_ev = nullptr;
+  // (row, position) of every token of a batched prefill: grow-only device buffer + pinned staging, like pos_hw (a
+  // stream-ordered allocation per call made the driver trim / re-map its pool around every call: prefill calls of 85 ms
+  // intermittently took 400-600 ms)
+  int* loc_dev = nullptr;
+  long loc_cap = 0;
+  int* loc_host = nullptr;
+  long loc_host_cap = 0;
+  cudaEvent_t loc_ev = nullptr;
   // captured CUDA graphs of the vision tower / the prefill layers, keyed by everything that is baked
   // into their nodes (shapes, workspace, KV binding): the sequences are ~500 small launches, which
   // the host cannot enqueue as fast as the B200 executes them
@@ -414,6 +422,25 @@ static int v2_upload_pos(b200_engine* e, const std::vector<int>& pos, cudaStream
   memcpy(e->pos_hw_host, pos.data(), n * 4);
   B200_CUDA(cudaMemcpyAsync(e->pos_hw, e->pos_hw_host, n * 4, cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaEventRecord(e->pos_ev, s));
+  return B200_OK;
+}
+
+static int upload_loc(b200_engine* e, const std::vector<int>& loc, cudaStream_t s) {
+  const long n = (long)loc.size();
+  if (!e->loc_ev) B200_CUDA(cudaEventCreateWithFlags(&e->loc_ev, cudaEventDisableTiming));
+  else B200_CUDA(cudaEventSynchronize(e->loc_ev));  // the previous prefill that read the table has finished
+  if (n > e->loc_cap) {
+    if (e->loc_dev) B200_CUDA(cudaFree(e->loc_dev));
+    B200_CUDA(cudaMalloc(&e->loc_dev, n * 4));
+    e->loc_cap = n;
+  }
+  if (n > e->loc_host_cap) {
+    if (e->loc_host) B200_CUDA(cudaFreeHost(e->loc_host));
+    B200_CUDA(cudaMallocHost(&e->loc_host, n * 4));
+    e->loc_host_cap = n;
+  }
+  memcpy(e->loc_host, loc.data(), n * 4);
+  B200_CUDA(cudaMemcpyAsync(e->loc_dev, e->loc_host, n * 4, cudaMemcpyHostToDevice, s));
   return B200_OK;
 }
 
@@ -819,6 +846,9 @@ int b200_engine_destroy(b200_engine* e) {
   if (e->pos_hw) cudaFree(e->pos_hw);
   if (e->pos_hw_host) cudaFreeHost(e->pos_hw_host);
   if (e->pos_ev) cudaEventDestroy(e->pos_ev);
+  if (e->loc_dev) cudaFree(e->loc_dev);
+  if (e->loc_host) cudaFreeHost(e->loc_host);
+  if (e->loc_ev) cudaEventDestroy(e->loc_ev);
   if (e->kvref) cudaFree(e->kvref);
   if (e->kvref_host) cudaFreeHost(e->kvref_host);
   if (e->kvref_ev) cudaEventDestroy(e->kvref_ev);
@@ -1112,7 +1142,7 @@ int b200_engine_prefill_batch(b200_engine* e, const void* embeds, const int* pos
   bf16* h = (bf16*)p;
   p += 2 * align256(T * H * 2) + align256(T * QKV * 2) + align256(T * QH * 2) + align256(T * 2 * I * 2) +
        align256(T * I * 2);
-  int* pos_stage = (int*)p;   // 3 * T ints; the tokens' (row, position) table gets a stream-ordered allocation
+  int* pos_stage = (int*)p;   // 3 * T ints; the tokens' (row, position) table lives in e->loc_dev
   B200_CUDA(cudaMemcpyAsync(h, embeds, (size_t)T * H * 2, cudaMemcpyDeviceToDevice, s));
   B200_CUDA(cudaMemcpyAsync(pos_stage, pos3, (size_t)3 * T * 4, cudaMemcpyDeviceToDevice, s));
   std::vector<int> loc(2 * (size_t)T, -1);   // padding tokens: row -1 = no cache write
@@ -1121,12 +1151,9 @@ int b200_engine_prefill_batch(b200_engine* e, const void* embeds, const int* pos
       loc[2 * ((size_t)segs[g].off + t)] = segs[g].row;
       loc[2 * ((size_t)segs[g].off + t) + 1] = t;
     }
-  int* loc_dev = nullptr;
-  B200_CUDA(cudaMallocAsync((void**)&loc_dev, loc.size() * 4, s));
-  B200_CUDA(cudaMemcpyAsync(loc_dev, loc.data(), loc.size() * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA(cudaStreamSynchronize(s));   // `loc` is pageable host memory: the copy must finish before it goes away
-  rc = prefill_layers_v2_body(e, pos_stage, (int)T, 0, nullptr, s, segs.data(), n_seq, loc_dev);
-  cudaFreeAsync(loc_dev, s);
+  if ((rc = upload_loc(e, loc, s))) return rc;
+  rc = prefill_layers_v2_body(e, pos_stage, (int)T, 0, nullptr, s, segs.data(), n_seq, e->loc_dev);
+  B200_CUDA(cudaEventRecord(e->loc_ev, s));   // the table (and its staging copy) may be rewritten after this point
   if (rc) return rc;
   const DecodeDims d = e->dims();
   if (e->prepared_cap != e->kv_cap || e->prepared_cluster != e->attn_cluster) {
