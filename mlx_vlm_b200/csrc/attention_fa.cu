@@ -38,6 +38,8 @@ struct FaParams {
   long o_ts;
   int n_heads, n_kv, hd, hdp, Lq, S, causal;
   int q0, k0;  // token offsets of this segment inside the tensors the maps describe
+  const int4* segs;  // optional [gridDim.z]: (q0, Lq, k0, S) of segment blockIdx.z — several independent sequences of one
+                     // concatenated batch in ONE launch (the tail wave of a 160-CTA launch per sequence idles half the SMs)
 };
 
 struct FaBars {
@@ -132,7 +134,13 @@ __device__ __forceinline__ float f_ex2(float x) {
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+                    const __grid_constant__ CUtensorMap tmV, const FaParams p_in) {
+  FaParams p = p_in;
+  if (p_in.segs) {   // static table (written before the producing kernels ran): safe to read ahead of griddepcontrol.wait
+    const int4 sg = __ldg(p_in.segs + blockIdx.z);
+    p.q0 = sg.x; p.Lq = sg.y; p.k0 = sg.z; p.S = sg.w;
+    if ((int)blockIdx.x * FA_TQ >= p.Lq) return;   // the grid is sized for the longest segment
+  }
   extern __shared__ uint8_t fa_smem_raw[];
   __shared__ FaBars bars;
   __shared__ uint32_t tmem_slot;
@@ -456,9 +464,10 @@ bool attention_fa_supported(const void* q, long q_ts, long q_hs, const void* k, 
 // [k0, k0+S) (one vision segment, or the whole prompt); out row t is written at out + t*o_ts.
 int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs, const void* vt,
                  long vt_hs, long vt_ds, void* out, long o_ts, int n_heads, int n_kv, int hd, int Lq, int S,
-                 int causal, cudaStream_t st, int q0, int q_tot, int k0, int k_tot) {
+                 int causal, cudaStream_t st, int q0, int q_tot, int k0, int k_tot, const void* segs, int n_seg) {
   if (q_tot <= 0) q_tot = q0 + Lq;
   if (k_tot <= 0) k_tot = k0 + S;
+  B200_REQUIRE(!segs || n_seg > 0, "attention_fa: segment table without segments");
   B200_REQUIRE(attention_fa_supported(q, q_ts, q_hs, k, k_ts, k_hs, vt, vt_hs, vt_ds, out, o_ts, hd),
                "attention_fa: unsupported layout (hd=%d)", hd);
   B200_REQUIRE(Lq > 0 && S > 0 && n_heads % n_kv == 0, "attention_fa: bad shape");
@@ -479,8 +488,9 @@ int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, 
   FaParams p;
   p.out = (bf16*)out; p.o_ts = o_ts; p.n_heads = n_heads; p.n_kv = n_kv; p.hd = hd; p.hdp = hdp;
   p.Lq = Lq; p.S = S; p.causal = causal; p.q0 = q0; p.k0 = k0;
+  p.segs = (const int4*)segs;
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(cdiv(Lq, FA_TQ), n_heads);
+  lc.gridDim = dim3(cdiv(Lq, FA_TQ), n_heads, segs ? n_seg : 1);
   lc.blockDim = dim3(FA_THREADS);
   lc.dynamicSmemBytes = smem;
   lc.stream = st;
@@ -499,5 +509,5 @@ extern "C" int b200_attention_fa(const void* q, long q_ts, long q_hs, const void
                                  const void* vt, long vt_hs, long vt_ds, void* out, long o_ts, int n_heads,
                                  int n_kv, int hd, int Lq, int S, int causal, void* stream) {
   return b200::attention_fa(q, q_ts, q_hs, k, k_ts, k_hs, vt, vt_hs, vt_ds, out, o_ts, n_heads, n_kv, hd, Lq, S,
-                            causal, (cudaStream_t)stream, 0, Lq, 0, S);
+                            causal, (cudaStream_t)stream, 0, Lq, 0, S, nullptr, 0);
 }

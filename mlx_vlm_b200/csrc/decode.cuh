@@ -168,7 +168,8 @@ bool attention_fa_supported(const void* q, long q_ts, long q_hs, const void* k, 
                             const void* vt, long vt_hs, long vt_ds, const void* out, long o_ts, int hd);
 int attention_fa(const void* q, long q_ts, long q_hs, const void* k, long k_ts, long k_hs, const void* vt,
                  long vt_hs, long vt_ds, void* out, long o_ts, int n_heads, int n_kv, int hd, int Lq, int S,
-                 int causal, cudaStream_t st, int q0 = 0, int q_tot = 0, int k0 = 0, int k_tot = 0);
+                 int causal, cudaStream_t st, int q0 = 0, int q_tot = 0, int k0 = 0, int k_tot = 0,
+                 const void* segs = nullptr, int n_seg = 0);   // segs: device int4 (q0, Lq, k0, S) per segment; Lq / S = the longest
 int swiglu(const void* gu, void* out, int rows, int inter, cudaStream_t st);
 int embed_merge(const int* ids, int B, int T, const void* table, int hidden, const void* feats,
                 int n_feats, int image_token, int video_token, void* out, int* src_out,

@@ -706,12 +706,13 @@ static int prefill_layers_v2_body(b200_engine* e, const int* pos3, int T, int ct
       if ((rc = mrope_kv_write(qkv, pos3, e->lm_inv_freq, e->axis_sel, e->kptr(l, 0), e->vptr(l, 0), T, 0, e->kv_cap,
                                c.n_heads, c.n_kv_heads, hd, s, scale_bf, vt, t_ld, nullptr, l, kws, tok_loc, row_stride)))
         return rc;
-      for (int g = 0; g < n_seg; ++g) {
-        if ((rc = attention_fa(qkv, QKV, hd, kws, hd, (long)T * hd, vt, (long)hd * t_ld, t_ld, att, QH, c.n_heads,
-                               c.n_kv_heads, hd, segs[g].T, segs[g].T, 1, s, segs[g].off, T, segs[g].off, T)))
-          return rc;
-      }
-      e->launches += 1 + n_seg;
+      // all sequences in ONE launch: the (q0, Lq, k0, S) table follows the (row, position) table in `tok_loc`
+      int longest = 0;
+      for (int g = 0; g < n_seg; ++g) longest = segs[g].T > longest ? segs[g].T : longest;
+      if ((rc = attention_fa(qkv, QKV, hd, kws, hd, (long)T * hd, vt, (long)hd * t_ld, t_ld, att, QH, c.n_heads,
+                             c.n_kv_heads, hd, longest, longest, 1, s, 0, T, 0, T, (const int*)tok_loc + 2L * T, n_seg)))
+        return rc;
+      e->launches += 2;
     } else {
     if ((rc = mrope_kv_write(qkv, pos3, e->lm_inv_freq, e->axis_sel, kc, vc, T, ctx0, e->kv_cap, c.n_heads,
                              c.n_kv_heads, hd, s, fa ? scale_bf : 0.f, fa ? vt : nullptr, t_ld,
@@ -1151,6 +1152,8 @@ int b200_engine_prefill_batch(b200_engine* e, const void* embeds, const int* pos
       loc[2 * ((size_t)segs[g].off + t)] = segs[g].row;
       loc[2 * ((size_t)segs[g].off + t) + 1] = t;
     }
+  for (int g = 0; g < n_seq; ++g)   // attention segments (q0, Lq, k0, S), 16-byte aligned behind the table (T % 8 == 0)
+    for (int v : {segs[g].off, segs[g].T, segs[g].off, segs[g].T}) loc.push_back(v);
   if ((rc = upload_loc(e, loc, s))) return rc;
   rc = prefill_layers_v2_body(e, pos_stage, (int)T, 0, nullptr, s, segs.data(), n_seq, e->loc_dev);
   B200_CUDA(cudaEventRecord(e->loc_ev, s));   // the table (and its staging copy) may be rewritten after this point
