@@ -5,15 +5,12 @@ tower and the connector is Idefics2's (models/idefics2/idefics2.py); SmolVLM is 
 (models/smolvlm)."""
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
-import numpy as np
 import torch
 
-from ... import _native as N
 from ..idefics2.idefics2 import Model as _Idefics2Model
 from ..idefics2.idefics2 import patch_attention_mask, real_image_indices  # noqa: F401  (same rules, :104-140)
-from ..qwen2_vl.language import _np
 from ..tower_ops import SplitBuf, TowerOps
 from .config import ModelConfig
 from .language import LanguageModel

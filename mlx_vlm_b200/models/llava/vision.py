@@ -4,11 +4,11 @@ llava.py:61-63).  GEMMs run on the tensor cores over split operands (models/towe
 fp32 kernels (csrc/tower_f32.cu)."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 
-from ..tower_ops import EPI_GELU_FAST, SplitBuf, TowerOps, pad64
+from ..tower_ops import EPI_GELU_FAST, SplitBuf, TowerOps
 from .config import VisionConfig
 
 

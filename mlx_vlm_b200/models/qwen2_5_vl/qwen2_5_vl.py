@@ -4,7 +4,7 @@ models/qwen2_vl/qwen2_vl.py); the tower (RMSNorm / SwiGLU blocks, windowed atten
 the decoder engine is created without its built-in Qwen2-VL tower."""
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 

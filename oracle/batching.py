@@ -18,7 +18,7 @@ acceptance oracle for the round-2 batched kernel (padding positions are dead wei
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import numpy as np
 import torch

@@ -18,7 +18,7 @@ floating-point rounding points are those of oracle/mlx_semantics.py (unpinned at
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch
