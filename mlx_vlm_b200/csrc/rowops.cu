@@ -212,6 +212,115 @@ __global__ void mrope_kv_write_kernel(bf16* __restrict__ qkv, const int* __restr
   }
 }
 
+// The same operation, tiled (head_dim a multiple of 16): a CTA takes 32 tokens x a group of head slots; thread (token,
+// chunk of 8 rotary pairs) computes its 8 cos / sin ONCE and re-uses them for every head of the group, all loads and
+// stores are 16-byte vectors, and V^T goes through a shared-memory tile so that its stores are contiguous along the
+// token axis.  Identical arithmetic, element for element, to the scalar kernel above (which evaluated cosf / sinf per
+// element and wrote V^T with 2-byte stores a row apart: 329 us per layer at T = 4864 on the Llama-7B geometry = 13 % of
+// the batched C3 prefill, profiles/r2_launches_c3_prefill_ncu.txt).  grid (ceil(T / 32), slot groups), 256 threads.
+__global__ void __launch_bounds__(256)
+mrope_kv_write_tiled_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos3, const float* __restrict__ inv_freq,
+                            const int* __restrict__ axis_sel, bf16* __restrict__ kc, bf16* __restrict__ vc, int T, int ctx0,
+                            int cap, int n_heads, int n_kv, int hd, float q_scale, bf16* __restrict__ vt, int t_ld,
+                            const KvRef* __restrict__ ref, int layer, bf16* __restrict__ kws,
+                            const int2* __restrict__ tok_loc, long row_stride, int slots_per_cta) {
+  pdl_prologue();
+  if (ref) {
+    kc = ref->k0 + (long)layer * ref->layer_stride;
+    vc = kc + ref->v_off;
+    cap = ref->cap;
+  }
+  __shared__ bf16 tile[32][136];
+  const int half = hd >> 1, nc = half >> 3, nv = hd >> 3;
+  const int slots = n_heads + 2 * n_kv;
+  const long row_elems = (long)slots * hd;
+  const int t0 = blockIdx.x * 32;
+  const int tl = threadIdx.x / nc, c = threadIdx.x % nc;
+  const int t = t0 + tl;
+  const bool act = threadIdx.x < 32 * nc && t < T;
+  float cs[8], sn[8];
+  int2 loc = make_int2(-1, 0);
+  if (act) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = c * 8 + u;
+      const float ang = (float)pos3[axis_sel[j] * T + t] * inv_freq[j];
+      cs[u] = rbf(cosf(ang));
+      sn[u] = rbf(sinf(ang));
+    }
+    loc = tok_loc ? tok_loc[t] : make_int2(0, ctx0 + t);
+  }
+  const int s_begin = blockIdx.y * slots_per_cta;
+  const int s_end = min(slots, s_begin + slots_per_cta);
+  for (int slot = s_begin; slot < s_end; ++slot) {
+    if (slot < n_heads + n_kv) {   // q or k head: rotate
+      if (!act) continue;
+      bf16* base = qkv + (long)t * row_elems + (long)slot * hd;
+      float x1[8], x2[8], o1[8], o2[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + c * 8), x1);
+      unpack8(*reinterpret_cast<const uint4*>(base + half + c * 8), x2);
+      const bool is_q = slot < n_heads;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        o1[u] = rbf(rbf(x1[u] * cs[u]) + rbf((-x2[u]) * sn[u]));
+        o2[u] = rbf(rbf(x2[u] * cs[u]) + rbf(x1[u] * sn[u]));
+        if (is_q && q_scale != 0.f) {   // qs = bf16(q * bf16(scale)) of the SDPA (base.py:305-373)
+          o1[u] *= q_scale;
+          o2[u] *= q_scale;
+        }
+      }
+      uint4 w1, w2;
+      w1.x = pack2(o1[0], o1[1]); w1.y = pack2(o1[2], o1[3]); w1.z = pack2(o1[4], o1[5]); w1.w = pack2(o1[6], o1[7]);
+      w2.x = pack2(o2[0], o2[1]); w2.y = pack2(o2[2], o2[3]); w2.z = pack2(o2[4], o2[5]); w2.w = pack2(o2[6], o2[7]);
+      if (is_q) {
+        *reinterpret_cast<uint4*>(base + c * 8) = w1;
+        *reinterpret_cast<uint4*>(base + half + c * 8) = w2;
+      } else {
+        const int kvh = slot - n_heads;
+        if (loc.x >= 0) {   // (row -1: a padding token of a batched prefill)
+          bf16* dst = kc + (long)loc.x * row_stride + ((long)kvh * cap + loc.y) * hd;
+          *reinterpret_cast<uint4*>(dst + c * 8) = w1;
+          *reinterpret_cast<uint4*>(dst + half + c * 8) = w2;
+        }
+        if (kws) {
+          bf16* d2 = kws + ((long)kvh * T + t) * hd;
+          *reinterpret_cast<uint4*>(d2 + c * 8) = w1;
+          *reinterpret_cast<uint4*>(d2 + half + c * 8) = w2;
+        }
+      }
+    } else {   // V head: copy into the cache, and transposed into V^T [kv head][dim][token]
+      const int kvh = slot - n_heads - n_kv;
+      for (int idx = threadIdx.x; idx < 32 * nv; idx += blockDim.x) {
+        const int tl2 = idx / nv, c2 = idx % nv;
+        const int t2 = t0 + tl2;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (t2 < T) {
+          v = *reinterpret_cast<const uint4*>(qkv + (long)t2 * row_elems + (long)slot * hd + c2 * 8);
+          const int2 l2 = tok_loc ? tok_loc[t2] : make_int2(0, ctx0 + t2);
+          if (l2.x >= 0)
+            *reinterpret_cast<uint4*>(vc + (long)l2.x * row_stride + ((long)kvh * cap + l2.y) * hd + c2 * 8) = v;
+        }
+        *reinterpret_cast<uint4*>(&tile[tl2][c2 * 8]) = v;
+      }
+      __syncthreads();
+      if (vt) {
+        for (int idx = threadIdx.x; idx < hd * 4; idx += blockDim.x) {
+          const int d = idx >> 2, ch = idx & 3;
+          if (t0 + ch * 8 >= t_ld) continue;
+          unsigned short e[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) e[u] = __bfloat16_as_ushort(tile[ch * 8 + u][d]);
+          uint4 o;
+          o.x = e[0] | ((uint32_t)e[1] << 16); o.y = e[2] | ((uint32_t)e[3] << 16);
+          o.z = e[4] | ((uint32_t)e[5] << 16); o.w = e[6] | ((uint32_t)e[7] << 16);
+          *reinterpret_cast<uint4*>(vt + ((long)kvh * hd + d) * t_ld + t0 + ch * 8) = o;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 __global__ void swiglu_kernel(const bf16* __restrict__ gu, bf16* __restrict__ out, int rows,
                               int inter) {
@@ -355,6 +464,18 @@ int mrope_kv_write(void* qkv, const int* pos3, const float* inv_freq, const int*
   B200_REQUIRE(T > 0 && ctx0 >= 0 && (ref || tok_loc || ctx0 + T <= cap), "mrope_kv_write: T=%d ctx0=%d cap=%d", T,
                ctx0, cap);
   B200_REQUIRE(!vt || t_ld >= T, "mrope_kv_write: V^T pitch %d < T %d", t_ld, T);
+  static const bool scalar_only = getenv("B200_MROPE_SCALAR") != nullptr;   // A/B and fallback
+  if (!scalar_only && (hd % 16) == 0 && hd <= 128 && (!vt || (t_ld % 8) == 0)) {
+    const int slots = n_heads + 2 * n_kv, tiles = (T + 31) / 32;
+    int groups = (4 * 148 + tiles - 1) / tiles;          // about four waves of CTAs
+    if (groups > slots) groups = slots;
+    if (groups < 1) groups = 1;
+    const int per = (slots + groups - 1) / groups;
+    B200_CUDA(launch_pdl(mrope_kv_write_tiled_kernel, dim3(tiles, (slots + per - 1) / per), dim3(256), 0, st, (bf16*)qkv,
+                         pos3, inv_freq, axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd, q_scale, (bf16*)vt,
+                         t_ld, ref, layer, (bf16*)kws, (const int2*)tok_loc, row_stride, per));
+    return B200_OK;
+  }
   const long total = (long)T * (n_heads + 2 * n_kv) * (hd / 2);
   B200_CUDA(launch_pdl(mrope_kv_write_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, (bf16*)qkv, pos3, inv_freq,
                        axis_sel, (bf16*)kc, (bf16*)vc, T, ctx0, cap, n_heads, n_kv, hd, q_scale, (bf16*)vt, t_ld, ref,
