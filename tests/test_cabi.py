@@ -27,6 +27,25 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert isinstance(lib.b200_last_error(), bytes)
 
 
+def test_ctypes_signatures_have_the_arity_of_the_header():
+    """every declaration of include/b200vlm.h and its ctypes signature in _native.py take the same number of arguments
+    (a drifted binding would pass garbage through the C ABI without any error)"""
+    from mlx_vlm_b200 import _native as N
+    src = open(os.path.join(ROOT, "include", "b200vlm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    decls = re.findall(r"\b(b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(decls) >= 60
+    seen = set()
+    for name, args in decls:
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert name in N.SIGNATURES, name
+        assert len(N.SIGNATURES[name][1]) == n, f"{name}: header has {n} arguments, _native.py {len(N.SIGNATURES[name][1])}"
+        seen.add(name)
+    assert seen == set(N.SIGNATURES), sorted(set(N.SIGNATURES) ^ seen)
+
+
 def test_no_oracle_import_in_product():
     """the product path may not import or execute anything under oracle/"""
     pkg = os.path.join(ROOT, "mlx_vlm_b200")
