@@ -27,9 +27,10 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert isinstance(lib.b200_last_error(), bytes)
 
 
-def test_ctypes_signatures_have_the_arity_of_the_header():
+def test_ctypes_signatures_match_the_header():
     """every declaration of include/b200vlm.h and its ctypes signature in _native.py take the same number of arguments
     (a drifted binding would pass garbage through the C ABI without any error)"""
+    import ctypes as C
     from mlx_vlm_b200 import _native as N
     src = open(os.path.join(ROOT, "include", "b200vlm.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
@@ -41,7 +42,16 @@ def test_ctypes_signatures_have_the_arity_of_the_header():
         args = " ".join(args.split())
         n = 0 if args in ("", "void") else args.count(",") + 1
         assert name in N.SIGNATURES, name
-        assert len(N.SIGNATURES[name][1]) == n, f"{name}: header has {n} arguments, _native.py {len(N.SIGNATURES[name][1])}"
+        sig = N.SIGNATURES[name][1]
+        assert len(sig) == n, f"{name}: header has {n} arguments, _native.py {len(sig)}"
+        for i, (decl, ct) in enumerate(zip(args.split(",") if n else [], sig)):   # and the same kind, argument by argument
+            decl = decl.strip()
+            kind = "ptr" if "*" in decl else " ".join(decl.split()[:-1])
+            want = {"ptr": None, "int": C.c_int, "unsigned": C.c_uint, "long": C.c_long, "float": C.c_float}[kind]
+            if want is None:
+                assert ct in (C.c_void_p, C.c_char_p) or issubclass(ct, C._Pointer), f"{name} arg {i}: `{decl}` bound as {ct}"
+            else:
+                assert ct is want, f"{name} arg {i}: `{decl}` bound as {ct}"
         seen.add(name)
     assert seen == set(N.SIGNATURES), sorted(set(N.SIGNATURES) ^ seen)
 
